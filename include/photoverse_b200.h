@@ -1,0 +1,110 @@
+/* photoverse_b200.h -- C ABI of libphotoverse_b200.so (sm_100a only).
+ *
+ * B200-native replacement for the arithmetic of PhotoVerse's dual-branch conditioning hot path:
+ *   reference  models/attention_processor.py:245-435  PhotoVerseAttnProcessor2_0.__call__
+ *   reference  models/adapters.py:30-44               PhotoVerseAdapter.forward
+ *   reference  models/unet.py:38-47                   get_visual_cross_attention_values_norm (side output)
+ *   dependency peft 0.10.0 lora.Linear.forward        (LoRA on attn2.to_q/to_k/to_v, train.py:348-354)
+ *
+ * The reference has no FFI (it is pure PyTorch); these entry points are what a binding for this path
+ * binds instead of the library calls listed in SURVEY.md section 2.2 (P1-P15, A1-A9).  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library allocates nothing
+ *     persistent except cached TMA descriptors; all tensors are dense row-major unless strides are given
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), perform no host sync and
+ *     no allocation, and are CUDA-graph capturable
+ *   - return value: PV_OK or an error code; pv_last_error() gives the message; nothing throws
+ *   - pv_dtype selects the arithmetic path:
+ *        PV_BF16  bf16 storage, tcgen05 tensor-core MMAs with fp32 accumulation in TMEM (throughput mode)
+ *        PV_F32   fp32 storage, fp32 FFMA arithmetic (parity mode: <= 1e-4 of the fp32 reference)
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns PV_ERR_CUDA
+ */
+#ifndef PHOTOVERSE_B200_H_
+#define PHOTOVERSE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PV_ABI_VERSION 1
+
+enum { PV_OK = 0, PV_ERR_INVALID = 1, PV_ERR_CUDA = 2, PV_ERR_UNSUPPORTED = 3 };
+typedef enum { PV_F32 = 0, PV_BF16 = 1 } pv_dtype;
+
+/* Keys are zero-padded to this many rows per (sample, head) in the packed K/V tiles. */
+#define PV_KEYS_PAD 96
+/* Maximum text / image tokens the fused kernel supports: Lt + Li <= PV_KEYS_PAD. */
+
+int pv_version(void);
+const char* pv_last_error(void);
+/* Number of kernels this library has launched since it was loaded (bench.py: "gpu_launches"). */
+unsigned long long pv_launch_count(void);
+/* Runtime switches for A/B testing kernel variants (name -> int). Unknown names return PV_ERR_INVALID. */
+int pv_set_option(const char* name, int value);
+
+/* ---- weights ---------------------------------------------------------------------------------------
+ * W_eff[out,in] = W[out,in] + scaling * B[out,r] * A[r,in]   (peft lora.Linear merged form; r == 0 -> cast)
+ * fp32 masters in, `out_dt` out.  Replaces the two skinny GEMMs + scale + add per projection
+ * for every call in which the weights did not change.                                                   */
+int pv_pack_weight(pv_dtype out_dt, const float* W, const float* lora_A, const float* lora_B, float scaling,
+                   void* W_eff, int out_features, int in_features, int r, void* stream);
+
+/* ---- generic projection -----------------------------------------------------------------------------
+ * D[b] = A[b] * W[b]^T + bias[b]     A:[batch,M,K] (row stride lda, batch stride strideA, elements)
+ *                                    W:[batch,N,K] (ldw, strideW; strideW == 0 -> one shared weight)
+ *                                    bias fp32 [batch,N] (strideBias) or NULL;  D:[batch,M,N] (ldd, strideD)
+ * dt is the type of A and W; out_dt the type of D.  PV_BF16: K % 8 == 0 and 16-byte aligned rows.
+ * Replaces nn.Linear (attention_processor.py:297,304,305,392,393,423; adapters.py:14-28).               */
+int pv_linear_fwd(pv_dtype dt, pv_dtype out_dt, const void* A, const void* W, const float* bias, void* D,
+                  int64_t M, int64_t N, int64_t K, int64_t batch, int64_t lda, int64_t ldw, int64_t ldd,
+                  int64_t strideA, int64_t strideW, int64_t strideBias, int64_t strideD, void* stream);
+
+/* ---- K/V projection + pack (attention_processor.py:304-313, 392-397) --------------------------------
+ * text:[B,Lt,Dc]  img:[B,Li,Dc]  (dt)      Wkv_text:[2C,Dc] = [to_k_eff ; to_v_eff]   Wkv_img:[2C,Dc] = [to_k_ip ; to_v_ip]
+ * kv_text_ws:[B*Lt,2C] fp32, kv_img_ws:[B*Li,2C] fp32   (outputs; also saved for backward)
+ * Kp, Vp: packed per-(sample,head) key / value tiles consumed by pv_dual_attn_fwd:
+ *     PV_BF16: Kp[b][h] = UMMA K-major core-matrix image of [PV_KEYS_PAD x d_pad], Vp[b][h] = image of V^T
+ *              [d_pad x PV_KEYS_PAD]; d_pad = round_up(C/H,16); pv_kv_tile_bytes() each
+ *     PV_F32 : Kp, Vp = [B,H,Lt+Li,d] fp32
+ * v_ip_norm:[B,H,Li] fp32 = ||V_img||_2 over head_dim  (the processor's `to_v_ip_norm` side output)     */
+int64_t pv_kv_tile_bytes(pv_dtype dt, int C, int H, int Lt, int Li);
+int pv_kv_pack_fwd(pv_dtype dt, const void* text, const void* img, const void* Wkv_text, const void* Wkv_img,
+                   float* kv_text_ws, float* kv_img_ws, void* Kp, void* Vp, float* v_ip_norm, int B, int Lt, int Li,
+                   int Dc, int C, int H, void* stream);
+
+/* ---- the dual-branch cross-attention (attention_processor.py:297, 307-322, 400-425) -----------------
+ * Y = (w_text * softmax(Q K_t^T / sqrt(d)) V_t + w_img * softmax(Q K_i^T / sqrt(d)) V_i) Wo^T + bo,  Q = X Wq^T
+ * X,Y:[B,S,C] (dt)   Wq,Wo:[C,C] (dt, Wq already LoRA-merged)   bo:[C] fp32   Kp,Vp from pv_kv_pack_fwd
+ * ws_q : PV_F32 only, [B,S,C] fp32 scratch for Q (may be NULL for PV_BF16: Q never leaves the SM)
+ * ws_o : [B,S,C] (dt) attention output before the out projection (saved for backward)
+ * stats: optional [B,H,S,4] fp32 = (max_text, sum_text, max_img, sum_img) of the scaled logits, for backward
+ * PV_BF16 path: ONE fused tcgen05 kernel does Q-projection -> QK^T over the concatenated keys -> per-segment
+ * softmax with the branch weights folded in -> ONE PV contraction; a second tcgen05 GEMM applies Wo + bias.
+ * Supported head dims: 40, 80, 160 (C = 320, 640, 1280 with H = 8); Lt + Li <= PV_KEYS_PAD; Li >= 1.          */
+int pv_dual_attn_fwd(pv_dtype dt, const void* X, const void* Wq, const void* Kp, const void* Vp, const void* Wo,
+                     const float* bo, void* Y, float* ws_q, void* ws_o, float* stats, int B, int S, int C, int H,
+                     int Lt, int Li, float w_text, float w_img, void* stream);
+
+/* ---- adapter epilogues (adapters.py:15-16,18-19: LayerNorm(1024) -> LeakyReLU(0.01)) ----------------
+ * y = leaky_relu(layer_norm(x) * gamma + beta); x:[rows,cols] fp32 (row stride ldx), y:[rows,cols] out_dt
+ * (row stride ldy); cols % 128 == 0, cols <= 4096.  Optional mean / rstd [rows] fp32 saved for backward.
+ * gamma/beta:[groups,cols]; row i uses group i / rows_per_group (rows_per_group <= 0: one shared gamma/beta) --
+ * the T token heads of an adapter are normalised in one launch.
+ * One warp per row, 16-byte vector loads, warp-shuffle reductions.                                        */
+int pv_ln_lrelu_fwd(pv_dtype out_dt, const float* x, const float* gamma, const float* beta, void* y,
+                    float* save_mean, float* save_rstd, int64_t rows, int cols, int64_t ldx, int64_t ldy,
+                    int64_t rows_per_group, float eps, float slope, void* stream);
+/* y[g, :] = mean over the P rows of group g: x:[groups,P,cols] (in_dt) -> y:[groups,cols] (out_dt, row stride ldy)
+ * (adapters.py:36,41 `.mean(dim=1, keepdim=True)` over the 256 patch tokens, commuted in front of the last
+ * Linear: mean(L3(h)) == L3(mean(h))).                                                       */
+int pv_group_mean_fwd(pv_dtype in_dt, pv_dtype out_dt, const void* x, void* y, int64_t groups, int P, int cols,
+                      int64_t ldy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHOTOVERSE_B200_H_ */

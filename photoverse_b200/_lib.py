@@ -1,0 +1,83 @@
+"""ctypes binding of libphotoverse_b200.so (the C ABI declared in include/photoverse_b200.h).
+
+There is deliberately no fallback: if the shared object is missing or a call fails, we raise.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphotoverse_b200.so")
+
+PV_F32 = 0
+PV_BF16 = 1
+PV_KEYS_PAD = 96
+
+
+class PhotoverseB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGNATURES = {
+    "pv_version": (c_int, []),
+    "pv_last_error": (c_char_p, []),
+    "pv_launch_count": (c_ulonglong, []),
+    "pv_set_option": (c_int, [c_char_p, c_int]),
+    "pv_pack_weight": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pv_linear_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 11 + [c_void_p]),
+    "pv_kv_tile_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    "pv_kv_pack_fwd": (c_int, [c_int] + [c_void_p] * 9 + [c_int] * 6 + [c_void_p]),
+    "pv_dual_attn_fwd": (c_int, [c_int] + [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p]),
+    "pv_ln_lrelu_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
+    "pv_group_mean_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),
+    "pv_dual_attn_bwd": (c_int, [c_int] + [c_void_p] * 14 + [c_int] * 6 + [c_float, c_float, c_void_p]),
+    "pv_kv_pack_bwd": (c_int, [c_int] + [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
+    "pv_linear_bwd_input": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p] + [c_int64] * 10 + [c_void_p]),
+    "pv_linear_bwd_weight": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 11 + [c_int, c_void_p]),
+    "pv_ln_lrelu_bwd": (c_int, [c_void_p] * 8 + [c_int64, c_int, c_float, c_void_p]),
+    "pv_group_mean_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+}
+
+# symbols every build must export (the rest are added as later ABI revisions land)
+REQUIRED_SYMBOLS = ["pv_version", "pv_last_error", "pv_launch_count", "pv_set_option", "pv_pack_weight",
+                    "pv_linear_fwd", "pv_kv_tile_bytes", "pv_kv_pack_fwd", "pv_dual_attn_fwd", "pv_ln_lrelu_fwd",
+                    "pv_group_mean_fwd"]
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the native library.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PhotoverseB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m photoverse_b200.build` "
+                "(photoverse_b200 has no CPU / PyTorch fallback)")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            try:
+                fn = getattr(l, name)
+            except AttributeError:
+                if name in REQUIRED_SYMBOLS:
+                    raise PhotoverseB200Error(f"{LIB_PATH} does not export {name}")
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().pv_last_error()
+        raise PhotoverseB200Error(f"{what or 'photoverse_b200 call'} failed (code {rc}): "
+                                  f"{msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(lib().pv_launch_count())
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().pv_set_option(name.encode(), int(value)), f"pv_set_option({name})")

@@ -1,0 +1,227 @@
+// photoverse_b200 -- the C ABI (include/photoverse_b200.h): argument checking, TMA descriptor encoding,
+// dispatch between the bf16 tcgen05 path and the fp32 parity path.  No CPU fallback anywhere.
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "pv_host.h"
+#include "../../include/photoverse_b200.h"
+
+namespace pv {
+
+// ---- forward declarations of the launchers -------------------------------------------------------
+int gemm_bf16(const void* A, const void* W, const float* bias, void* D, bool out_f32, long long M, long long N,
+              long long K, long long batch, long long lda, long long ldw, long long ldd, long long strideA,
+              long long strideW, long long strideBias, long long strideD, cudaStream_t stream);
+int gemm_f32(const float* A, const float* W, const float* bias, float* D, long long M, long long N, long long K,
+             long long batch, long long lda, long long ldw, long long ldd, long long strideA, long long strideW,
+             long long strideBias, long long strideD, cudaStream_t stream);
+int dual_attn_core_bf16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
+                        int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
+int dual_attn_core_f32(const float* Q, const float* Kp, const float* Vp, float* O, float* stats, int B, int S, int C,
+                       int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
+int64_t attn_kv_tile_bytes(int d);
+int pack_weight(bool out_bf16, const float* W, const float* A, const float* Bm, float scaling, void* out, int out_f,
+                int in_f, int r, cudaStream_t stream);
+int kv_pack(bool bf16, const float* kv_text, const float* kv_img, void* Kp, void* Vp, float* v_ip_norm, int B, int Lt,
+            int Li, int C, int H, cudaStream_t stream);
+int ln_lrelu(bool out_bf16, const float* x, const float* gamma, const float* beta, void* y, float* save_mean,
+             float* save_rstd, long long rows, int cols, long long ldx, long long ldy, long long rows_per_group,
+             float eps, float slope, cudaStream_t stream);
+int group_mean(bool in_bf16, bool out_bf16, const void* x, void* y, long long groups, int P, int cols, long long ldy,
+               cudaStream_t stream);
+
+// ---- globals ---------------------------------------------------------------------------------------
+std::atomic<unsigned long long> g_launches{0};
+int g_opt_epi_swizzle = 1;
+int g_opt_force_bn = 0;
+static thread_local std::string t_error;
+
+void set_error(const std::string& msg) { t_error = msg; }
+const char* last_error_cstr() { return t_error.c_str(); }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// ---- TMA descriptor encoding (driver entry point fetched through the runtime: no link against libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  uint64_t v[12];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+    return static_cast<size_t>(h);
+  }
+};
+
+int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, Swz swz) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key = {{reinterpret_cast<uint64_t>(base), static_cast<uint64_t>(elem_bytes), d0, d1, d2, stride1_bytes,
+                  stride2_bytes, b0, b1, b2, static_cast<uint64_t>(swz), 0}};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver / device)"); return 1; }
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = swz == Swz::B128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swz == Swz::B64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[384];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d): base=%p elem=%d dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u) swz=%d",
+             (int)r, base, elem_bytes, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, b0, b1, b2, (int)swz);
+    set_error(buf);
+    return 1;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return 0;
+}
+
+static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+}  // namespace pv
+
+using namespace pv;
+
+extern "C" {
+
+int pv_version(void) { return PV_ABI_VERSION; }
+const char* pv_last_error(void) { return last_error_cstr(); }
+unsigned long long pv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int pv_set_option(const char* name, int value) {
+  if (!name) PV_FAIL(PV_ERR_INVALID, "null option name");
+  if (!strcmp(name, "epi_swizzle")) { g_opt_epi_swizzle = value; return PV_OK; }
+  if (!strcmp(name, "force_bn")) { g_opt_force_bn = value; return PV_OK; }
+  PV_FAIL(PV_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int pv_pack_weight(pv_dtype out_dt, const float* W, const float* lora_A, const float* lora_B, float scaling,
+                   void* W_eff, int out_features, int in_features, int r, void* stream) {
+  PV_REQUIRE(W && W_eff, "null pointer");
+  return pack_weight(out_dt == PV_BF16, W, lora_A, lora_B, scaling, W_eff, out_features, in_features, r, as_stream(stream));
+}
+
+int pv_linear_fwd(pv_dtype dt, pv_dtype out_dt, const void* A, const void* W, const float* bias, void* D, int64_t M,
+                  int64_t N, int64_t K, int64_t batch, int64_t lda, int64_t ldw, int64_t ldd, int64_t strideA,
+                  int64_t strideW, int64_t strideBias, int64_t strideD, void* stream) {
+  PV_REQUIRE(A && W && D, "null pointer");
+  if (dt == PV_BF16)
+    return gemm_bf16(A, W, bias, D, out_dt == PV_F32, M, N, K, batch, lda, ldw, ldd, strideA, strideW, strideBias,
+                     strideD, as_stream(stream));
+  PV_REQUIRE(out_dt == PV_F32, "fp32 inputs produce fp32 outputs");
+  return gemm_f32(static_cast<const float*>(A), static_cast<const float*>(W), bias, static_cast<float*>(D), M, N, K,
+                  batch, lda, ldw, ldd, strideA, strideW, strideBias, strideD, as_stream(stream));
+}
+
+int64_t pv_kv_tile_bytes(pv_dtype dt, int C, int H, int Lt, int Li) {
+  if (H <= 0 || C % H != 0) return -1;
+  const int d = C / H;
+  if (dt == PV_BF16) return attn_kv_tile_bytes(d);
+  return static_cast<int64_t>(Lt + Li) * d * 4;
+}
+
+int pv_kv_pack_fwd(pv_dtype dt, const void* text, const void* img, const void* Wkv_text, const void* Wkv_img,
+                   float* kv_text_ws, float* kv_img_ws, void* Kp, void* Vp, float* v_ip_norm, int B, int Lt, int Li,
+                   int Dc, int C, int H, void* stream) {
+  PV_REQUIRE(text && img && Wkv_text && Wkv_img && kv_text_ws && kv_img_ws && Kp && Vp && v_ip_norm, "null pointer");
+  PV_REQUIRE(B > 0 && Lt >= 1 && Li >= 1 && Lt + Li <= PV_KEYS_PAD && C > 0 && H > 0 && C % H == 0 && Dc > 0,
+             "bad shape B=%d Lt=%d Li=%d Dc=%d C=%d H=%d", B, Lt, Li, Dc, C, H);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (dt == PV_BF16) {
+    rc = gemm_bf16(text, Wkv_text, nullptr, kv_text_ws, true, (long long)B * Lt, 2 * C, Dc, 1, Dc, Dc, 2 * C, 0, 0, 0, 0, st);
+    if (rc) return rc;
+    rc = gemm_bf16(img, Wkv_img, nullptr, kv_img_ws, true, (long long)B * Li, 2 * C, Dc, 1, Dc, Dc, 2 * C, 0, 0, 0, 0, st);
+    if (rc) return rc;
+  } else {
+    rc = gemm_f32(static_cast<const float*>(text), static_cast<const float*>(Wkv_text), nullptr, kv_text_ws,
+                  (long long)B * Lt, 2 * C, Dc, 1, Dc, Dc, 2 * C, 0, 0, 0, 0, st);
+    if (rc) return rc;
+    rc = gemm_f32(static_cast<const float*>(img), static_cast<const float*>(Wkv_img), nullptr, kv_img_ws,
+                  (long long)B * Li, 2 * C, Dc, 1, Dc, Dc, 2 * C, 0, 0, 0, 0, st);
+    if (rc) return rc;
+  }
+  return kv_pack(dt == PV_BF16, kv_text_ws, kv_img_ws, Kp, Vp, v_ip_norm, B, Lt, Li, C, H, st);
+}
+
+int pv_dual_attn_fwd(pv_dtype dt, const void* X, const void* Wq, const void* Kp, const void* Vp, const void* Wo,
+                     const float* bo, void* Y, float* ws_q, void* ws_o, float* stats, int B, int S, int C, int H,
+                     int Lt, int Li, float w_text, float w_img, void* stream) {
+  PV_REQUIRE(X && Wq && Kp && Vp && Wo && Y && ws_o, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (dt == PV_BF16) {
+    rc = dual_attn_core_bf16(X, Wq, Kp, Vp, ws_o, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+    if (rc) return rc;
+    return gemm_bf16(ws_o, Wo, bo, Y, false, (long long)B * S, C, C, 1, C, C, C, 0, 0, 0, 0, st);
+  }
+  PV_REQUIRE(ws_q != nullptr, "PV_F32 needs the ws_q scratch");
+  rc = gemm_f32(static_cast<const float*>(X), static_cast<const float*>(Wq), nullptr, ws_q, (long long)B * S, C, C, 1, C,
+                C, C, 0, 0, 0, 0, st);
+  if (rc) return rc;
+  rc = dual_attn_core_f32(ws_q, static_cast<const float*>(Kp), static_cast<const float*>(Vp),
+                          static_cast<float*>(ws_o), stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+  if (rc) return rc;
+  return gemm_f32(static_cast<const float*>(ws_o), static_cast<const float*>(Wo), bo, static_cast<float*>(Y),
+                  (long long)B * S, C, C, 1, C, C, C, 0, 0, 0, 0, st);
+}
+
+int pv_ln_lrelu_fwd(pv_dtype out_dt, const float* x, const float* gamma, const float* beta, void* y, float* save_mean,
+                    float* save_rstd, int64_t rows, int cols, int64_t ldx, int64_t ldy, int64_t rows_per_group,
+                    float eps, float slope, void* stream) {
+  PV_REQUIRE(x && gamma && beta && y, "null pointer");
+  return ln_lrelu(out_dt == PV_BF16, x, gamma, beta, y, save_mean, save_rstd, rows, cols, ldx, ldy, rows_per_group, eps,
+                  slope, as_stream(stream));
+}
+
+int pv_group_mean_fwd(pv_dtype in_dt, pv_dtype out_dt, const void* x, void* y, int64_t groups, int P, int cols,
+                      int64_t ldy, void* stream) {
+  PV_REQUIRE(x && y, "null pointer");
+  return group_mean(in_dt == PV_BF16, out_dt == PV_BF16, x, y, groups, P, cols, ldy, as_stream(stream));
+}
+
+}  // extern "C"

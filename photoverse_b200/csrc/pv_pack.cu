@@ -1,0 +1,149 @@
+// photoverse_b200 -- layout / packing kernels (HBM-bound, vectorised, coalesced).
+//
+//  * pack_weight      : W_eff = W + scaling * B A  (peft lora.Linear merged form) -> bf16 / fp32
+//  * kv_pack_bf16     : fp32 K/V projections -> per-(sample, head) UMMA operand images consumed by the fused
+//                       attention kernel via 1-D TMA bulk copies, + the `to_v_ip_norm` side output
+//                       (attention_processor.py:395-397)
+//  * kv_pack_f32      : same gather for the fp32 parity path ([B,H,L,d] fp32)
+#include "pv_common.cuh"
+#include "pv_host.h"
+#include "../../include/photoverse_b200.h"
+
+namespace pv {
+
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ W, const float* __restrict__ A, const float* __restrict__ Bm,
+                   float scaling, void* __restrict__ out, int out_f, int in_f, int r) {
+  // one thread = 4 consecutive input features of one output row
+  const long long idx = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const long long total = static_cast<long long>(out_f) * in_f;
+  if (idx >= total) return;
+  const int o = static_cast<int>(idx / in_f);
+  const int i = static_cast<int>(idx % in_f);
+  float4 w = *reinterpret_cast<const float4*>(W + idx);
+  if (r > 0) {
+    float dx = 0.f, dy = 0.f, dz = 0.f, dw = 0.f;
+    for (int k = 0; k < r; ++k) {
+      const float bk = Bm[static_cast<long long>(o) * r + k];
+      const float4 a = *reinterpret_cast<const float4*>(A + static_cast<long long>(k) * in_f + i);
+      dx = fmaf(bk, a.x, dx); dy = fmaf(bk, a.y, dy); dz = fmaf(bk, a.z, dz); dw = fmaf(bk, a.w, dw);
+    }
+    w.x = fmaf(scaling, dx, w.x); w.y = fmaf(scaling, dy, w.y);
+    w.z = fmaf(scaling, dz, w.z); w.w = fmaf(scaling, dw, w.w);
+  }
+  if constexpr (OUT_BF16) {
+    uint2 pk = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + idx) = pk;
+  } else {
+    *reinterpret_cast<float4*>(static_cast<float*>(out) + idx) = w;
+  }
+}
+
+int pack_weight(bool out_bf16, const float* W, const float* A, const float* Bm, float scaling, void* out, int out_f,
+                int in_f, int r, cudaStream_t stream) {
+  PV_REQUIRE(out_f > 0 && in_f > 0 && in_f % 4 == 0 && r >= 0, "bad shape out=%d in=%d r=%d", out_f, in_f, r);
+  PV_REQUIRE(r == 0 || (A != nullptr && Bm != nullptr), "LoRA rank %d without A/B", r);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(A)) % 16 == 0,
+             "pointers must be 16-byte aligned");
+  const long long total4 = static_cast<long long>(out_f) * in_f / 4;
+  const int blocks = static_cast<int>((total4 + 255) / 256);
+  if (out_bf16) pack_weight_kernel<true><<<blocks, 256, 0, stream>>>(W, A, Bm, scaling, out, out_f, in_f, r);
+  else pack_weight_kernel<false><<<blocks, 256, 0, stream>>>(W, A, Bm, scaling, out, out_f, in_f, r);
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kv_text:[B*Lt, 2C] fp32 (cols [0,C)=K, [C,2C)=V), kv_img:[B*Li, 2C] fp32
+// Kp[b][h] : K-major core-matrix image of K_h  [96 keys  x d_pad]: chunk kc (8 dims) of key r at (kc*96   + r)*16 B
+// Vp[b][h] : K-major core-matrix image of V_h^T [d_pad   x 96   ]: chunk kc (8 keys) of dim n at (kc*d_pad + n)*16 B
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float kv_fetch(const float* __restrict__ kv_text, const float* __restrict__ kv_img, int b,
+                                          int key, int col, int Lt, int Li, int C2) {
+  if (key < Lt) return kv_text[(static_cast<size_t>(b) * Lt + key) * C2 + col];
+  if (key < Lt + Li) return kv_img[(static_cast<size_t>(b) * Li + (key - Lt)) * C2 + col];
+  return 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+kv_pack_bf16_kernel(const float* __restrict__ kv_text, const float* __restrict__ kv_img, uint8_t* __restrict__ Kp,
+                    uint8_t* __restrict__ Vp, float* __restrict__ v_ip_norm, int Lt, int Li, int C, int H, int d,
+                    int d_pad) {
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int C2 = 2 * C;
+  const size_t tile_bytes = static_cast<size_t>(PV_KEYS_PAD) * d_pad * 2;
+  uint8_t* kt = Kp + (static_cast<size_t>(b) * H + h) * tile_bytes;
+  uint8_t* vt = Vp + (static_cast<size_t>(b) * H + h) * tile_bytes;
+  const int nkc = d_pad / 8;
+  // K tile: nkc * 96 chunks
+  for (int idx = threadIdx.x; idx < nkc * PV_KEYS_PAD; idx += blockDim.x) {
+    const int kc = idx / PV_KEYS_PAD, key = idx % PV_KEYS_PAD;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int dim = kc * 8 + i;
+      v[i] = (dim < d) ? kv_fetch(kv_text, kv_img, b, key, h * d + dim, Lt, Li, C2) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(kt + static_cast<size_t>(idx) * 16) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+  // V^T tile: 12 * d_pad chunks
+  for (int idx = threadIdx.x; idx < (PV_KEYS_PAD / 8) * d_pad; idx += blockDim.x) {
+    const int kc = idx / d_pad, dim = idx % d_pad;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int key = kc * 8 + i;
+      v[i] = (dim < d) ? kv_fetch(kv_text, kv_img, b, key, C + h * d + dim, Lt, Li, C2) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(vt + static_cast<size_t>(idx) * 16) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+  // ||V_img||_2 over head_dim, from the fp32 projections
+  for (int li = threadIdx.x; li < Li; li += blockDim.x) {
+    const float* row = kv_img + (static_cast<size_t>(b) * Li + li) * C2 + C + h * d;
+    float s = 0.f;
+    for (int i = 0; i < d; ++i) s = fmaf(row[i], row[i], s);
+    v_ip_norm[(static_cast<size_t>(b) * H + h) * Li + li] = sqrtf(s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kv_pack_f32_kernel(const float* __restrict__ kv_text, const float* __restrict__ kv_img, float* __restrict__ Kp,
+                   float* __restrict__ Vp, float* __restrict__ v_ip_norm, int Lt, int Li, int C, int H, int d) {
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int C2 = 2 * C, L = Lt + Li;
+  float* kt = Kp + (static_cast<size_t>(b) * H + h) * L * d;
+  float* vt = Vp + (static_cast<size_t>(b) * H + h) * L * d;
+  for (int idx = threadIdx.x; idx < L * d; idx += blockDim.x) {
+    const int key = idx / d, dim = idx % d;
+    kt[idx] = kv_fetch(kv_text, kv_img, b, key, h * d + dim, Lt, Li, C2);
+    vt[idx] = kv_fetch(kv_text, kv_img, b, key, C + h * d + dim, Lt, Li, C2);
+  }
+  for (int li = threadIdx.x; li < Li; li += blockDim.x) {
+    const float* row = kv_img + (static_cast<size_t>(b) * Li + li) * C2 + C + h * d;
+    float s = 0.f;
+    for (int i = 0; i < d; ++i) s = fmaf(row[i], row[i], s);
+    v_ip_norm[(static_cast<size_t>(b) * H + h) * Li + li] = sqrtf(s);
+  }
+}
+
+int kv_pack(bool bf16, const float* kv_text, const float* kv_img, void* Kp, void* Vp, float* v_ip_norm, int B, int Lt,
+            int Li, int C, int H, cudaStream_t stream) {
+  const int d = C / H;
+  PV_REQUIRE(B <= 65535, "grid too large");
+  dim3 grid(H, B);
+  if (bf16) {
+    const int d_pad = (d + 15) / 16 * 16;
+    kv_pack_bf16_kernel<<<grid, 256, 0, stream>>>(kv_text, kv_img, static_cast<uint8_t*>(Kp),
+                                                  static_cast<uint8_t*>(Vp), v_ip_norm, Lt, Li, C, H, d, d_pad);
+  } else {
+    kv_pack_f32_kernel<<<grid, 256, 0, stream>>>(kv_text, kv_img, static_cast<float*>(Kp), static_cast<float*>(Vp),
+                                                 v_ip_norm, Lt, Li, C, H, d);
+  }
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
+}  // namespace pv

@@ -1,0 +1,313 @@
+"""Host model: a Stable-Diffusion-1.5-shaped UNet in plain PyTorch (random-init; diffusers is not installable here).
+
+This is NOT part of the B200 hot path -- it is the *caller* of the path: the backbone the
+PhotoVerse processors are plugged into so that images/s can be measured.  ResNet blocks, self-attention (attn1),
+GEGLU feed-forward, up/down-sampling run as stock PyTorch / cuDNN library code on both the reference arm and ours;
+only the 16 ``attn2`` layers go through photoverse_b200's kernels.
+
+It reproduces diffusers 0.27.2's ``UNet2DConditionModel`` for the SD-1.5 config (module tree, parameter names,
+``attn_processors`` / ``set_attn_processor`` / ``config`` protocol, processor key names consumed by the reference's
+``models/unet.py:10-19``) so the reference's installation code and checkpoints' key layout apply unchanged.
+"""
+import math
+from types import SimpleNamespace
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class AttnProcessor2_0:
+    """Stock SDPA processor for the self-attention (attn1) layers -- library code, outside the hot path."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, **kw):
+        B, S, C = hidden_states.shape
+        ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
+        if isinstance(ctx, tuple):
+            ctx = ctx[0]
+        h = attn.heads
+        q = attn.to_q(hidden_states).view(B, -1, h, C // h).transpose(1, 2)
+        k = attn.to_k(ctx).view(B, -1, h, C // h).transpose(1, 2)
+        v = attn.to_v(ctx).view(B, -1, h, C // h).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=False)
+        o = o.transpose(1, 2).reshape(B, -1, C).to(q.dtype)
+        return attn.to_out[1](attn.to_out[0](o))
+
+
+class Attention(nn.Module):
+    """The subset of diffusers' ``Attention`` that SD-1.5 uses (bias-free q/k/v, out projection with bias)."""
+
+    def __init__(self, query_dim: int, cross_attention_dim: Optional[int] = None, heads: int = 8):
+        super().__init__()
+        self.heads = heads
+        self.inner_dim = query_dim
+        self.cross_attention_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.scale = (query_dim // heads) ** -0.5
+        self.to_q = nn.Linear(query_dim, query_dim, bias=False)
+        self.to_k = nn.Linear(self.cross_attention_dim, query_dim, bias=False)
+        self.to_v = nn.Linear(self.cross_attention_dim, query_dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(query_dim, query_dim, bias=True), nn.Dropout(0.0)])
+        self.spatial_norm = None
+        self.group_norm = None
+        self.norm_cross = None
+        self.norm_encoder_hidden_states = None
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+        self.processor = AttnProcessor2_0()
+
+    def set_processor(self, processor):
+        # nn.Module processors become sub-modules named `processor` (their weights enter unet.state_dict(),
+        # reference models/modeling_utils.py:33-37)
+        if isinstance(getattr(self, "processor", None), nn.Module) and not isinstance(processor, nn.Module):
+            self._modules.pop("processor", None)
+        self.processor = processor
+
+    def prepare_attention_mask(self, *a, **k):
+        raise NotImplementedError("attention masks are not used by SD-1.5")
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kw):
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                              attention_mask=attention_mask, **kw)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        x, gate = self.proj(x).chunk(2, dim=-1)
+        return x * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+    def forward(self, x):
+        for m in self.net:
+            x = m(x)
+        return x
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, cross_attention_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, cross_attention_dim, heads)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+    def forward(self, x, encoder_hidden_states):
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), encoder_hidden_states=encoder_hidden_states) + x
+        return self.ff(self.norm3(x)) + x
+
+
+class Transformer2DModel(nn.Module):
+    def __init__(self, channels, heads, cross_attention_dim, groups=32):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, channels, eps=1e-6)
+        self.proj_in = nn.Conv2d(channels, channels, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(channels, heads, cross_attention_dim)])
+        self.proj_out = nn.Conv2d(channels, channels, 1)
+
+    def forward(self, x, encoder_hidden_states):
+        B, C, H, W = x.shape
+        res = x
+        h = self.proj_in(self.norm(x))
+        h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
+        for blk in self.transformer_blocks:
+            h = blk(h, encoder_hidden_states)
+        h = h.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+        return self.proj_out(h) + res
+
+
+class ResnetBlock2D(nn.Module):
+    def __init__(self, cin, cout, temb_ch, groups=32):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=1e-5)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_ch, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=1e-5)
+        self.dropout = nn.Dropout(0.0)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+
+    def forward(self, x, temb):
+        h = self.conv1(F.silu(self.norm1(x)))
+        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        h = self.conv2(self.dropout(F.silu(self.norm2(h))))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        return x + h
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class DownBlock(nn.Module):
+    def __init__(self, cin, cout, temb_ch, layers, heads, cross_dim, has_attn, add_down):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb_ch) for i in range(layers)])
+        self.attentions = nn.ModuleList(
+            [Transformer2DModel(cout, heads, cross_dim) for _ in range(layers)]) if has_attn else None
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_down else None
+
+    def forward(self, x, temb, ctx):
+        outs = []
+        for i, r in enumerate(self.resnets):
+            x = r(x, temb)
+            if self.attentions is not None:
+                x = self.attentions[i](x, ctx)
+            outs.append(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](x)
+            outs.append(x)
+        return x, outs
+
+
+class UpBlock(nn.Module):
+    def __init__(self, cin, cout, prev_out, temb_ch, layers, heads, cross_dim, has_attn, add_up):
+        super().__init__()
+        res = []
+        for i in range(layers):
+            skip = cin if i == layers - 1 else cout
+            rin = prev_out if i == 0 else cout
+            res.append(ResnetBlock2D(rin + skip, cout, temb_ch))
+        self.resnets = nn.ModuleList(res)
+        self.attentions = nn.ModuleList(
+            [Transformer2DModel(cout, heads, cross_dim) for _ in range(layers)]) if has_attn else None
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
+
+    def forward(self, x, skips, temb, ctx):
+        for i, r in enumerate(self.resnets):
+            x = torch.cat([x, skips.pop()], dim=1)
+            x = r(x, temb)
+            if self.attentions is not None:
+                x = self.attentions[i](x, ctx)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0](x)
+        return x
+
+
+class MidBlock(nn.Module):
+    def __init__(self, ch, temb_ch, heads, cross_dim):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(ch, ch, temb_ch), ResnetBlock2D(ch, ch, temb_ch)])
+        self.attentions = nn.ModuleList([Transformer2DModel(ch, heads, cross_dim)])
+
+    def forward(self, x, temb, ctx):
+        x = self.resnets[0](x, temb)
+        x = self.attentions[0](x, ctx)
+        return self.resnets[1](x, temb)
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, cout)
+        self.linear_2 = nn.Linear(cout, cout)
+
+    def forward(self, x):
+        return self.linear_2(F.silu(self.linear_1(x)))
+
+
+def timestep_sinusoid(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """diffusers ``Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0)``."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    args = t.float()[:, None] * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+class UNetSD15(nn.Module):
+    """SD-1.5 defaults: block_out_channels=(320,640,1280,1280), layers_per_block=2, 8 heads, cross dim 768,
+    cross-attention in the first three down blocks / last three up blocks / the mid block -> 16 attn2 layers."""
+
+    def __init__(self, in_channels=4, out_channels=4, block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280),
+                 layers_per_block=2, heads=8, cross_attention_dim=768, sample_size=64):
+        super().__init__()
+        boc = tuple(block_out_channels)
+        n = len(boc)
+        self.config = SimpleNamespace(in_channels=in_channels, out_channels=out_channels, block_out_channels=boc,
+                                      layers_per_block=layers_per_block, attention_head_dim=heads,
+                                      cross_attention_dim=cross_attention_dim, sample_size=sample_size)
+        temb_ch = boc[0] * 4
+        self.conv_in = nn.Conv2d(in_channels, boc[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(boc[0], temb_ch)
+        self.down_blocks = nn.ModuleList()
+        cout = boc[0]
+        for i in range(n):
+            cin, cout = cout, boc[i]
+            last = i == n - 1
+            self.down_blocks.append(DownBlock(cin, cout, temb_ch, layers_per_block, heads, cross_attention_dim,
+                                              has_attn=not last or n == 1, add_down=not last))
+        self.mid_block = MidBlock(boc[-1], temb_ch, heads, cross_attention_dim)
+        self.up_blocks = nn.ModuleList()
+        rev = list(reversed(boc))
+        cout = rev[0]
+        for i in range(n):
+            prev_out, cout = cout, rev[i]
+            cin = rev[min(i + 1, n - 1)]
+            last = i == n - 1
+            self.up_blocks.append(UpBlock(cin, cout, prev_out, temb_ch, layers_per_block + 1, heads,
+                                          cross_attention_dim, has_attn=i > 0 or n == 1, add_up=not last))
+        self.conv_norm_out = nn.GroupNorm(32, boc[0], eps=1e-5)
+        self.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
+
+    # ---- diffusers attention-processor protocol ------------------------------------------------
+    @property
+    def attn_processors(self) -> Dict[str, object]:
+        procs = {}
+        for name, m in self.named_modules():
+            if isinstance(m, Attention):
+                procs[f"{name}.processor"] = m.processor
+        return procs
+
+    def set_attn_processor(self, processor):
+        mods = {f"{name}.processor": m for name, m in self.named_modules() if isinstance(m, Attention)}
+        if isinstance(processor, dict):
+            if len(processor) != len(mods):
+                raise ValueError(f"A dict of processors was passed, but the number of processors {len(processor)} "
+                                 f"does not match the number of attention layers: {len(mods)}.")
+            for k, m in mods.items():
+                m.set_processor(processor[k])
+        else:
+            for m in mods.values():
+                m.set_processor(processor)
+
+    def forward(self, sample, timestep, encoder_hidden_states):
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([timestep], device=sample.device)
+        t = timestep.reshape(-1).expand(sample.shape[0]) if timestep.numel() == 1 else timestep
+        temb = self.time_embedding(timestep_sinusoid(t, self.config.block_out_channels[0]).to(sample.dtype))
+        x = self.conv_in(sample)
+        skips = [x]
+        for blk in self.down_blocks:
+            x, outs = blk(x, temb, encoder_hidden_states)
+            skips += outs
+        x = self.mid_block(x, temb, encoder_hidden_states)
+        for blk in self.up_blocks:
+            x = blk(x, skips, temb, encoder_hidden_states)
+        x = self.conv_out(F.silu(self.conv_norm_out(x)))
+        return SimpleNamespace(sample=x)

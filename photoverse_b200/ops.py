@@ -1,0 +1,168 @@
+"""Torch-tensor front end of the C ABI: pointer / stride marshalling only, no arithmetic.
+
+PyTorch owns every buffer (inputs, outputs, workspaces); the native library gets raw device pointers and the
+current CUDA stream.  Anything that is not a CUDA tensor of a supported dtype raises -- there is no fallback.
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import PV_BF16, PV_F32, PV_KEYS_PAD, check
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return PV_BF16
+    if t.dtype == torch.float32:
+        return PV_F32
+    raise _lib.PhotoverseB200Error(f"unsupported dtype {t.dtype}: photoverse_b200 computes in bfloat16 or float32")
+
+
+def _code(dtype: torch.dtype) -> int:
+    return PV_BF16 if dtype == torch.bfloat16 else PV_F32
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.PhotoverseB200Error("photoverse_b200 ops need CUDA tensors (no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    return t
+
+
+def pack_weight(w: torch.Tensor, out: torch.Tensor, lora_A=None, lora_B=None, scaling: float = 0.0) -> torch.Tensor:
+    """out[out_f, in_f] (bf16|f32) = w + scaling * lora_B @ lora_A  (fp32 masters)."""
+    out_f, in_f = w.shape
+    assert out.shape == w.shape and out.is_contiguous() and w.is_contiguous() and w.dtype == torch.float32
+    r = 0
+    if lora_A is not None:
+        r = lora_A.shape[0]
+        assert lora_A.shape == (r, in_f) and lora_B.shape == (out_f, r)
+        lora_A, lora_B = _f32(lora_A.contiguous()), _f32(lora_B.contiguous())
+    check(_lib.lib().pv_pack_weight(_dt(out), _ptr(w), _ptr(lora_A), _ptr(lora_B), float(scaling), _ptr(out),
+                                    out_f, in_f, r, _stream()), "pv_pack_weight")
+    return out
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """out[..., N] = a[..., K] @ w[..., N, K]^T + bias.  a: [M,K] or [batch,M,K]; w: [N,K] or [batch,N,K];
+    bias fp32 [N] or [batch,N].  Inner-most dims must be contiguous; ``out`` may be a strided view."""
+    batched = a.dim() == 3
+    if not batched:
+        a3 = a.unsqueeze(0)
+    else:
+        a3 = a
+    batch, M, K = a3.shape
+    w3 = w if w.dim() == 3 else w.unsqueeze(0)
+    N = w3.shape[1]
+    assert w3.shape[2] == K and a3.stride(2) == 1 and w3.stride(2) == 1
+    assert a.dtype == w.dtype, (a.dtype, w.dtype)
+    if out_dtype is None:
+        out_dtype = a.dtype if out is None else out.dtype
+    if out is None:
+        out = torch.empty((batch, M, N) if batched else (M, N), device=a.device, dtype=out_dtype)
+    o3 = out if out.dim() == 3 else out.unsqueeze(0)
+    assert o3.shape == (batch, M, N) and o3.stride(2) == 1
+    stride_w = w3.stride(0) if (w.dim() == 3 and w3.shape[0] > 1) else 0
+    if w.dim() == 3 and w3.shape[0] not in (1, batch):
+        raise ValueError("weight batch must be 1 or match the activation batch")
+    stride_b = 0
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.stride(-1) == 1
+        stride_b = bias.stride(0) if (bias.dim() == 2 and bias.shape[0] > 1) else 0
+    check(_lib.lib().pv_linear_fwd(_dt(a), _code(out_dtype), _ptr(a3), _ptr(w3), _ptr(bias), _ptr(o3),
+                                   M, N, K, batch, a3.stride(1), w3.stride(1), o3.stride(1),
+                                   a3.stride(0) if batch > 1 else 0, stride_w, stride_b,
+                                   o3.stride(0) if batch > 1 else 0, _stream()), "pv_linear_fwd")
+    return out
+
+
+def kv_tile_bytes(dtype: torch.dtype, C: int, H: int, Lt: int, Li: int) -> int:
+    n = int(_lib.lib().pv_kv_tile_bytes(_code(dtype), C, H, Lt, Li))
+    if n <= 0:
+        raise _lib.PhotoverseB200Error(f"bad K/V tile query C={C} H={H}")
+    return n
+
+
+class PackedKV:
+    """Device buffers produced by :func:`kv_pack` (owned by PyTorch)."""
+    __slots__ = ("Kp", "Vp", "v_ip_norm", "kv_text", "kv_img", "B", "Lt", "Li", "C", "H", "dtype", "_keepalive")
+
+
+def kv_pack(text: torch.Tensor, img: torch.Tensor, wkv_text: torch.Tensor, wkv_img: torch.Tensor, H: int) -> PackedKV:
+    """text [B,Lt,Dc], img [B,Li,Dc], wkv_* [2C,Dc] (all the compute dtype) -> packed K/V tiles + ||V_img||."""
+    B, Lt, Dc = text.shape
+    Li = img.shape[1]
+    C = wkv_text.shape[0] // 2
+    assert text.is_contiguous() and img.is_contiguous() and wkv_text.is_contiguous() and wkv_img.is_contiguous()
+    assert text.dtype == img.dtype == wkv_text.dtype == wkv_img.dtype
+    dev = text.device
+    kv = PackedKV()
+    kv.B, kv.Lt, kv.Li, kv.C, kv.H, kv.dtype = B, Lt, Li, C, H, text.dtype
+    tile = kv_tile_bytes(text.dtype, C, H, Lt, Li)
+    kv.Kp = torch.empty(B * H * tile, device=dev, dtype=torch.uint8)
+    kv.Vp = torch.empty(B * H * tile, device=dev, dtype=torch.uint8)
+    kv.kv_text = torch.empty(B * Lt, 2 * C, device=dev, dtype=torch.float32)
+    kv.kv_img = torch.empty(B * Li, 2 * C, device=dev, dtype=torch.float32)
+    kv.v_ip_norm = torch.empty(B, H, Li, device=dev, dtype=torch.float32)
+    check(_lib.lib().pv_kv_pack_fwd(_dt(text), _ptr(text), _ptr(img), _ptr(wkv_text), _ptr(wkv_img),
+                                    _ptr(kv.kv_text), _ptr(kv.kv_img), _ptr(kv.Kp), _ptr(kv.Vp), _ptr(kv.v_ip_norm),
+                                    B, Lt, Li, Dc, C, H, _stream()), "pv_kv_pack_fwd")
+    return kv
+
+
+def dual_attn(x: torch.Tensor, wq: torch.Tensor, kv: PackedKV, wo: torch.Tensor, bo: torch.Tensor,
+              w_text: float = 1.0, w_img: float = 1.0, want_stats: bool = False):
+    """Y = (w_t softmax(QK_t^T/sqrt d) V_t + w_i softmax(QK_i^T/sqrt d) V_i) Wo^T + bo with Q = x Wq^T.
+    Returns (Y, O, stats|None, Q|None); O (pre-out-projection) and Q (fp32 mode only) are kept for backward."""
+    B, S, C = x.shape
+    assert x.is_contiguous() and wq.is_contiguous() and wo.is_contiguous()
+    assert x.dtype == wq.dtype == wo.dtype == kv.dtype and bo.dtype == torch.float32
+    assert (kv.B, kv.C) == (B, C)
+    y = torch.empty_like(x)
+    o = torch.empty_like(x)
+    q = torch.empty(B, S, C, device=x.device, dtype=torch.float32) if x.dtype == torch.float32 else None
+    stats = torch.empty(B, kv.H, S, 4, device=x.device, dtype=torch.float32) if want_stats else None
+    check(_lib.lib().pv_dual_attn_fwd(_dt(x), _ptr(x), _ptr(wq), _ptr(kv.Kp), _ptr(kv.Vp), _ptr(wo), _ptr(bo),
+                                      _ptr(y), _ptr(q), _ptr(o), _ptr(stats), B, S, C, kv.H, kv.Lt, kv.Li,
+                                      float(w_text), float(w_img), _stream()), "pv_dual_attn_fwd")
+    return y, o, stats, q
+
+
+def ln_lrelu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor,
+             rows_per_group: int = 0, eps: float = 1e-5, slope: float = 0.01, save_stats: bool = False):
+    """out = leaky_relu(layer_norm(x) * gamma + beta); x fp32 [rows, cols] (row-strided ok), out bf16|fp32."""
+    rows, cols = x.shape
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and out.stride(1) == 1 and out.shape == x.shape
+    assert gamma.dtype == beta.dtype == torch.float32 and gamma.is_contiguous() and beta.is_contiguous()
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    check(_lib.lib().pv_ln_lrelu_fwd(_dt(out), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(mean), _ptr(rstd),
+                                     rows, cols, x.stride(0), out.stride(0), rows_per_group, eps, slope, _stream()),
+          "pv_ln_lrelu_fwd")
+    return out, mean, rstd
+
+
+def group_mean(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """x [groups, P, cols] contiguous -> out [groups, cols] (row-strided ok) = mean over P."""
+    groups, P, cols = x.shape
+    assert x.is_contiguous() and out.shape == (groups, cols) and out.stride(1) == 1
+    check(_lib.lib().pv_group_mean_fwd(_dt(x), _dt(out), _ptr(x), _ptr(out), groups, P, cols, out.stride(0),
+                                       _stream()), "pv_group_mean_fwd")
+    return out

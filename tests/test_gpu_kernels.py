@@ -1,0 +1,204 @@
+"""GPU (B200): parity of every CUDA entry point, called through the C ABI, against the oracle / golden vectors.
+
+Tolerances (north_star): attention output max-abs <= 2e-2 in bf16, <= 1e-4 in fp32.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import adapter_oracle, cases
+from oracle.processor_oracle import dual_branch_attention
+from tests.helpers import build_product_layer, force_fusion_seed, golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def _lib_loaded():
+    # the native library must be the thing that ran: fail if /proc/self/maps does not show it
+    with open("/proc/self/maps") as f:
+        return "libphotoverse_b200.so" in f.read()
+
+
+@pytest.mark.parametrize("swz", [0, 1])
+@pytest.mark.parametrize("out_f32", [False, True])
+@pytest.mark.parametrize("M,N,K,bn", [(256, 320, 320, 0), (300, 640, 768, 0), (128, 1280, 1280, 256), (77 * 2, 640, 768, 160),
+                                      (1000, 768, 2048, 128), (64, 64, 64, 64), (8, 1024, 1024, 0)])
+def test_linear_bf16(cuda_device, M, N, K, bn, out_f32, swz):
+    from photoverse_b200 import _lib, ops
+    _lib.set_option("epi_swizzle", swz)
+    _lib.set_option("force_bn", bn)
+    try:
+        g = torch.Generator().manual_seed(M * 7 + N)
+        a = torch.randn(M, K, generator=g).to(cuda_device, torch.bfloat16)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device, torch.bfloat16)
+        b = torch.randn(N, generator=g).to(cuda_device)
+        y = ops.linear(a, w, b, out_dtype=torch.float32 if out_f32 else torch.bfloat16)
+        ref = a.float() @ w.float().t() + b
+        err = (y.float() - ref).abs().max().item()
+        tol = 2e-5 * K ** 0.5 + (0 if out_f32 else 4e-3 * ref.abs().max().item())
+        assert err <= tol, f"max err {err} > {tol}"
+    finally:
+        _lib.set_option("epi_swizzle", 1)
+        _lib.set_option("force_bn", 0)
+    assert _lib_loaded()
+
+
+def test_linear_bf16_batched_strided(cuda_device):
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    T, M, K, N = 3, 200, 1024, 768
+    a = torch.randn(T, M, K, generator=g).to(cuda_device, torch.bfloat16)
+    w = (torch.randn(T, N, K, generator=g) / 32).to(cuda_device, torch.bfloat16)
+    b = torch.randn(T, N, generator=g).to(cuda_device)
+    out = torch.zeros(M, T, N, device=cuda_device, dtype=torch.bfloat16)
+    ops.linear(a, w, b, out=out.permute(1, 0, 2))
+    ref = torch.einsum("tmk,tnk->tmn", a.float(), w.float()) + b[:, None]
+    assert (out.permute(1, 0, 2).float() - ref).abs().max().item() <= 3e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(130, 70, 100), (64, 320, 768), (5, 1280, 1280)])
+def test_linear_f32(cuda_device, M, N, K):
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    a = torch.randn(M, K, generator=g).to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device)
+    b = torch.randn(N, generator=g).to(cuda_device)
+    y = ops.linear(a, w, b)
+    ref = (a.double() @ w.double().t() + b.double()).float()
+    assert (y - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_pack_weight_merges_lora(cuda_device, out_dtype):
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(320, 768, generator=g).to(cuda_device)
+    A = torch.randn(8, 768, generator=g).to(cuda_device)
+    B = torch.randn(320, 8, generator=g).to(cuda_device)
+    out = ops.pack_weight(w, torch.empty(320, 768, device=cuda_device, dtype=out_dtype), A, B, 0.125)
+    ref = w.double() + 0.125 * (B.double() @ A.double())
+    tol = 1e-5 if out_dtype == torch.float32 else 2e-2
+    assert (out.double() - ref).abs().max().item() <= tol
+    out2 = ops.pack_weight(w, torch.empty(320, 768, device=cuda_device, dtype=out_dtype))
+    assert torch.equal(out2, w.to(out_dtype))
+
+
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_ln_lrelu_and_group_mean(cuda_device, out_dtype):
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    T, M = 3, 70
+    x = (torch.randn(T * M, 1024, generator=g) * 2 + 0.5).to(cuda_device)
+    gamma = (1 + 0.1 * torch.randn(T, 1024, generator=g)).to(cuda_device)
+    beta = (0.1 * torch.randn(T, 1024, generator=g)).to(cuda_device)
+    out = torch.empty(T * M, 1024, device=cuda_device, dtype=out_dtype)
+    _, mean, rstd = ops.ln_lrelu(x, gamma, beta, out, rows_per_group=M, save_stats=True)
+    xr = x.view(T, M, 1024).double()
+    ref = torch.nn.functional.layer_norm(xr, (1024,), eps=1e-5) * gamma.double()[:, None] + beta.double()[:, None]
+    ref = torch.nn.functional.leaky_relu(ref, 0.01).view(T * M, 1024)
+    tol = 1e-5 if out_dtype == torch.float32 else 2e-2
+    assert (out.double() - ref).abs().max().item() <= tol
+    assert (mean.double() - x.double().mean(1)).abs().max().item() <= 1e-5
+    xm = out.view(T, M, 1024).contiguous()
+    ym = torch.empty(T, 2048, device=cuda_device, dtype=out_dtype)
+    ops.group_mean(xm, ym[:, 1024:])
+    assert (ym[:, 1024:].double() - xm.double().mean(1)).abs().max().item() <= (1e-5 if out_dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", cases.PROC_CASES, ids=lambda c: c.name)
+def test_processor_matches_golden(cuda_device, case, dtype):
+    """The drop-in processor (reference call signature) vs the golden vectors of the verbatim reference."""
+    g = golden(case.name)
+    attn, proc = build_product_layer(case, cuda_device)
+    x, text, img = (t.to(cuda_device, dtype) for t in cases.proc_inputs(case, torch.float32))
+    if (case.w_text, case.w_img) == (1.0, 1.0):
+        with torch.no_grad():
+            y = attn(x, encoder_hidden_states=(text, img))
+    else:
+        # grad mode + forced branch of the stochastic rule; all parameters frozen so the forward-only path runs
+        for p in list(attn.parameters()):
+            p.requires_grad_(False)
+        force_fusion_seed(case.w_text, case.w_img)
+        with torch.enable_grad():
+            y = attn(x, encoder_hidden_states=(text, img))
+        assert proc.last_fusion == (case.w_text, case.w_img)
+    err = np.abs(y.float().cpu().numpy() - g["y"]).max()
+    # ||V_img|| ~ 4..8: compare relatively (bf16 rounding of the image tokens / weights alone is ~4e-3 relative)
+    nerr = np.abs(proc.to_v_ip_norm.float().cpu().numpy() / g["vnorm"] - 1.0).max()
+    assert y.dtype == dtype and y.shape == (case.B, case.S, case.C)
+    assert proc.to_v_ip_norm.shape == (case.B, case.H, case.Li, 1)
+    assert err <= TOL[dtype], f"attention output max-abs {err} > {TOL[dtype]}"
+    assert nerr <= (1e-5 if dtype == torch.float32 else 1e-2), f"to_v_ip_norm relative err {nerr}"
+
+
+@pytest.mark.parametrize("S,C,Li,B", [(4096, 320, 5, 2), (1024, 640, 1, 2), (256, 1280, 16, 2), (64, 1280, 5, 3),
+                                      (2304, 640, 4, 1), (576, 1280, 8, 1)])
+def test_processor_bf16_full_size_vs_oracle(cuda_device, S, C, Li, B):
+    """BASELINE shapes (latent 64^2 and 96^2): CUDA bf16 path vs the fp32 oracle evaluated on the same inputs."""
+    case = cases.ProcCase(f"full_{S}_{C}", B=B, S=S, C=C, Li=Li, seed=40 + Li)
+    attn, proc = build_product_layer(case, cuda_device)
+    x, text, img = cases.proc_inputs(case, torch.float32)
+    with torch.no_grad():
+        y = attn(x.to(cuda_device, torch.bfloat16), encoder_hidden_states=(text.to(cuda_device, torch.bfloat16),
+                                                                          img.to(cuda_device, torch.bfloat16)))
+        w = cases.proc_weights(case).to(device=cuda_device)      # oracle (torch fp32) on the same device: checker only
+        y_ref, vn_ref = dual_branch_attention(x.to(cuda_device), text.to(cuda_device), img.to(cuda_device), w)
+    err = (y.float() - y_ref).abs().max().item()
+    assert err <= 2e-2, f"max-abs {err}"
+    assert (proc.to_v_ip_norm.float() / vn_ref - 1.0).abs().max().item() <= 1e-2
+
+
+def test_processor_linearity_in_value_path(cuda_device):
+    """Size-independent property at full size: the output is linear in (V_text, V_img, bias) -> doubling to_v, to_v_ip
+    and the out-bias... is checked through w_text/w_img instead: Y(2,0) + Y(0,2) - 2*bias_term == 2*Y(1,1) - ..."""
+    case = cases.ProcCase("lin", B=1, S=1024, C=640, Li=5, seed=77)
+    attn, proc = build_product_layer(case, cuda_device)
+    x, text, img = (t.to(cuda_device) for t in cases.proc_inputs(case, torch.float32))
+    for p in attn.parameters():
+        p.requires_grad_(False)
+    outs = {}
+    for wt, wi in ((1.0, 1.0), (2.0, 0.0), (0.0, 2.0)):
+        force_fusion_seed(wt, wi)
+        with torch.enable_grad():
+            outs[(wt, wi)] = attn(x, encoder_hidden_states=(text, img)).double()
+    bias = attn.to_out[0].bias.double()
+    lhs = (outs[(2.0, 0.0)] - bias) + (outs[(0.0, 2.0)] - bias)
+    rhs = 2.0 * (outs[(1.0, 1.0)] - bias)
+    assert (lhs - rhs).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", cases.ADAPTER_CASES, ids=lambda c: c.name)
+def test_adapter_matches_golden(cuda_device, case, dtype):
+    from photoverse_b200 import PhotoVerseAdapter
+    g = golden(case.name)
+    ad = PhotoVerseAdapter(num_tokens=case.T)
+    ad.load_state_dict(adapter_oracle.make_state_dict(case.T, case.seed), strict=True)
+    ad.to(cuda_device)
+    embs = [e.to(cuda_device, dtype) for e in cases.adapter_inputs(case)]
+    with torch.no_grad():
+        y = ad(embs, token_index=case.token_index)
+    err = np.abs(y.float().cpu().numpy() - g["y"]).max()
+    tol = 1e-4 if dtype == torch.float32 else 4e-2      # adapter output rms ~0.5, three bf16 GEMMs + 2 LayerNorms deep
+    assert y.shape == g["y"].shape and y.dtype == dtype
+    assert err <= tol, f"adapter max-abs {err} > {tol}"
+
+
+def test_kv_cache_reuses_projection(cuda_device):
+    from photoverse_b200 import _lib
+    case = cases.PROC_CASES[0]
+    attn, proc = build_product_layer(case, cuda_device)
+    x, text, img = (t.to(cuda_device, torch.bfloat16) for t in cases.proc_inputs(case, torch.float32))
+    with torch.no_grad():
+        y0 = attn(x, encoder_hidden_states=(text, img))
+        proc.enable_kv_cache(True)
+        y1 = attn(x, encoder_hidden_states=(text, img))
+        n0 = _lib.launch_count()
+        y2 = attn(x, encoder_hidden_states=(text, img))
+        n1 = _lib.launch_count()
+        proc.enable_kv_cache(False)
+    assert torch.equal(y0, y1) and torch.equal(y1, y2)
+    assert n1 - n0 == 2, f"cached call should launch attention + out-proj only, launched {n1 - n0}"
