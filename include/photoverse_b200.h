@@ -89,6 +89,13 @@ int pv_dual_attn_fwd(pv_dtype dt, const void* X, const void* Wq, const void* Kp,
                      const float* bo, void* Y, float* ws_q, void* ws_o, float* stats, int B, int S, int C, int H,
                      int Lt, int Li, float w_text, float w_img, void* stream);
 
+/* The fused kernel alone (no out projection): PV_BF16: XorQ = X [B,S,C] bf16 and Wq is used (Q-projection fused);
+ * PV_F32: XorQ = Q [B,S,C] fp32 (already projected) and Wq is ignored.  O:[B,S,C] (dt).  Used by the roofline
+ * measurement in bench.py and by the backward pass (recompute).                                               */
+int pv_dual_attn_core_fwd(pv_dtype dt, const void* XorQ, const void* Wq, const void* Kp, const void* Vp, void* O,
+                          float* stats, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                          void* stream);
+
 /* ---- adapter epilogues (adapters.py:15-16,18-19: LayerNorm(1024) -> LeakyReLU(0.01)) ----------------
  * y = leaky_relu(layer_norm(x) * gamma + beta); x:[rows,cols] fp32 (row stride ldx), y:[rows,cols] out_dt
  * (row stride ldy); cols % 128 == 0, cols <= 4096.  Optional mean / rstd [rows] fp32 saved for backward.

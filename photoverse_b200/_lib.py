@@ -30,6 +30,7 @@ _SIGNATURES = {
     "pv_kv_tile_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "pv_kv_pack_fwd": (c_int, [c_int] + [c_void_p] * 9 + [c_int] * 6 + [c_void_p]),
     "pv_dual_attn_fwd": (c_int, [c_int] + [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p]),
+    "pv_dual_attn_core_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int] * 6 + [c_float, c_float, c_void_p]),
     "pv_ln_lrelu_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     "pv_group_mean_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),
     "pv_dual_attn_bwd": (c_int, [c_int] + [c_void_p] * 14 + [c_int] * 6 + [c_float, c_float, c_void_p]),
@@ -42,7 +43,7 @@ _SIGNATURES = {
 
 # symbols every build must export (the rest are added as later ABI revisions land)
 REQUIRED_SYMBOLS = ["pv_version", "pv_last_error", "pv_launch_count", "pv_set_option", "pv_pack_weight",
-                    "pv_linear_fwd", "pv_kv_tile_bytes", "pv_kv_pack_fwd", "pv_dual_attn_fwd", "pv_ln_lrelu_fwd",
+                    "pv_linear_fwd", "pv_kv_tile_bytes", "pv_kv_pack_fwd", "pv_dual_attn_fwd", "pv_dual_attn_core_fwd", "pv_ln_lrelu_fwd",
                     "pv_group_mean_fwd"]
 
 

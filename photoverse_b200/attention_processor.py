@@ -67,13 +67,36 @@ class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):
         self.to_v_ip_norm = None
         self._packed = {}          # dtype -> _PackedWeights
         self._kv_cache = None      # dict while a kv_cache scope is active, else None
+        self._kv_static = False
         self.last_fusion = (1.0, 1.0)
 
     # ------------------------------------------------------------------------------------------
     # K/V cache control (used by the denoise loop; off by default == reference behaviour)
     # ------------------------------------------------------------------------------------------
-    def enable_kv_cache(self, enabled: bool = True):
+    def enable_kv_cache(self, enabled: bool = True, static: bool = False):
+        """``static=True``: entries are keyed by buffer address only and live in persistent device buffers that
+        :meth:`prepare_kv` refreshes in place -- what a captured CUDA graph needs (stable K/V addresses)."""
         self._kv_cache = {} if enabled else None
+        self._kv_static = bool(static) and enabled
+
+    def _kv_key(self, text, img):
+        key = (text.data_ptr(), img.data_ptr(), tuple(text.shape), tuple(img.shape), text.dtype)
+        if not getattr(self, "_kv_static", False):
+            key += (text._version, img._version)
+        return key
+
+    @torch.no_grad()
+    def prepare_kv(self, attn, text, img):
+        """(Re)compute the packed K/V of this layer for the given contexts into the cache (in place when the
+        entry exists).  Called once per generation by the denoise loop."""
+        if self._kv_cache is None:
+            raise RuntimeError("enable_kv_cache() first")
+        pk = self._weights(attn, text.dtype, text.device)
+        ck = self._kv_key(text, img)
+        kv = ops.kv_pack(text, img, pk.wkv_text, pk.wkv_img, attn.heads, out=self._kv_cache.get(ck))
+        kv._keepalive = (text, img)
+        self._kv_cache[ck] = kv
+        return kv
 
     # ------------------------------------------------------------------------------------------
     def _weights(self, attn, dtype, device):
@@ -190,7 +213,7 @@ class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):
         kv = None
         ck = None
         if self._kv_cache is not None:
-            ck = (text.data_ptr(), text._version, img.data_ptr(), img._version, tuple(text.shape), tuple(img.shape))
+            ck = self._kv_key(text, img)
             kv = self._kv_cache.get(ck)
         if kv is None:
             kv = ops.kv_pack(text, img, pk.wkv_text, pk.wkv_img, attn.heads)
@@ -199,5 +222,5 @@ class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):
                 self._kv_cache[ck] = kv
         y, _, _, _ = ops.dual_attn(x, pk.wq, kv, pk.wo, pk.bo, w_text, w_img)
         # side output (:397): [B, H, Li, 1] in the activation dtype
-        self.to_v_ip_norm = kv.v_ip_norm.to(dtype).unsqueeze(-1)
+        self.to_v_ip_norm = kv.vnorm_act
         return y

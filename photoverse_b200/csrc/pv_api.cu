@@ -210,6 +210,19 @@ int pv_dual_attn_fwd(pv_dtype dt, const void* X, const void* Wq, const void* Kp,
                   (long long)B * S, C, C, 1, C, C, C, 0, 0, 0, 0, st);
 }
 
+int pv_dual_attn_core_fwd(pv_dtype dt, const void* XorQ, const void* Wq, const void* Kp, const void* Vp, void* O,
+                          float* stats, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                          void* stream) {
+  PV_REQUIRE(XorQ && Kp && Vp && O, "null pointer");
+  if (dt == PV_BF16) {
+    PV_REQUIRE(Wq != nullptr, "PV_BF16 fuses the Q projection: Wq required");
+    return dual_attn_core_bf16(XorQ, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, as_stream(stream));
+  }
+  return dual_attn_core_f32(static_cast<const float*>(XorQ), static_cast<const float*>(Kp),
+                            static_cast<const float*>(Vp), static_cast<float*>(O), stats, B, S, C, H, Lt, Li, w_text,
+                            w_img, as_stream(stream));
+}
+
 int pv_ln_lrelu_fwd(pv_dtype out_dt, const float* x, const float* gamma, const float* beta, void* y, float* save_mean,
                     float* save_rstd, int64_t rows, int cols, int64_t ldx, int64_t ldy, int64_t rows_per_group,
                     float eps, float slope, void* stream) {

@@ -20,7 +20,8 @@ from typing import List, Optional
 
 import torch
 
-from ..unet import set_kv_cache
+from .. import _lib
+from ..unet import prepare_kv, set_kv_cache
 from .ddim import make_ddim_schedule
 
 
@@ -149,3 +150,113 @@ def synthetic_inputs(batch: int, latent: int = 64, tokens: int = 257, T: int = 5
         clip_u = [t.pin_memory() for t in clip_u]
     return GenInputs(clip, clip_u, rn(batch, 77, 768), rn(1, 77, 768).expand(batch, 77, 768).contiguous(),
                      rn(batch, 4, latent, latent))
+
+
+class GenerationEngine:
+    """Persistent generation state for repeated generations of one geometry (bench / serving loop):
+    static device buffers for the encoder outputs, statically addressed K/V caches refreshed once per generation,
+    and ONE captured CUDA graph of the UNet evaluation that every step of every generation replays.
+    ``generate()`` performs no host<->device synchronisation."""
+
+    def __init__(self, unet, image_adapter, text_adapter, batch: int, latent: int = 64, num_steps: int = 50,
+                 guidance_scale: float = 1.0, token_index=0, mode: str = "batched", dtype=torch.bfloat16,
+                 device="cuda", num_heads_T: int = 5, use_cuda_graph: bool = True):
+        assert mode in ("batched", "two_call", "cond_only")
+        if mode == "cond_only" and guidance_scale != 1.0:
+            raise ValueError("mode='cond_only' is only valid for guidance_scale == 1")
+        self.unet, self.image_adapter, self.text_adapter = unet, image_adapter, text_adapter
+        self.B, self.latent, self.num_steps, self.g = batch, latent, num_steps, float(guidance_scale)
+        self.token_index, self.mode, self.dtype, self.dev = token_index, mode, dtype, torch.device(device)
+        self.use_graph = use_cuda_graph
+        self.sched = make_ddim_schedule(num_steps)
+        self.ts_dev = torch.tensor(self.sched.timesteps, device=self.dev, dtype=torch.float32)
+        self.inp = synthetic_inputs(batch, latent, T=num_heads_T, seed=0, device=self.dev, dtype=dtype)
+        Li = 1 if (token_index is not None and token_index != "full") else num_heads_T
+        rows = 2 * batch if mode == "batched" else batch
+        nctx = 2 if mode == "two_call" else 1
+        self.ctx = [(torch.zeros(rows, 77, 768, device=self.dev, dtype=dtype),
+                     torch.zeros(rows, Li, 768, device=self.dev, dtype=dtype)) for _ in range(nctx)]
+        self.x_in = torch.zeros(rows, 4, latent, latent, device=self.dev, dtype=dtype)
+        self.t_in = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        self.graphs = None
+        self.outs = None
+        self.launches_per_eval = 0      # native kernels inside one captured UNet evaluation
+        self.replays = 0
+        set_kv_cache(unet, True, static=True)
+
+    def load_inputs(self, host_inputs: GenInputs):
+        """Host (pinned) -> static device buffers; asynchronous on the current stream."""
+        for dst, src in zip(self.inp.clip_hidden + self.inp.clip_hidden_uncond + [self.inp.text, self.inp.text_uncond, self.inp.noise],
+                            host_inputs.clip_hidden + host_inputs.clip_hidden_uncond
+                            + [host_inputs.text, host_inputs.text_uncond, host_inputs.noise]):
+            dst.copy_(src, non_blocking=True)
+
+    def _eval(self, j):
+        return self.unet(self.x_in, self.t_in, encoder_hidden_states=self.ctx[j]).sample
+
+    def _build_graphs(self):
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                for j in range(len(self.ctx)):
+                    self._eval(j)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        self.graphs, self.outs = [], []
+        for j in range(len(self.ctx)):
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                out = self._eval(j)
+            self.launches_per_eval = _lib.launch_count() - n0
+            self.graphs.append(g)
+            self.outs.append(out)
+
+    @torch.no_grad()
+    def generate(self) -> torch.Tensor:
+        inp, B = self.inp, self.B
+        # adapters once per generation (infer.py:89-91)
+        if self.text_adapter is not None:
+            self.concept_text = self.text_adapter(inp.clip_hidden, token_index=self.token_index)
+        img = self.image_adapter(inp.clip_hidden, token_index=self.token_index)
+        img_u = self.image_adapter(inp.clip_hidden_uncond, token_index=self.token_index)
+        if self.mode == "batched":
+            self.ctx[0][0][:B].copy_(inp.text_uncond); self.ctx[0][0][B:].copy_(inp.text)
+            self.ctx[0][1][:B].copy_(img_u); self.ctx[0][1][B:].copy_(img)
+        elif self.mode == "two_call":
+            self.ctx[0][0].copy_(inp.text_uncond); self.ctx[0][1].copy_(img_u)
+            self.ctx[1][0].copy_(inp.text); self.ctx[1][1].copy_(img)
+        else:
+            self.ctx[0][0].copy_(inp.text); self.ctx[0][1].copy_(img)
+        for c in self.ctx:
+            prepare_kv(self.unet, c[0], c[1])
+        if self.use_graph and self.graphs is None:
+            self._build_graphs()
+        latents = inp.noise * self.sched.init_noise_sigma
+        for i in range(self.num_steps):
+            self.t_in.copy_(self.ts_dev[i:i + 1])
+            if self.mode == "batched":
+                self.x_in[:B].copy_(latents); self.x_in[B:].copy_(latents)
+            else:
+                self.x_in.copy_(latents)
+            outs = []
+            for j in range(len(self.ctx)):
+                if self.use_graph:
+                    self.graphs[j].replay()
+                    self.replays += 1
+                    outs.append(self.outs[j])
+                else:
+                    outs.append(self._eval(j))
+            if self.mode == "batched":
+                eps_u, eps_c = outs[0][:B], outs[0][B:]
+                eps = eps_u + self.g * (eps_c - eps_u)
+            elif self.mode == "two_call":
+                eps = outs[0] + self.g * (outs[1] - outs[0])
+            else:
+                eps = outs[0]
+            latents = self.sched.c_x[i] * latents + self.sched.c_eps[i] * eps
+        return latents
+
+    def close(self):
+        set_kv_cache(self.unet, False)
+        self.graphs = None

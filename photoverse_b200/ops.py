@@ -100,28 +100,38 @@ def kv_tile_bytes(dtype: torch.dtype, C: int, H: int, Lt: int, Li: int) -> int:
 
 class PackedKV:
     """Device buffers produced by :func:`kv_pack` (owned by PyTorch)."""
-    __slots__ = ("Kp", "Vp", "v_ip_norm", "kv_text", "kv_img", "B", "Lt", "Li", "C", "H", "dtype", "_keepalive")
+    __slots__ = ("Kp", "Vp", "v_ip_norm", "kv_text", "kv_img", "B", "Lt", "Li", "C", "H", "dtype", "_keepalive", "vnorm_act")
 
 
-def kv_pack(text: torch.Tensor, img: torch.Tensor, wkv_text: torch.Tensor, wkv_img: torch.Tensor, H: int) -> PackedKV:
-    """text [B,Lt,Dc], img [B,Li,Dc], wkv_* [2C,Dc] (all the compute dtype) -> packed K/V tiles + ||V_img||."""
+def kv_pack(text: torch.Tensor, img: torch.Tensor, wkv_text: torch.Tensor, wkv_img: torch.Tensor, H: int,
+            out: Optional["PackedKV"] = None) -> PackedKV:
+    """text [B,Lt,Dc], img [B,Li,Dc], wkv_* [2C,Dc] (all the compute dtype) -> packed K/V tiles + ||V_img||.
+    ``out``: refresh an existing PackedKV of the same geometry in place (stable addresses for CUDA graphs)."""
     B, Lt, Dc = text.shape
     Li = img.shape[1]
     C = wkv_text.shape[0] // 2
     assert text.is_contiguous() and img.is_contiguous() and wkv_text.is_contiguous() and wkv_img.is_contiguous()
     assert text.dtype == img.dtype == wkv_text.dtype == wkv_img.dtype
     dev = text.device
-    kv = PackedKV()
-    kv.B, kv.Lt, kv.Li, kv.C, kv.H, kv.dtype = B, Lt, Li, C, H, text.dtype
-    tile = kv_tile_bytes(text.dtype, C, H, Lt, Li)
-    kv.Kp = torch.empty(B * H * tile, device=dev, dtype=torch.uint8)
-    kv.Vp = torch.empty(B * H * tile, device=dev, dtype=torch.uint8)
-    kv.kv_text = torch.empty(B * Lt, 2 * C, device=dev, dtype=torch.float32)
-    kv.kv_img = torch.empty(B * Li, 2 * C, device=dev, dtype=torch.float32)
-    kv.v_ip_norm = torch.empty(B, H, Li, device=dev, dtype=torch.float32)
+    if out is not None and (out.B, out.Lt, out.Li, out.C, out.H, out.dtype) == (B, Lt, Li, C, H, text.dtype):
+        kv = out
+    else:
+        kv = PackedKV()
+        kv.B, kv.Lt, kv.Li, kv.C, kv.H, kv.dtype = B, Lt, Li, C, H, text.dtype
+        tile = kv_tile_bytes(text.dtype, C, H, Lt, Li)
+        kv.Kp = torch.empty(B * H * tile, device=dev, dtype=torch.uint8)
+        kv.Vp = torch.empty(B * H * tile, device=dev, dtype=torch.uint8)
+        kv.kv_text = torch.empty(B * Lt, 2 * C, device=dev, dtype=torch.float32)
+        kv.kv_img = torch.empty(B * Li, 2 * C, device=dev, dtype=torch.float32)
+        kv.v_ip_norm = torch.empty(B, H, Li, device=dev, dtype=torch.float32)
     check(_lib.lib().pv_kv_pack_fwd(_dt(text), _ptr(text), _ptr(img), _ptr(wkv_text), _ptr(wkv_img),
                                     _ptr(kv.kv_text), _ptr(kv.kv_img), _ptr(kv.Kp), _ptr(kv.Vp), _ptr(kv.v_ip_norm),
                                     B, Lt, Li, Dc, C, H, _stream()), "pv_kv_pack_fwd")
+    # the processor's `to_v_ip_norm` side output in the activation dtype, [B,H,Li,1] (refreshed in place)
+    if getattr(kv, "vnorm_act", None) is None:
+        kv.vnorm_act = kv.v_ip_norm.to(text.dtype).unsqueeze(-1)
+    else:
+        kv.vnorm_act.copy_(kv.v_ip_norm.unsqueeze(-1))
     return kv
 
 

@@ -60,9 +60,17 @@ def set_cross_attention_layers_to_train(unet):
             module.train()
 
 
-def set_kv_cache(unet, enabled: bool):
+def set_kv_cache(unet, enabled: bool, static: bool = False):
     """Enable / clear / disable K/V-projection caching on every PhotoVerse processor of ``unet`` (used by the
     denoise loop: encoder_hidden_states are constant across steps, models/infer.py:89-98)."""
     for proc in unet.attn_processors.values():
         if isinstance(proc, PhotoVerseAttnProcessor2_0):
-            proc.enable_kv_cache(enabled)
+            proc.enable_kv_cache(enabled, static=static)
+
+
+def prepare_kv(unet, text, img):
+    """Project + pack K/V of every attn2 layer for the given (text, image) contexts (once per generation)."""
+    for m in unet.modules():
+        proc = getattr(m, "processor", None)
+        if isinstance(proc, PhotoVerseAttnProcessor2_0):
+            proc.prepare_kv(m, text, img)

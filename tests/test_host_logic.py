@@ -1,0 +1,144 @@
+"""CPU: host-side logic that mirrors the reference interface (constructor validation, names, installation,
+fusion-rule RNG consumption, LoRA injection, DDIM schedule)."""
+import pytest
+import torch
+
+import photoverse_b200 as pv
+from oracle import adapter_oracle, ref_loader
+from photoverse_b200.host.ddim import make_ddim_schedule
+from photoverse_b200.host.unet_sd15 import UNetSD15
+from photoverse_b200.lora import LoraLinear, inject_lora, linear_parts
+
+SD15_ATTN2 = (["down_blocks.%d.attentions.%d" % (i, j) for i in range(3) for j in range(2)]
+              + ["mid_block.attentions.0"] + ["up_blocks.%d.attentions.%d" % (i, j) for i in (1, 2, 3) for j in range(3)])
+
+
+def test_ctor_validation_matches_reference():
+    # attention_processor.py:37-48
+    with pytest.raises(ValueError, match="tuple of two floats"):
+        pv.PhotoVerseAttnProcessor2_0(320, 768, fusion_rules=[1 / 3, 2 / 3])
+    with pytest.raises(ValueError, match="tuple of two floats"):
+        pv.PhotoVerseAttnProcessor2_0(320, 768, fusion_rules=(1, 0))
+    with pytest.raises(ValueError, match="equal to 1"):
+        pv.PhotoVerseAttnProcessor2_0(320, 768, fusion_rules=(0.5, 0.6))
+    with pytest.raises(ValueError, match="same length"):
+        pv.PhotoVerseAttnProcessor2_0(320, 768, num_tokens=(5,), scale=[1.0, 2.0])
+    p = pv.PhotoVerseAttnProcessor2_0(hidden_size=640, cross_attention_dim=768, num_tokens=5)
+    assert p.num_tokens == [5] and p.scale == [2.0] and p.to_v_ip_norm is None
+    assert sorted(p.state_dict().keys()) == ["to_k_ip.0.weight", "to_v_ip.0.weight"]
+    assert p.to_k_ip[0].weight.shape == (640, 768) and p.to_k_ip[0].bias is None
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not mounted")
+def test_processor_state_dict_and_ctor_match_live_reference():
+    mod = ref_loader.load_reference_processor_module()
+    ref = mod.PhotoVerseAttnProcessor2_0(hidden_size=320, cross_attention_dim=768, num_tokens=(5,))
+    ours = pv.PhotoVerseAttnProcessor2_0(hidden_size=320, cross_attention_dim=768, num_tokens=(5,))
+    assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert (ref.scale, ref.fusion_rule1, ref.fusion_rule2, ref.num_tokens) == (ours.scale, ours.fusion_rule1, ours.fusion_rule2, ours.num_tokens)
+    for bad in (dict(fusion_rules=(0.5, 0.6)), dict(fusion_rules=[0.5, 0.5]), dict(scale=[1.0, 2.0])):
+        with pytest.raises(ValueError) as e_ref:
+            mod.PhotoVerseAttnProcessor2_0(320, 768, **bad)
+        with pytest.raises(ValueError) as e_ours:
+            pv.PhotoVerseAttnProcessor2_0(320, 768, **bad)
+        assert str(e_ref.value) == str(e_ours.value)
+
+
+def test_adapter_state_dict_names_match_reference_layout():
+    ad = pv.PhotoVerseAdapter(num_tokens=3)
+    want = adapter_oracle.make_state_dict(3, 1)
+    assert {k: tuple(v.shape) for k, v in ad.state_dict().items()} == {k: tuple(v.shape) for k, v in want.items()}
+    assert sum(p.numel() for p in pv.PhotoVerseAdapter(num_tokens=5).parameters()) == 28_904_960
+    if ref_loader.reference_available():
+        ref = ref_loader.load_reference_adapter_module().PhotoVerseAdapter(num_tokens=3)
+        assert list(ref.state_dict().keys()) == list(ad.state_dict().keys())
+
+
+def test_fusion_rule_consumes_exactly_one_rand_per_grad_call():
+    p = pv.PhotoVerseAttnProcessor2_0(320, 768)
+    torch.manual_seed(123)
+    expect = [torch.rand(1).item() for _ in range(4)]
+    torch.manual_seed(123)
+    with torch.enable_grad():
+        got = [p._fusion_weights() for _ in range(3)]
+    for u, w in zip(expect, got):
+        assert w == ((2.0, 0.0) if u < 1 / 3 else (0.0, 2.0) if u > 2 / 3 else (1.0, 1.0))
+    assert torch.rand(1).item() == expect[3]          # RNG stream stays aligned with the reference's
+    torch.manual_seed(123)
+    with torch.no_grad():
+        assert p._fusion_weights() == (1.0, 1.0)
+    assert torch.rand(1).item() == expect[0]          # no draw without grad (attention_processor.py:411)
+
+
+def test_install_on_sd15_unet_and_regulariser_gather():
+    unet = UNetSD15()
+    assert len(unet.attn_processors) == 32
+    pv.set_visual_cross_attention_adapter(unet, num_tokens=(5,))
+    procs = unet.attn_processors
+    attn2 = {k: v for k, v in procs.items() if k.endswith("attn2.processor")}
+    assert sorted(attn2) == sorted(f"{p}.transformer_blocks.0.attn2.processor" for p in SD15_ATTN2)
+    widths = {k: v.hidden_size for k, v in attn2.items()}
+    assert widths["down_blocks.0.attentions.0.transformer_blocks.0.attn2.processor"] == 320
+    assert widths["down_blocks.1.attentions.1.transformer_blocks.0.attn2.processor"] == 640
+    assert widths["mid_block.attentions.0.transformer_blocks.0.attn2.processor"] == 1280
+    assert widths["up_blocks.1.attentions.2.transformer_blocks.0.attn2.processor"] == 1280
+    assert widths["up_blocks.3.attentions.0.transformer_blocks.0.attn2.processor"] == 320
+    assert all(not isinstance(v, torch.nn.Module) for k, v in procs.items() if k.endswith("attn1.processor"))
+    # processor weights live in unet.state_dict() under the reference's key names (modeling_utils.py:33-37)
+    keys = [k for k in unet.state_dict() if "attn2" in k and ("processor" in k or "to_q" in k or "to_k" in k or "to_v" in k)]
+    assert "mid_block.attentions.0.transformer_blocks.0.attn2.processor.to_k_ip.0.weight" in keys
+    assert sum(unet.state_dict()[k].numel() for k in keys if "processor" in k) == 19_169_280
+    for i, p in enumerate(attn2.values()):
+        p.to_v_ip_norm = torch.full((2, 8, 5, 1), float(i))
+    g = pv.get_visual_cross_attention_values_norm(unet)
+    assert g.shape == (2, 16 * 8 * 5)
+    pv.set_cross_attention_layers_to_train(unet)
+    with pytest.raises(ValueError, match="number of processors"):
+        unet.set_attn_processor({"x": None})
+
+
+def test_unet_forward_shapes_cpu_tiny():
+    """Backbone wiring (skip connections, up/down sampling) on a 2-level variant with stock processors."""
+    unet = UNetSD15(block_out_channels=(32, 64), layers_per_block=1, heads=4, cross_attention_dim=16)
+    x = torch.randn(2, 4, 16, 16)
+    y = unet(x, torch.tensor([10.0]), encoder_hidden_states=torch.randn(2, 7, 16)).sample
+    assert y.shape == x.shape and torch.isfinite(y).all()
+
+
+def test_lora_injection_matches_peft_layout():
+    unet = UNetSD15(block_out_channels=(320, 640), layers_per_block=1)
+    pv.set_visual_cross_attention_adapter(unet)
+    inject_lora(unet, r=8, lora_alpha=1.0)
+    names = [n for n, m in unet.named_modules() if isinstance(m, LoraLinear)]
+    assert names and all(n.split(".")[-2] == "attn2" and n.split(".")[-1] in ("to_q", "to_k", "to_v") for n in names)
+    sd = unet.state_dict()
+    k = "mid_block.attentions.0.transformer_blocks.0.attn2.to_q"
+    assert f"{k}.base_layer.weight" in sd and f"{k}.lora_A.default.weight" in sd and f"{k}.lora_B.default.weight" in sd
+    assert sd[f"{k}.lora_A.default.weight"].shape == (8, 640) and sd[f"{k}.lora_B.default.weight"].abs().sum() == 0
+    trainable = [n for n, p in unet.named_parameters() if p.requires_grad]
+    assert trainable and all("lora_" in n for n in trainable)          # peft freezes the rest
+    w, A, B, s, p = linear_parts(unet.mid_block.attentions[0].transformer_blocks[0].attn2.to_q)
+    assert w.shape == (640, 640) and A.shape == (8, 640) and B.shape == (640, 8) and s == 1 / 8 and p == 0.0
+    n_lora = sum(p.numel() for n, p in UNetSD15_lora_params().items())
+    assert n_lora == 595_968                                            # SURVEY 8 a5 (r = 8, 16 layers)
+
+
+def UNetSD15_lora_params():
+    unet = UNetSD15()
+    inject_lora(unet, r=8)
+    return {n: p for n, p in unet.named_parameters() if "lora_" in n}
+
+
+def test_ddim_schedule():
+    s = make_ddim_schedule(50)
+    assert len(s.timesteps) == 50 and s.timesteps[0] == 981 and s.timesteps[-1] == 1
+    assert all(a > b for a, b in zip(s.timesteps, s.timesteps[1:]))
+    # one step with eps = 0 only rescales x; with the true noise it recovers x0 on the last step
+    import numpy as np
+    betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000) ** 2
+    ac = np.cumprod(1 - betas)
+    t = s.timesteps[-1]
+    x0, eps = 0.7, -1.3
+    xt = ac[t] ** 0.5 * x0 + (1 - ac[t]) ** 0.5 * eps
+    x_prev = s.c_x[-1] * xt + s.c_eps[-1] * eps
+    assert abs(x_prev - (ac[0] ** 0.5 * x0 + (1 - ac[0]) ** 0.5 * eps)) < 1e-9
