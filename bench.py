@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--mode", default="batched", choices=["batched", "two_call", "cond_only"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--nchw", action="store_true", help="keep the host UNet in NCHW (default: channels_last)")
     return ap.parse_args()
 
 
@@ -115,8 +116,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # model construction (identical seeds on both arms)
 # ------------------------------------------------------------------------------------------------------------
-def build_models(device, dtype, T=5):
+def build_models(device, dtype, T=5, channels_last=True):
     import photoverse_b200 as pv
+    torch.backends.cudnn.benchmark = True
     from photoverse_b200.host.unet_sd15 import UNetSD15
     torch.manual_seed(0)
     unet = UNetSD15()
@@ -127,6 +129,8 @@ def build_models(device, dtype, T=5):
         m.requires_grad_(False)
         m.eval()
         m.to(device=device, dtype=dtype)
+    if channels_last:      # host-model plumbing: NHWC activations for the cuDNN convolutions of the backbone
+        unet.to(memory_format=torch.channels_last)
     return unet, image_adapter, text_adapter
 
 
@@ -316,7 +320,7 @@ def main():
                     "sample": r["sample"], "denoise_step_s": round(r["denoise_step_s"], 3)}
 
     dtype = torch.bfloat16
-    unet, image_adapter, text_adapter = build_models(device, dtype)
+    unet, image_adapter, text_adapter = build_models(device, dtype, channels_last=not args.nchw)
     eng = GenerationEngine(unet, image_adapter, text_adapter, args.batch, args.latent, args.denoise_steps, 1.0,
                            token_index, args.mode, dtype, device, use_cuda_graph=not args.no_graph)
     host = pinned_inputs(args.batch, args.latent, seed=100 + rank, dtype=dtype)

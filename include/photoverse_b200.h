@@ -37,7 +37,9 @@ typedef enum { PV_F32 = 0, PV_BF16 = 1 } pv_dtype;
 
 /* Keys are zero-padded to this many rows per (sample, head) in the packed K/V tiles. */
 #define PV_KEYS_PAD 96
-/* Maximum text / image tokens the fused kernel supports: Lt + Li <= PV_KEYS_PAD. */
+/* PV_BF16 tiles: text keys occupy slots [0,Lt), image keys slots [PV_IMG_KEY_OFFSET, PV_IMG_KEY_OFFSET+Li).
+ * Limits of the fused kernel: 1 <= Lt <= 80 (CLIP: 77), 1 <= Li <= 16.                                    */
+#define PV_IMG_KEY_OFFSET 80
 
 int pv_version(void);
 const char* pv_last_error(void);
@@ -84,7 +86,7 @@ int pv_kv_pack_fwd(pv_dtype dt, const void* text, const void* img, const void* W
  * stats: optional [B,H,S,4] fp32 = (max_text, sum_text, max_img, sum_img) of the scaled logits, for backward
  * PV_BF16 path: ONE fused tcgen05 kernel does Q-projection -> QK^T over the concatenated keys -> per-segment
  * softmax with the branch weights folded in -> ONE PV contraction; a second tcgen05 GEMM applies Wo + bias.
- * Supported head dims: 40, 80, 160 (C = 320, 640, 1280 with H = 8); Lt + Li <= PV_KEYS_PAD; Li >= 1.          */
+ * Supported head dims: 40, 80, 160 (C = 320, 640, 1280 with H = 8); 1 <= Lt <= 80; 1 <= Li <= 16.                */
 int pv_dual_attn_fwd(pv_dtype dt, const void* X, const void* Wq, const void* Kp, const void* Vp, const void* Wo,
                      const float* bo, void* Y, float* ws_q, void* ws_o, float* stats, int B, int S, int C, int H,
                      int Lt, int Li, float w_text, float w_img, void* stream);

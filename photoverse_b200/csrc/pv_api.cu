@@ -170,6 +170,9 @@ int pv_kv_pack_fwd(pv_dtype dt, const void* text, const void* img, const void* W
   PV_REQUIRE(text && img && Wkv_text && Wkv_img && kv_text_ws && kv_img_ws && Kp && Vp && v_ip_norm, "null pointer");
   PV_REQUIRE(B > 0 && Lt >= 1 && Li >= 1 && Lt + Li <= PV_KEYS_PAD && C > 0 && H > 0 && C % H == 0 && Dc > 0,
              "bad shape B=%d Lt=%d Li=%d Dc=%d C=%d H=%d", B, Lt, Li, Dc, C, H);
+  PV_REQUIRE(dt != PV_BF16 || (Lt <= PV_IMG_KEY_OFFSET && Li <= PV_KEYS_PAD - PV_IMG_KEY_OFFSET),
+             "PV_BF16 tiles hold at most %d text and %d image keys (Lt=%d Li=%d)", PV_IMG_KEY_OFFSET,
+             PV_KEYS_PAD - PV_IMG_KEY_OFFSET, Lt, Li);
   cudaStream_t st = as_stream(stream);
   int rc;
   if (dt == PV_BF16) {

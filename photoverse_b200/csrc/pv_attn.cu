@@ -18,7 +18,8 @@
 //               segment softmax straight out of TMEM (all <=96 keys are resident: no online rescaling),
 //               branch weights and 1/rowsum folded into P (bf16, smem), drain O -> bf16 -> TMA store.
 //
-// Key layout inside the 96 padded key slots: [0,Lt) text, [Lt,Lt+Li) image, rest zero padding (masked).
+// Key layout inside the 96 padded key slots: [0,Lt) text (Lt <= 80), [80,80+Li) image (Li <= 16), the rest is
+// zero padding that the softmax masks to -inf (segment membership of a column is static).
 #include "pv_common.cuh"
 #include "pv_host.h"
 #include "../../include/photoverse_b200.h"
@@ -29,6 +30,7 @@ constexpr int AT_BM = 128;          // query rows per CTA
 constexpr int AT_BN = 160;          // channels (heads * head_dim) per CTA
 constexpr int AT_BK = 64;
 constexpr int AT_KEYS = PV_KEYS_PAD;  // 96
+constexpr int AT_IMG_OFF = PV_IMG_KEY_OFFSET;  // 80: first image-key slot
 constexpr int AT_STAGES = 4;
 constexpr int AT_THREADS = 192;
 constexpr int AT_A_BYTES = AT_BM * AT_BK * 2;              // 16384
@@ -260,25 +262,56 @@ dual_attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
 
     uint8_t* ost = smem + Cfg::OFF_OST + q * (32 * AT_BN * 2);   // this warp's [32 x 160] bf16 staging
     const int Lt = p.Lt;
-    const int L = p.Lt + p.Li;
+    const int Li = p.Li;
     const float cs = p.scale_log2e;
 
-    auto drain_o = [&](int j) {
+    // O_j: TMEM fp32 -> * row scale -> bf16 -> staging.  TMEM is read in the widest shapes that tile D.
+    auto drain_o = [&](int j, float oscale) {
       mbar_wait(&o_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t o_col = (j & 1) ? Cfg::TM_O1 : Cfg::TM_O0;
+      const uint32_t o_addr = tmem + lane_addr + ((j & 1) ? Cfg::TM_O1 : Cfg::TM_O0);
       uint8_t* dst = ost + lane * (AT_BN * 2) + j * (D * 2);
+      auto emit = [&](const uint32_t* v, int col0, int n) {
 #pragma unroll
-      for (int c = 0; c < D / 8; ++c) {
-        uint32_t v[8];
-        tmem_ld_x8(tmem + lane_addr + o_col + c * 8, v);
+        for (int c = 0; c < n / 8; ++c) {
+          const uint32_t* w = v + c * 8;
+          st_shared_v4(dst + (col0 / 8 + c) * 16,
+                       pack_bf16x2(__uint_as_float(w[0]) * oscale, __uint_as_float(w[1]) * oscale),
+                       pack_bf16x2(__uint_as_float(w[2]) * oscale, __uint_as_float(w[3]) * oscale),
+                       pack_bf16x2(__uint_as_float(w[4]) * oscale, __uint_as_float(w[5]) * oscale),
+                       pack_bf16x2(__uint_as_float(w[6]) * oscale, __uint_as_float(w[7]) * oscale));
+        }
+      };
+      if constexpr (D == 40) {
+        uint32_t a[32], c8[8];
+        tmem_ld_x32(o_addr, a);
+        tmem_ld_x8(o_addr + 32, c8);
         tmem_ld_wait();
-        store_chunk8(dst + c * 16, v);
+        emit(a, 0, 32);
+        emit(c8, 32, 8);
+      } else if constexpr (D == 80) {
+        uint32_t a[32], b2[32], c16[16];
+        tmem_ld_x32(o_addr, a);
+        tmem_ld_x32(o_addr + 32, b2);
+        tmem_ld_x16(o_addr + 64, c16);
+        tmem_ld_wait();
+        emit(a, 0, 32);
+        emit(b2, 32, 32);
+        emit(c16, 64, 16);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t a[32];
+          tmem_ld_x32(o_addr + c * 32, a);
+          tmem_ld_wait();
+          emit(a, c * 32, 32);
+        }
       }
       tc_fence_before();
       mbar_arrive(&o_free[j & 1]);
     };
 
+    float oscale_prev = 0.f;
 #pragma unroll 1
     for (int j = 0; j < HPC; ++j) {
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
@@ -293,49 +326,94 @@ dual_attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[i]);
       }
-      // segment maxima
-      float mt = -INFINITY, mi = -INFINITY;
+      // Static segments: columns [0,80) are the text keys, [80,96) the image keys; padding slots -> -inf.
+      if (Lt < 64) {                                   // uncommon short prompts (warp-uniform)
 #pragma unroll
-      for (int k = 0; k < AT_KEYS; ++k) {
-        if (k < Lt) mt = fmaxf(mt, s[k]);
-        else if (k < L) mi = fmaxf(mi, s[k]);
+        for (int k = 0; k < 64; ++k) s[k] = (k < Lt) ? s[k] : -INFINITY;
       }
+#pragma unroll
+      for (int k = 64; k < AT_IMG_OFF; ++k) s[k] = (k < Lt) ? s[k] : -INFINITY;
+#pragma unroll
+      for (int k = AT_IMG_OFF; k < AT_KEYS; ++k) s[k] = (k - AT_IMG_OFF < Li) ? s[k] : -INFINITY;
+      // segment maxima (4-way trees for ILP)
+      float m4[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+      for (int k = 4; k < AT_IMG_OFF; ++k) m4[k & 3] = fmaxf(m4[k & 3], s[k]);
+      const float mt = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      float i4[4] = {s[AT_IMG_OFF], s[AT_IMG_OFF + 1], s[AT_IMG_OFF + 2], s[AT_IMG_OFF + 3]};
+#pragma unroll
+      for (int k = AT_IMG_OFF + 4; k < AT_KEYS; ++k) i4[k & 3] = fmaxf(i4[k & 3], s[k]);
+      const float mi = fmaxf(fmaxf(i4[0], i4[1]), fmaxf(i4[2], i4[3]));
       const float mts = mt * cs, mis = mi * cs;
-      float lt = 0.f, li = 0.f;
+      // exponentials: one FFMA + one MUFU.EX2 per key; 8-key chunks that are entirely padding are skipped
+      float l4[4] = {0.f, 0.f, 0.f, 0.f}, li4[2] = {0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < AT_KEYS; ++k) {
-        float e;
-        if (k < Lt) { e = exp2f(fmaf(s[k], cs, -mts)); lt += e; }
-        else if (k < L) { e = exp2f(fmaf(s[k], cs, -mis)); li += e; }
-        else e = 0.f;
-        s[k] = e;
+      for (int kc = 0; kc < AT_IMG_OFF / 8; ++kc) {
+        if (kc * 8 < Lt) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e = fast_exp2(fmaf(s[kc * 8 + i], cs, -mts));
+            s[kc * 8 + i] = e;
+            l4[i & 3] += e;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[kc * 8 + i] = 0.f;
+        }
       }
-      const float at = p.w_text / lt;
-      const float ai = (p.Li > 0) ? p.w_img / li : 0.f;
+#pragma unroll
+      for (int kc = AT_IMG_OFF / 8; kc < AT_KEYS / 8; ++kc) {
+        if ((kc - AT_IMG_OFF / 8) * 8 < Li) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e = fast_exp2(fmaf(s[kc * 8 + i], cs, -mis));
+            s[kc * 8 + i] = e;
+            li4[i & 1] += e;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[kc * 8 + i] = 0.f;
+        }
+      }
+      const float lt = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      const float li = li4[0] + li4[1];
+      const float at = p.w_text / lt;                  // branch weight / row sum, text segment
+      const float ai = p.w_img / li;                   // image segment (Li >= 1 is enforced by the host)
       if (p.stats != nullptr && m0 + row < p.S) {
-        float4 st = make_float4(mts, lt, mis, li);
         const size_t idx = ((static_cast<size_t>(b) * p.H + (g * HPC + j)) * p.S + (m0 + row));
-        reinterpret_cast<float4*>(p.stats)[idx] = st;
+        reinterpret_cast<float4*>(p.stats)[idx] = make_float4(mts, lt, mis, li);
       }
+      // P = [e_text * ft | e_img * fi], O row scaled by `oscale` afterwards: the dominant segment stays unscaled
+      // (ft or fi == 1), saving one multiply per key.  w_text == 0 (image-only fusion branch) flips the roles.
+      float ft, fi, oscale;
+      if (p.w_text != 0.f) { ft = 1.f; fi = ai / at; oscale = at; }
+      else                 { ft = 0.f; fi = 1.f;     oscale = ai; }
       // P tile (bf16, K-major core matrices): chunk kc (8 keys) of row r at kc*2048 + r*16
       uint8_t* ptile = smem + Cfg::OFF_P + (j % Cfg::NPBUF) * Cfg::P_TILE_BYTES + row * 16;
+      if (ft == 1.f) {
 #pragma unroll
-      for (int kc = 0; kc < AT_KEYS / 8; ++kc) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = kc * 8 + i;
-          e[i] = s[k] * ((k < Lt) ? at : ai);
+        for (int kc = 0; kc < AT_IMG_OFF / 8; ++kc) {
+          const float* e = &s[kc * 8];
+          st_shared_v4(ptile + kc * (AT_BM * 16), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
+                       pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
         }
-        st_shared_v4(ptile + kc * (AT_BM * 16), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
-                     pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+      } else {
+#pragma unroll
+        for (int kc = 0; kc < AT_IMG_OFF / 8; ++kc) st_shared_v4(ptile + kc * (AT_BM * 16), 0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int kc = AT_IMG_OFF / 8; kc < AT_KEYS / 8; ++kc) {
+        const float* e = &s[kc * 8];
+        st_shared_v4(ptile + kc * (AT_BM * 16), pack_bf16x2(e[0] * fi, e[1] * fi), pack_bf16x2(e[2] * fi, e[3] * fi),
+                     pack_bf16x2(e[4] * fi, e[5] * fi), pack_bf16x2(e[6] * fi, e[7] * fi));
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_ready[j & 1]);
-      if (j >= 1) drain_o(j - 1);
+      if (j >= 1) drain_o(j - 1, oscale_prev);
+      oscale_prev = oscale;
     }
-    drain_o(HPC - 1);
+    drain_o(HPC - 1, oscale_prev);
 
     // ---- O tile -> HBM: each warp stores its own [32 rows x 160 channels] slab; TMA clips rows >= S ----
     fence_proxy_async_smem();
@@ -382,7 +460,8 @@ int dual_attn_core_bf16(const void* X, const void* Wq, const void* Kp, const voi
   const int d = C / H;
   PV_REQUIRE(d == 40 || d == 80 || d == 160, "head_dim %d unsupported (40/80/160)", d);
   PV_REQUIRE(C % AT_BN == 0 && C % AT_BK == 0, "C=%d must be a multiple of 320", C);
-  PV_REQUIRE(Lt >= 1 && Li >= 1 && Lt + Li <= AT_KEYS, "need 1 <= Lt, 1 <= Li, Lt+Li <= %d (Lt=%d Li=%d)", AT_KEYS, Lt, Li);
+  PV_REQUIRE(Lt >= 1 && Lt <= AT_IMG_OFF && Li >= 1 && Li <= AT_KEYS - AT_IMG_OFF,
+             "need 1 <= Lt <= %d and 1 <= Li <= %d (Lt=%d Li=%d)", AT_IMG_OFF, AT_KEYS - AT_IMG_OFF, Lt, Li);
   PV_REQUIRE(B <= 65535 && (S + AT_BM - 1) / AT_BM <= 65535, "grid too large");
   PV_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wq) | reinterpret_cast<uintptr_t>(Kp) |
               reinterpret_cast<uintptr_t>(Vp) | reinterpret_cast<uintptr_t>(O)) % 16 == 0, "pointers must be 16-byte aligned");

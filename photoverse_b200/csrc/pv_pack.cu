@@ -59,10 +59,11 @@ int pack_weight(bool out_bf16, const float* W, const float* A, const float* Bm, 
 // Kp[b][h] : K-major core-matrix image of K_h  [96 keys  x d_pad]: chunk kc (8 dims) of key r at (kc*96   + r)*16 B
 // Vp[b][h] : K-major core-matrix image of V_h^T [d_pad   x 96   ]: chunk kc (8 keys) of dim n at (kc*d_pad + n)*16 B
 // ------------------------------------------------------------------------------------------------
+// `img_off`: slot of the first image key (PV_IMG_KEY_OFFSET in the padded bf16 tiles, Lt in the compact fp32 layout)
 __device__ __forceinline__ float kv_fetch(const float* __restrict__ kv_text, const float* __restrict__ kv_img, int b,
-                                          int key, int col, int Lt, int Li, int C2) {
+                                          int key, int col, int Lt, int Li, int C2, int img_off) {
   if (key < Lt) return kv_text[(static_cast<size_t>(b) * Lt + key) * C2 + col];
-  if (key < Lt + Li) return kv_img[(static_cast<size_t>(b) * Li + (key - Lt)) * C2 + col];
+  if (key >= img_off && key < img_off + Li) return kv_img[(static_cast<size_t>(b) * Li + (key - img_off)) * C2 + col];
   return 0.f;
 }
 
@@ -83,7 +84,7 @@ kv_pack_bf16_kernel(const float* __restrict__ kv_text, const float* __restrict__
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int dim = kc * 8 + i;
-      v[i] = (dim < d) ? kv_fetch(kv_text, kv_img, b, key, h * d + dim, Lt, Li, C2) : 0.f;
+      v[i] = (dim < d) ? kv_fetch(kv_text, kv_img, b, key, h * d + dim, Lt, Li, C2, PV_IMG_KEY_OFFSET) : 0.f;
     }
     *reinterpret_cast<uint4*>(kt + static_cast<size_t>(idx) * 16) =
         make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -95,7 +96,7 @@ kv_pack_bf16_kernel(const float* __restrict__ kv_text, const float* __restrict__
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int key = kc * 8 + i;
-      v[i] = (dim < d) ? kv_fetch(kv_text, kv_img, b, key, C + h * d + dim, Lt, Li, C2) : 0.f;
+      v[i] = (dim < d) ? kv_fetch(kv_text, kv_img, b, key, C + h * d + dim, Lt, Li, C2, PV_IMG_KEY_OFFSET) : 0.f;
     }
     *reinterpret_cast<uint4*>(vt + static_cast<size_t>(idx) * 16) =
         make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -118,8 +119,8 @@ kv_pack_f32_kernel(const float* __restrict__ kv_text, const float* __restrict__ 
   float* vt = Vp + (static_cast<size_t>(b) * H + h) * L * d;
   for (int idx = threadIdx.x; idx < L * d; idx += blockDim.x) {
     const int key = idx / d, dim = idx % d;
-    kt[idx] = kv_fetch(kv_text, kv_img, b, key, h * d + dim, Lt, Li, C2);
-    vt[idx] = kv_fetch(kv_text, kv_img, b, key, C + h * d + dim, Lt, Li, C2);
+    kt[idx] = kv_fetch(kv_text, kv_img, b, key, h * d + dim, Lt, Li, C2, Lt);
+    vt[idx] = kv_fetch(kv_text, kv_img, b, key, C + h * d + dim, Lt, Li, C2, Lt);
   }
   for (int li = threadIdx.x; li < Li; li += blockDim.x) {
     const float* row = kv_img + (static_cast<size_t>(b) * Li + li) * C2 + C + h * d;

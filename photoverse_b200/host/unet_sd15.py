@@ -123,7 +123,7 @@ class Transformer2DModel(nn.Module):
         h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
         for blk in self.transformer_blocks:
             h = blk(h, encoder_hidden_states)
-        h = h.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+        h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)      # NHWC-strided view: free under channels_last
         return self.proj_out(h) + res
 
 
