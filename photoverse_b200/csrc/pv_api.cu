@@ -19,6 +19,8 @@ int gemm_f32(const float* A, const float* W, const float* bias, float* D, long l
              long long strideBias, long long strideD, cudaStream_t stream);
 int dual_attn_core_bf16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
                         int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
+int dual_attn_core_bf16_ts(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
+                           int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
 int dual_attn_core_f32(const float* Q, const float* Kp, const float* Vp, float* O, float* stats, int B, int S, int C,
                        int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
 int64_t attn_kv_tile_bytes(int d);
@@ -36,6 +38,8 @@ int group_mean(bool in_bf16, bool out_bf16, const void* x, void* y, long long gr
 std::atomic<unsigned long long> g_launches{0};
 int g_opt_epi_swizzle = 1;
 int g_opt_force_bn = 0;
+int g_opt_gemm_two_cta = 1;
+int g_opt_attn_variant = 2;   // 1: operands staged in smem (pv_attn.cu)   2: operands in TMEM, 2 CTAs/SM (pv_attn2.cu)
 static thread_local std::string t_error;
 
 void set_error(const std::string& msg) { t_error = msg; }
@@ -122,6 +126,12 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0
 
 static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
+static int attn_core_bf16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
+                          int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t st) {
+  if (g_opt_attn_variant == 1) return dual_attn_core_bf16(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+  return dual_attn_core_bf16_ts(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+}
+
 }  // namespace pv
 
 using namespace pv;
@@ -136,6 +146,8 @@ int pv_set_option(const char* name, int value) {
   if (!name) PV_FAIL(PV_ERR_INVALID, "null option name");
   if (!strcmp(name, "epi_swizzle")) { g_opt_epi_swizzle = value; return PV_OK; }
   if (!strcmp(name, "force_bn")) { g_opt_force_bn = value; return PV_OK; }
+  if (!strcmp(name, "gemm_two_cta")) { g_opt_gemm_two_cta = value; return PV_OK; }
+  if (!strcmp(name, "attn_variant")) { g_opt_attn_variant = value; return PV_OK; }
   PV_FAIL(PV_ERR_INVALID, "unknown option '%s'", name);
 }
 
@@ -198,7 +210,7 @@ int pv_dual_attn_fwd(pv_dtype dt, const void* X, const void* Wq, const void* Kp,
   cudaStream_t st = as_stream(stream);
   int rc;
   if (dt == PV_BF16) {
-    rc = dual_attn_core_bf16(X, Wq, Kp, Vp, ws_o, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+    rc = attn_core_bf16(X, Wq, Kp, Vp, ws_o, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
     if (rc) return rc;
     return gemm_bf16(ws_o, Wo, bo, Y, false, (long long)B * S, C, C, 1, C, C, C, 0, 0, 0, 0, st);
   }
@@ -219,7 +231,7 @@ int pv_dual_attn_core_fwd(pv_dtype dt, const void* XorQ, const void* Wq, const v
   PV_REQUIRE(XorQ && Kp && Vp && O, "null pointer");
   if (dt == PV_BF16) {
     PV_REQUIRE(Wq != nullptr, "PV_BF16 fuses the Q projection: Wq required");
-    return dual_attn_core_bf16(XorQ, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, as_stream(stream));
+    return attn_core_bf16(XorQ, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, as_stream(stream));
   }
   return dual_attn_core_f32(static_cast<const float*>(XorQ), static_cast<const float*>(Kp),
                             static_cast<const float*>(Vp), static_cast<float*>(O), stats, B, S, C, H, Lt, Li, w_text,

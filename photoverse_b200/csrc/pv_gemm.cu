@@ -22,11 +22,15 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
 
-template <int BN>
+// STAGES_ == 0: deep ring, one CTA per SM (long K).  STAGES_ == 2: shallow ring so that TWO CTAs fit per SM
+// (<= 113 KB smem, <= 256 TMEM columns each): with short K (the C=320 projections have 5 K-blocks) a tile is
+// dominated by its prologue / epilogue, which the second resident CTA overlaps with its own main loop.
+template <int BN, int STAGES_>
 struct GemmCfg {
   static constexpr int W_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + W_BYTES;
-  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 160 ? 5 : 6);
+  static constexpr int STAGES = STAGES_ > 0 ? STAGES_ : (BN >= 256 ? 4 : (BN >= 160 ? 5 : 6));
+  static constexpr int MIN_CTAS = STAGES_ == 2 ? 2 : 1;
   static constexpr int EPI_TILE_BYTES = 32 * 128;          // per warp per buffer (fp32: 32x32x4, bf16 uses half)
   static constexpr int EPI_BYTES = 4 * 2 * EPI_TILE_BYTES;  // 4 warps, double buffered
   static constexpr int BAR_BYTES = 256;
@@ -34,12 +38,12 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
 };
 
-template <int BN, bool OUT_F32, bool EPI_SWZ>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int STAGES_, bool OUT_F32, bool EPI_SWZ>
+__global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ == 2 ? 2 : 1))
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                          const __grid_constant__ CUtensorMap tmD, const float* __restrict__ bias,
                          long long strideBias, int N, int K, int w_batched) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, STAGES_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -179,11 +183,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 extern int g_opt_epi_swizzle;
 extern int g_opt_force_bn;
 
-template <int BN, bool OUT_F32, bool EPI_SWZ>
+template <int BN, int STAGES_, bool OUT_F32, bool EPI_SWZ>
 static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD, const float* bias,
                       long long strideBias, int M, int N, int K, int batch, int w_batched, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, OUT_F32, EPI_SWZ>;
+  using Cfg = GemmCfg<BN, STAGES_>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES_, OUT_F32, EPI_SWZ>;
   static bool attr_done = false;
   if (!attr_done) {
     PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -195,23 +199,29 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUte
   return PV_OK;
 }
 
+extern int g_opt_gemm_two_cta;
+
 template <int BN>
 static int launch_bn(bool out_f32, bool swz, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD,
                      const float* bias, long long strideBias, int M, int N, int K, int batch, int w_batched,
                      cudaStream_t stream) {
-  if (out_f32) {
-    return swz ? launch_one<BN, true, true>(tmA, tmW, tmD, bias, strideBias, M, N, K, batch, w_batched, stream)
-               : launch_one<BN, true, false>(tmA, tmW, tmD, bias, strideBias, M, N, K, batch, w_batched, stream);
+  // short K (<= 8 K-blocks): shallow ring, two CTAs per SM; the un-swizzled staging variant is kept for the
+  // deep-ring bf16-out kernel only (A/B switch `epi_swizzle`, validated identical on B200)
+  const bool two = g_opt_gemm_two_cta != 0 && (K + GEMM_BK - 1) / GEMM_BK <= 8;
+  if (two) {
+    return out_f32 ? launch_one<BN, 2, true, true>(tmA, tmW, tmD, bias, strideBias, M, N, K, batch, w_batched, stream)
+                   : launch_one<BN, 2, false, true>(tmA, tmW, tmD, bias, strideBias, M, N, K, batch, w_batched, stream);
   }
-  return swz ? launch_one<BN, false, true>(tmA, tmW, tmD, bias, strideBias, M, N, K, batch, w_batched, stream)
-             : launch_one<BN, false, false>(tmA, tmW, tmD, bias, strideBias, M, N, K, batch, w_batched, stream);
+  if (out_f32) return launch_one<BN, 0, true, true>(tmA, tmW, tmD, bias, strideBias, M, N, K, batch, w_batched, stream);
+  return swz ? launch_one<BN, 0, false, true>(tmA, tmW, tmD, bias, strideBias, M, N, K, batch, w_batched, stream)
+             : launch_one<BN, 0, false, false>(tmA, tmW, tmD, bias, strideBias, M, N, K, batch, w_batched, stream);
 }
 
-static int pick_bn(long long M, long long N, long long batch) {
+static int pick_bn(long long M, long long N, long long batch, bool two_cta) {
   if (g_opt_force_bn == 64 || g_opt_force_bn == 128 || g_opt_force_bn == 160 || g_opt_force_bn == 256)
     return g_opt_force_bn;
   const int cands[4] = {256, 160, 128, 64};
-  const long long sms = sm_count();
+  const long long sms = static_cast<long long>(sm_count()) * (two_cta ? 2 : 1);   // resident CTA slots
   long long best_cost = -1;
   int best = 128;
   for (int bn : cands) {
@@ -240,8 +250,9 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* D, bool out
   PV_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(D)) % 16 == 0,
              "pointers must be 16-byte aligned");
   PV_REQUIRE(batch <= 65535 && (M + GEMM_BM - 1) / GEMM_BM <= 65535, "grid too large");
-  const int bn = pick_bn(M, N, batch);
-  const bool swz = g_opt_epi_swizzle != 0;
+  const bool two_cta = g_opt_gemm_two_cta != 0 && (K + GEMM_BK - 1) / GEMM_BK <= 8;
+  const int bn = pick_bn(M, N, batch, two_cta);
+  const bool swz = g_opt_epi_swizzle != 0 || out_f32 || two_cta;
   const int w_batched = strideW != 0;
   CUtensorMap tmA, tmW, tmD;
   // batch stride 0 is not encodable: give un-batched operands a dummy stride with extent 1

@@ -202,3 +202,29 @@ def test_kv_cache_reuses_projection(cuda_device):
         proc.enable_kv_cache(False)
     assert torch.equal(y0, y1) and torch.equal(y1, y2)
     assert n1 - n0 == 2, f"cached call should launch attention + out-proj only, launched {n1 - n0}"
+
+
+@pytest.mark.parametrize("variant", [1, 2], ids=["smem-operands", "tmem-operands"])
+@pytest.mark.parametrize("S,C,Li,wt,wi", [(384, 320, 5, 1.0, 1.0), (200, 640, 16, 1.0, 1.0), (128, 1280, 1, 1.0, 1.0),
+                                          (256, 320, 3, 2.0, 0.0), (256, 640, 5, 0.0, 2.0)])
+def test_attention_kernel_variants(cuda_device, variant, S, C, Li, wt, wi):
+    """Both fused-kernel variants (A operands staged in shared memory / kept in tensor memory) vs the oracle."""
+    from photoverse_b200 import _lib
+    case = cases.ProcCase(f"var_{S}_{C}", B=2, S=S, C=C, Li=Li, seed=60 + Li, w_text=wt, w_img=wi)
+    _lib.set_option("attn_variant", variant)
+    try:
+        attn, proc = build_product_layer(case, cuda_device)
+        for p_ in attn.parameters():
+            p_.requires_grad_(False)
+        x, text, img = cases.proc_inputs(case, torch.float32)
+        force_fusion_seed(wt, wi)
+        with torch.enable_grad():
+            y = attn(x.to(cuda_device, torch.bfloat16), encoder_hidden_states=(text.to(cuda_device, torch.bfloat16),
+                                                                              img.to(cuda_device, torch.bfloat16)))
+        with torch.no_grad():
+            w = cases.proc_weights(case).to(device=cuda_device)
+            y_ref, _ = dual_branch_attention(x.to(cuda_device), text.to(cuda_device), img.to(cuda_device), w, wt, wi)
+        err = (y.float() - y_ref).abs().max().item()
+        assert err <= 2e-2, f"variant {variant}: max-abs {err}"
+    finally:
+        _lib.set_option("attn_variant", 2)
