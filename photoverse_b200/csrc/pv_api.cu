@@ -21,6 +21,9 @@ int dual_attn_core_bf16(const void* X, const void* Wq, const void* Kp, const voi
                         int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
 int dual_attn_core_bf16_ts(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
                            int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
+int dual_attn_core_bf16_persistent(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
+                                   int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                                   cudaStream_t stream);
 int dual_attn_core_f32(const float* Q, const float* Kp, const float* Vp, float* O, float* stats, int B, int S, int C,
                        int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
 int64_t attn_kv_tile_bytes(int d);
@@ -39,7 +42,9 @@ std::atomic<unsigned long long> g_launches{0};
 int g_opt_epi_swizzle = 1;
 int g_opt_force_bn = 0;
 int g_opt_gemm_two_cta = 1;
-int g_opt_attn_variant = 2;   // 1: operands staged in smem (pv_attn.cu)   2: operands in TMEM, 2 CTAs/SM (pv_attn2.cu)
+// 1: operands staged in smem (pv_attn.cu)   2: operands in TMEM, 2 CTAs/SM (pv_attn2.cu)
+// 3: persistent, projection / attention / softmax pipelined against each other (pv_attn3.cu)
+int g_opt_attn_variant = 3;
 static thread_local std::string t_error;
 
 void set_error(const std::string& msg) { t_error = msg; }
@@ -129,6 +134,8 @@ static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>
 static int attn_core_bf16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
                           int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t st) {
   if (g_opt_attn_variant == 1) return dual_attn_core_bf16(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+  if (g_opt_attn_variant == 3)
+    return dual_attn_core_bf16_persistent(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
   return dual_attn_core_bf16_ts(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
 }
 
