@@ -47,6 +47,9 @@ const char* pv_last_error(void);
 unsigned long long pv_launch_count(void);
 /* Runtime switches for A/B testing kernel variants (name -> int). Unknown names return PV_ERR_INVALID. */
 int pv_set_option(const char* name, int value);
+/* Debug only: device buffer of 4 + 3*capacity uint64 (zeroed by the caller) that CTA 0 of the persistent attention
+ * kernel fills with (event, index, SM clock) triples; NULL switches tracing off.                                */
+int pv_debug_trace(void* buf, int capacity_events);
 
 /* ---- weights ---------------------------------------------------------------------------------------
  * W_eff[out,in] = W[out,in] + scaling * B[out,r] * A[r,in]   (peft lora.Linear merged form; r == 0 -> cast)

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "pv_last_error": (c_char_p, []),
     "pv_launch_count": (c_ulonglong, []),
     "pv_set_option": (c_int, [c_char_p, c_int]),
+    "pv_debug_trace": (c_int, [c_void_p, c_int]),
     "pv_pack_weight": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pv_linear_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 11 + [c_void_p]),
     "pv_kv_tile_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),

@@ -45,6 +45,10 @@ int g_opt_gemm_two_cta = 1;
 // 1: operands staged in smem (pv_attn.cu)   2: operands in TMEM, 2 CTAs/SM (pv_attn2.cu)
 // 3: persistent, projection / attention / softmax pipelined against each other (pv_attn3.cu)
 int g_opt_attn_variant = 3;
+int g_opt_attn3_stages = 0;
+unsigned long long* g_attn3_trace = nullptr;   // debug timeline buffer (pv_debug_trace)
+int g_attn3_trace_cap = 0;
+int g_opt_attn3_dbg = 0;       // timing experiments on the persistent kernel (results are wrong when != 0)
 static thread_local std::string t_error;
 
 void set_error(const std::string& msg) { t_error = msg; }
@@ -155,7 +159,15 @@ int pv_set_option(const char* name, int value) {
   if (!strcmp(name, "force_bn")) { g_opt_force_bn = value; return PV_OK; }
   if (!strcmp(name, "gemm_two_cta")) { g_opt_gemm_two_cta = value; return PV_OK; }
   if (!strcmp(name, "attn_variant")) { g_opt_attn_variant = value; return PV_OK; }
+  if (!strcmp(name, "attn3_dbg")) { g_opt_attn3_dbg = value; return PV_OK; }
+  if (!strcmp(name, "attn3_stages")) { g_opt_attn3_stages = value; return PV_OK; }
   PV_FAIL(PV_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int pv_debug_trace(void* buf, int capacity_events) {
+  g_attn3_trace = static_cast<unsigned long long*>(buf);
+  g_attn3_trace_cap = buf ? capacity_events : 0;
+  return PV_OK;
 }
 
 int pv_pack_weight(pv_dtype out_dt, const float* W, const float* lora_A, const float* lora_B, float scaling,

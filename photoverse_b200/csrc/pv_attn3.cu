@@ -16,11 +16,9 @@
 //   warps 8..11   softmax group 1   odd heads : O drained -> scaled -> bf16 -> HBM; both groups convert Q to bf16
 //
 // TMEM (512 columns): two 160-column slots (Q accumulator of unit i, i+1; after conversion the slot holds the packed
-// bf16 Q and the O accumulator) + two 96-column S/P buffers (one per softmax group):
-//            slot s = [160 s, 160 s + 160)                       S/P buffers
-//   d=40     Q bf16 4 x 24 = [0,96)    O [96,144)                [320,416) [416,512)
-//   d=80     Q bf16 2 x 40 = [0,80)    O [80,160)                [320,416) [416,512)
-//   d=160    Q bf16 80     = [0,80)    O dims 0..79 [80,160)     [320,416) ; O dims 80..159 at [416,496)
+// bf16 Q and, once the QK^T MMAs have consumed it, the O accumulators -- column maps in Attn3Cfg) + two 96-column
+// S/P buffers at [320,416) and [416,512), one per softmax group.  Each group drains its O accumulator only after
+// computing its NEXT softmax, so the PV MMA latency is hidden.
 #include "pv_common.cuh"
 #include "pv_host.h"
 #include "../../include/photoverse_b200.h"
@@ -37,7 +35,8 @@ constexpr int A3_THREADS = A3_WARPS * 32;
 constexpr int A3_A_BYTES = A3_BM * A3_BK * 2;
 constexpr int A3_W_BYTES = A3_BN * A3_BK * 2;
 constexpr int A3_STAGE_BYTES = A3_A_BYTES + A3_W_BYTES;
-constexpr int A3_STAGES = 4;
+constexpr int A3_STAGES = 3;        // measured on B200: 3, 4, 5 stages give the same projection-pipeline rate
+constexpr int A3_MAX_STAGES = 6;    // timing experiments only (dbg >= 4 lets the ring spill into the unused K/V area)
 
 template <int D>
 struct Attn3Cfg {
@@ -47,13 +46,22 @@ struct Attn3Cfg {
   static constexpr int KV_TILE_BYTES = A3_KEYS * D_PAD * 2;
   static constexpr int KV_BYTES = HPC * 2 * KV_TILE_BYTES;
   static constexpr int OFF_KV = A3_STAGES * A3_STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_KV + KV_BYTES;
+  static constexpr int OW = (D == 160) ? 80 : D;                 // channels per O staging tile / TMA store
+  static constexpr int OST_WARP_BYTES = 32 * OW * 2;             // one [32 rows x OW] bf16 tile per softmax warp
+  static constexpr int OFF_OST = OFF_KV + KV_BYTES;
+  static constexpr int OFF_BAR = OFF_OST + 8 * OST_WARP_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static constexpr uint32_t TM_SBUF0 = 320;
   static constexpr uint32_t TM_SBUF1 = 416;
-  static constexpr uint32_t TM_O_OFF = (D == 40) ? 96 : 80;     // inside the slot
-  static constexpr uint32_t TM_OHI = 416;                        // d = 160 only
+  // Column maps inside a 160-column slot.  The packed bf16 Q of head j is written INSIDE the fp32 columns the
+  // converting softmax group has just read (no cross-group hazard); the O accumulator of group w re-uses columns
+  // whose Q has already been consumed by the (in-order) QK^T MMAs issued before the first PV of the unit.
+  //   d=40 : fp32 Q_j [40j,40j+40)  -> bf16 Q_j [40j+16,40j+40)   O(w) = [48w, 48w+48)
+  //   d=80 : fp32 Q_j [80j,80j+80)  -> bf16 Q_j [80j+40,80j+80)   O(w) = [80w, 80w+80)
+  //   d=160: fp32 Q   [0,160)       -> bf16 Q   [40,120)          O    = [0,160) (two N=80 halves)
+  __host__ __device__ static constexpr uint32_t q_col(int j) { return D == 40 ? 40 * j + 16 : D == 80 ? 80 * j + 40 : 40; }
+  __host__ __device__ static constexpr uint32_t o_col(int w) { return D == 40 ? 48 * w : D == 80 ? 80 * w : 0; }
 };
 
 struct Attn3Params {
@@ -65,6 +73,10 @@ struct Attn3Params {
   int G, MT;               // head groups per sample (C/160), row tiles per sample
   long long units;         // B * G * MT
   float w_text, w_img, scale_log2e;
+  int dbg_stages;
+  unsigned long long* trace;   // optional [1 + 3*n] event buffer (CTA 0 only): count, then (event, index, clock) triples
+  int trace_cap;
+  int dbg;                 // timing experiments only (pv_set_option attn3_dbg): 1 no softmax math, 2 + no S load / O store, 3 + no Q conversion
 };
 
 template <int N>
@@ -73,10 +85,84 @@ __device__ __forceinline__ void pack_pairs3(const uint32_t* v, uint32_t* out) {
   for (int i = 0; i < N / 2; ++i) out[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
 }
 
-template <int D>
+// A drained-later O accumulator of one softmax group (the PV MMA runs while the group computes its next softmax).
+struct PendingO {
+  uint32_t taddr;          // TMEM address (lane quarter included) of the O accumulator
+  float oscale;
+  uint32_t parity;         // phase parity of o_full[wg]
+  int c0, r0, b;           // TMA store coordinates: first channel, first row of this warp's 32-row slab, sample
+  int slot;
+  bool valid;
+};
+
+// Debug timeline: lane 0 of a role warp of CTA 0 appends (event, index, SM clock) to the role's private region of the
+// trace buffer (no atomics: the stores are fire-and-forget).  Off (trace == nullptr) in production.
+struct A3Trace {
+  unsigned long long* base;
+  int n, cap;
+};
+__device__ __forceinline__ A3Trace a3_trace_init(const Attn3Params& p, int role) {
+  A3Trace t;
+  const int per = p.trace_cap / 4;
+  t.base = (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? p.trace + 4 + static_cast<size_t>(role) * per * 3 : nullptr;
+  t.n = 0;
+  t.cap = per;
+  return t;
+}
+__device__ __forceinline__ void a3_trace(A3Trace& t, int ev, int idx) {
+  if (t.base != nullptr && t.n < t.cap) {
+    t.base[3 * t.n] = static_cast<unsigned long long>(ev);
+    t.base[3 * t.n + 1] = static_cast<unsigned long long>(idx);
+    t.base[3 * t.n + 2] = static_cast<unsigned long long>(clock64());
+    ++t.n;
+  }
+}
+__device__ __forceinline__ void a3_trace_done(const Attn3Params& p, const A3Trace& t, int role) {
+  if (t.base != nullptr) p.trace[role] = static_cast<unsigned long long>(t.n);
+}
+
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 -- half the issue slots of the scalar forms)
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 32 consecutive TMEM columns of this thread's lane into r[0..31] (no wait)
+__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int D, bool LT77>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
-                                const Attn3Params p) {
+                                const __grid_constant__ CUtensorMap tmO, const Attn3Params p) {
   using Cfg = Attn3Cfg<D>;
   constexpr int HPC = Cfg::HPC;
   constexpr int D_PAD = Cfg::D_PAD;
@@ -85,28 +171,30 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
   uint8_t* kv = smem + Cfg::OFF_KV;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full = bars;                        // [STAGES]  TMA -> projection MMA
-  uint64_t* empty = full + A3_STAGES;           // [STAGES]
-  uint64_t* kv_full = empty + A3_STAGES;        // 1
+  uint64_t* empty = full + A3_MAX_STAGES;       // [STAGES]
+  uint64_t* kv_full = empty + A3_MAX_STAGES;    // 1
   uint64_t* kv_free = kv_full + 1;              // 1
   uint64_t* q_full = kv_free + 1;               // [2] projection MMA -> softmax groups (Q accumulator complete)
   uint64_t* q_ready = q_full + 2;               // [2] softmax groups -> attention MMA (packed bf16 Q in TMEM)
-  uint64_t* slot_free = q_ready + 2;            // [2] softmax group -> projection MMA (slot fully consumed)
+  uint64_t* slot_free = q_ready + 2;            // [2] softmax groups -> projection MMA (slot fully consumed)
   uint64_t* s_full = slot_free + 2;             // [2] per softmax group
   uint64_t* p_ready = s_full + 2;               // [2]
   uint64_t* o_full = p_ready + 2;               // [2]
-  uint64_t* o_free = o_full + 2;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kblocks = p.C / A3_BK;
+  const int nst_max = Cfg::OFF_BAR / A3_STAGE_BYTES < A3_MAX_STAGES ? Cfg::OFF_BAR / A3_STAGE_BYTES : A3_MAX_STAGES;
+  const int nst = (p.dbg >= 4 && p.dbg_stages > 0) ? (p.dbg_stages < nst_max ? p.dbg_stages : nst_max) : A3_STAGES;
   const int u0 = static_cast<int>((p.units * blockIdx.x) / gridDim.x);
   const int u1 = static_cast<int>((p.units * (blockIdx.x + 1)) / gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWq);
-    for (int s = 0; s < A3_STAGES; ++s) {
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < A3_MAX_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -115,11 +203,10 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_ready[i], 256);
-      mbar_init(&slot_free[i], 128);
+      mbar_init(&slot_free[i], 256);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 128);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_free[i], 128);
     }
     fence_barrier_init();
   }
@@ -131,10 +218,10 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
 
   // register re-distribution (warpgroup granular): the producer / issuer warps need few, the row threads many
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
       uint32_t it = 0;
       int prev_bg = -1;
       uint32_t kv_gen = 0;
@@ -144,23 +231,29 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
         const int b = bg / p.G;
         const int g = bg - b * p.G;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % A3_STAGES;
-          const uint32_t ph = (it / A3_STAGES) & 1;
+          const int s = it % nst;
+          const uint32_t ph = (it / nst) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* a_dst = smem + s * A3_STAGE_BYTES;
-          mbar_expect_tx(&full[s], A3_STAGE_BYTES);
-          tma_load_3d(a_dst, &tmX, &full[s], kb * A3_BK, mt * A3_BM, b);
-          tma_load_3d(a_dst + A3_A_BYTES, &tmWq, &full[s], kb * A3_BK, g * A3_BN, 0);
+          if (elect_one()) {
+            uint8_t* a_dst = smem + s * A3_STAGE_BYTES;
+            mbar_expect_tx(&full[s], A3_STAGE_BYTES);
+            tma_load_3d(a_dst, &tmX, &full[s], kb * A3_BK, mt * A3_BM, b);
+            tma_load_3d(a_dst + A3_A_BYTES, &tmWq, &full[s], kb * A3_BK, g * A3_BN, 0);
+          }
+          __syncwarp();
         }
-        if (bg != prev_bg) {
+        if (bg != prev_bg && p.dbg < 4) {
           // K / V^T tiles of this (sample, head group): needed only once the projection above has completed
           if (kv_gen > 0) mbar_wait(kv_free, (kv_gen - 1) & 1);
-          mbar_expect_tx(kv_full, Cfg::KV_BYTES);
-          for (int j = 0; j < HPC; ++j) {
-            const size_t tile = (static_cast<size_t>(b) * p.H + (g * HPC + j)) * Cfg::KV_TILE_BYTES;
-            bulk_load_1d(kv + (2 * j) * Cfg::KV_TILE_BYTES, p.Kp + tile, Cfg::KV_TILE_BYTES, kv_full);
-            bulk_load_1d(kv + (2 * j + 1) * Cfg::KV_TILE_BYTES, p.Vp + tile, Cfg::KV_TILE_BYTES, kv_full);
+          if (elect_one()) {
+            mbar_expect_tx(kv_full, Cfg::KV_BYTES);
+            for (int j = 0; j < HPC; ++j) {
+              const size_t tile = (static_cast<size_t>(b) * p.H + (g * HPC + j)) * Cfg::KV_TILE_BYTES;
+              bulk_load_1d(kv + (2 * j) * Cfg::KV_TILE_BYTES, p.Kp + tile, Cfg::KV_TILE_BYTES, kv_full);
+              bulk_load_1d(kv + (2 * j + 1) * Cfg::KV_TILE_BYTES, p.Vp + tile, Cfg::KV_TILE_BYTES, kv_full);
+            }
           }
+          __syncwarp();
           ++kv_gen;
           prev_bg = bg;
         }
@@ -169,114 +262,196 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
   } else if (warp == 1) {
     // ===================== projection MMA issuer: Q(unit) = X Wq^T  (M=128, N=160, K=C) =====================
     constexpr uint32_t idesc_q = umma_idesc_bf16(A3_BM, A3_BN);
+    A3Trace tr = a3_trace_init(p, 0);
     uint32_t it = 0;
     int i = 0;
     for (int u = u0; u < u1; ++u, ++i) {
       const int slot = i & 1;
       if (i >= 2) mbar_wait(&slot_free[slot], ((i >> 1) - 1) & 1);
       tc_fence_after();
+      a3_trace(tr, 10, i);
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        const int s = it % A3_STAGES;
-        const uint32_t ph = (it / A3_STAGES) & 1;
+        const int s = it % nst;
+        const uint32_t ph = (it / nst) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        a3_trace(tr, 12, kb);
+        if (elect_one()) {
+          if (p.dbg >= 5) {                       // pure TMA streaming rate: consume the stage without MMAs
+            mbar_arrive(&empty[s]);
+            if (kb == kblocks - 1) mbar_arrive(&q_full[slot]);
+          } else {
           const uint8_t* a_src = smem + s * A3_STAGE_BYTES;
           const uint64_t da = umma_desc_sw128(a_src);
           const uint64_t dw = umma_desc_sw128(a_src + A3_A_BYTES);
 #pragma unroll
           for (int k = 0; k < A3_BK / 16; ++k)
-            umma_bf16_ss(tmem + slot * A3_BN, da + 2 * k, dw + 2 * k, idesc_q, (kb | k) != 0);
+            if (p.dbg != 6 || k == 0) umma_bf16_ss(tmem + slot * A3_BN, da + 2 * k, dw + 2 * k, idesc_q, (kb | k) != 0);
           umma_commit(&empty[s]);
           if (kb == kblocks - 1) umma_commit(&q_full[slot]);
+          }
         }
         __syncwarp();
+        a3_trace(tr, 13, kb);
       }
+      a3_trace(tr, 11, i);
     }
+    a3_trace_done(p, tr, 0);
   } else if (warp == 2) {
     // ===================== attention MMA issuer =====================
+    // Flat loop over the heads of all units of this CTA (head nn belongs to softmax group nn & 1 and uses that
+    // group's S/P buffer).  Issue order  QK(nn+1) ; [wait P(nn)] ; PV(nn)  keeps one QK^T ahead of the softmax.
+    // The tensor pipe executes the MMAs of this thread in order, which is what makes the TMEM re-use legal:
+    //   S/P buffer of nn+2 <- overwritten only after PV(nn) has read P(nn);   O(w) columns <- overwritten only after
+    //   the QK^T MMAs that read the packed Q living there.
     constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BM, A3_KEYS);
     constexpr uint32_t idesc_o = umma_idesc_bf16(A3_BM, (D == 160) ? 80 : D_PAD);
-    uint32_t n = 0;                 // global head counter of this CTA
+    A3Trace tr = a3_trace_init(p, 1);
+    const int nheads = (p.dbg >= 4) ? 0 : (u1 - u0) * HPC;
+    int issued_qk = 0;
     uint32_t kv_gen = 0;
-    int prev_bg = -1;
-    int i = 0;
-    for (int u = u0; u < u1; ++u, ++i) {
-      const int slot = i & 1;
-      const uint32_t tslot = tmem + slot * A3_BN;
-      const int bg = u / p.MT;
-      mbar_wait(&q_ready[slot], (i >> 1) & 1);
-      if (bg != prev_bg) {
-        mbar_wait(kv_full, kv_gen & 1);
-        ++kv_gen;
-        prev_bg = bg;
-      }
-      tc_fence_after();
-      auto issue_qk = [&](int j, uint32_t nn) {
-        const uint32_t sbuf = tmem + ((D != 160 && (nn & 1)) ? Cfg::TM_SBUF1 : Cfg::TM_SBUF0);
-        const uint32_t k_tile = smem_u32(kv + (2 * j) * Cfg::KV_TILE_BYTES);
+    int kv_bg = -1;                 // (sample, head group) whose K/V tiles are resident
+    int q_units_ready = 0;          // units [0, q_units_ready) have had their q_ready observed
+    auto unit_of = [&](int nn) { return nn / HPC; };
+    auto issue_qk = [&](int nn) {
+      const int i = unit_of(nn), j = nn - i * HPC;
+      const uint32_t tslot = tmem + (i & 1) * A3_BN;
+      const uint32_t sbuf = tmem + ((nn & 1) ? Cfg::TM_SBUF1 : Cfg::TM_SBUF0);
+      const uint32_t k_tile = smem_u32(kv + (2 * j) * Cfg::KV_TILE_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < D_PAD / 16; ++k) {
           const uint64_t db = umma_desc(k_tile + k * 2 * (A3_KEYS * 16), A3_KEYS * 16, 128, UMMA_LAYOUT_NONE);
-          umma_bf16_ts(sbuf, tslot + j * Cfg::QB_COLS + k * 8, db, idesc_s, k != 0);
+          umma_bf16_ts(sbuf, tslot + Cfg::q_col(j) + k * 8, db, idesc_s, k != 0);
         }
         umma_commit(&s_full[nn & 1]);
-      };
-      if (lane == 0) issue_qk(0, n);
-      __syncwarp();
-#pragma unroll 1
-      for (int j = 0; j < HPC; ++j) {
-        const uint32_t nn = n + j;
-        const uint32_t w = nn & 1;
-        if (j + 1 < HPC) {
-          // the S/P buffer of head nn+1 was last used by head nn-1, whose PV has already been issued (in order)
-          if (lane == 0) issue_qk(j + 1, nn + 1);
-          __syncwarp();
-        }
-        mbar_wait(&p_ready[w], (nn >> 1) & 1);
-        if (nn >= 1) mbar_wait(&o_free[(nn - 1) & 1], ((nn - 1) >> 1) & 1);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sbuf = tmem + ((D != 160 && w) ? Cfg::TM_SBUF1 : Cfg::TM_SBUF0);
-          const uint32_t v_tile = smem_u32(kv + (2 * j + 1) * Cfg::KV_TILE_BYTES);
-          if constexpr (D == 160) {
-#pragma unroll
-            for (int k = 0; k < A3_KEYS / 16; ++k) {
-              const uint64_t db = umma_desc(v_tile + k * 2 * (D_PAD * 16), D_PAD * 16, 128, UMMA_LAYOUT_NONE);
-              umma_bf16_ts(tslot + Cfg::TM_O_OFF, sbuf + k * 8, db, idesc_o, k != 0);
-            }
-#pragma unroll
-            for (int k = 0; k < A3_KEYS / 16; ++k) {
-              const uint64_t db = umma_desc(v_tile + 80 * 16 + k * 2 * (D_PAD * 16), D_PAD * 16, 128, UMMA_LAYOUT_NONE);
-              umma_bf16_ts(tmem + Cfg::TM_OHI, sbuf + k * 8, db, idesc_o, k != 0);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < A3_KEYS / 16; ++k) {
-              const uint64_t db = umma_desc(v_tile + k * 2 * (D_PAD * 16), D_PAD * 16, 128, UMMA_LAYOUT_NONE);
-              umma_bf16_ts(tslot + Cfg::TM_O_OFF, sbuf + k * 8, db, idesc_o, k != 0);
-            }
-          }
-          umma_commit(&o_full[w]);
-          if (j == HPC - 1 && u + 1 < u1 && (u + 1) / p.MT != bg) umma_commit(kv_free);
-        }
-        __syncwarp();
       }
-      n += HPC;
+      __syncwarp();
+      a3_trace(tr, 20, nn);
+    };
+#pragma unroll 1
+    for (int nn = 0; nn < nheads; ++nn) {
+      const int i = unit_of(nn), j = nn - i * HPC;
+      const int bg = (u0 + i) / p.MT;
+      if (issued_qk <= nn) {
+        // first head of a unit whose Q was not ready for look-ahead (or new K/V tiles): blocking
+        if (q_units_ready <= i) { mbar_wait(&q_ready[i & 1], (i >> 1) & 1); q_units_ready = i + 1; }
+        if (bg != kv_bg) { mbar_wait(kv_full, kv_gen & 1); ++kv_gen; kv_bg = bg; }
+        tc_fence_after();
+        issue_qk(nn);
+        issued_qk = nn + 1;
+      }
+      if (nn + 1 < nheads && issued_qk == nn + 1) {
+        const int i2 = unit_of(nn + 1);
+        bool ok = (i2 == i);
+        if (!ok && (u0 + i2) / p.MT == kv_bg) {             // next unit, same K/V: look ahead only if Q is ready
+          if (q_units_ready > i2) ok = true;
+          else if (mbar_test_wait(&q_ready[i2 & 1], (i2 >> 1) & 1)) { ok = true; q_units_ready = i2 + 1; }
+        }
+        if (ok) {
+          tc_fence_after();
+          issue_qk(nn + 1);
+          issued_qk = nn + 2;
+        }
+      }
+      const uint32_t w = nn & 1;
+      a3_trace(tr, 25, nn);
+      mbar_wait(&p_ready[w], (nn >> 1) & 1);
+      tc_fence_after();
+      a3_trace(tr, 26, nn);
+      if (elect_one()) {
+        const uint32_t tslot = tmem + (i & 1) * A3_BN;
+        const uint32_t sbuf = tmem + (w ? Cfg::TM_SBUF1 : Cfg::TM_SBUF0);
+        const uint32_t v_tile = smem_u32(kv + (2 * j + 1) * Cfg::KV_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < A3_KEYS / 16; ++k) {
+          const uint64_t db = umma_desc(v_tile + k * 2 * (D_PAD * 16), D_PAD * 16, 128, UMMA_LAYOUT_NONE);
+          umma_bf16_ts(tslot + Cfg::o_col(w), sbuf + k * 8, db, idesc_o, k != 0);
+        }
+        if constexpr (D == 160) {
+#pragma unroll
+          for (int k = 0; k < A3_KEYS / 16; ++k) {
+            const uint64_t db = umma_desc(v_tile + 80 * 16 + k * 2 * (D_PAD * 16), D_PAD * 16, 128, UMMA_LAYOUT_NONE);
+            umma_bf16_ts(tslot + 80, sbuf + k * 8, db, idesc_o, k != 0);
+          }
+        }
+        umma_commit(&o_full[w]);
+        // last head of the last unit that uses the resident K/V tiles -> the producer may overwrite them
+        if (j == HPC - 1 && nn + 1 < nheads && (u0 + i + 1) / p.MT != bg) umma_commit(kv_free);
+      }
+      __syncwarp();
+      a3_trace(tr, 21, nn);
     }
+    a3_trace_done(p, tr, 1);
   }
   } else {
     // ===================== softmax groups (warps 4..7 and 8..11): one thread per query row =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int wg = (warp - 4) >> 2;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t sbuf = tlane + (wg ? Cfg::TM_SBUF1 : Cfg::TM_SBUF0);
     const int Lt = p.Lt;
     const int Li = p.Li;
     const float cs = p.scale_log2e;
-    uint32_t n = 0;
+    A3Trace tr = a3_trace_init(p, 2 + wg);
+    if (q != 0) tr.base = nullptr;
+    PendingO pend;
+    pend.valid = false;
+
+    // O accumulator -> registers -> * row scale -> bf16 -> this warp's staging tile -> TMA store (clips rows >= S)
+    uint8_t* ost = smem + Cfg::OFF_OST + ((warp - 4) * Cfg::OST_WARP_BYTES);
+    auto stage_store = [&](const uint32_t* v, float oscale, int col0, int ncols) {
+      const uint64_t sc2 = f2_pack(oscale, oscale);
+#pragma unroll
+      for (int c = 0; c < ncols / 8; ++c) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a, b2;
+          f2_unpack(f2_mul(f2_pack(__uint_as_float(v[c * 8 + 2 * k]), __uint_as_float(v[c * 8 + 2 * k + 1])), sc2), a, b2);
+          w4[k] = pack_bf16x2(a, b2);
+        }
+        st_shared_v4(ost + lane * (Cfg::OW * 2) + (col0 + c * 8) * 2, w4[0], w4[1], w4[2], w4[3]);
+      }
+    };
+    auto drain = [&](const PendingO& po) {
+      mbar_wait(&o_full[wg], po.parity);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < (D == 160 ? 2 : 1); ++h) {
+        if (elect_one()) bulk_wait_read<0>();          // the previous TMA store of this warp has read the tile
+        __syncwarp();
+        if constexpr (D == 40) {
+          uint32_t a[32], c8[8];
+          tmem_ld_x32(po.taddr, a);
+          tmem_ld_x8(po.taddr + 32, c8);
+          tmem_ld_wait();
+          stage_store(a, po.oscale, 0, 32);
+          stage_store(c8, po.oscale, 32, 8);
+        } else {
+          uint32_t a[32], b2[32], c16[16];
+          tmem_ld_x32(po.taddr + h * 80, a);
+          tmem_ld_x32(po.taddr + h * 80 + 32, b2);
+          tmem_ld_x16(po.taddr + h * 80 + 64, c16);
+          tmem_ld_wait();
+          stage_store(a, po.oscale, 0, 32);
+          stage_store(b2, po.oscale, 32, 32);
+          stage_store(c16, po.oscale, 64, 16);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (p.dbg < 2 && elect_one()) {
+          tma_store_3d(&tmO, ost, po.c0 + h * 80, po.r0, po.b);
+          bulk_commit();
+        }
+        __syncwarp();
+      }
+    };
+
     int i = 0;
+#pragma unroll 1
     for (int u = u0; u < u1; ++u, ++i) {
       const int slot = i & 1;
       const uint32_t tslot = tlane + slot * A3_BN;
@@ -286,199 +461,208 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
       const int g = bg - b * p.G;
       const int m0 = mt * A3_BM;
 
-      // ---- Q: fp32 accumulator -> packed bf16 in place.  Group wg converts columns [80 wg, 80 wg + 80). ----
+      // ---- Q: fp32 accumulator -> packed bf16, written inside the columns this group has just read ----
       mbar_wait(&q_full[slot], (i >> 1) & 1);
       tc_fence_after();
-      {
-        uint32_t a[32], b2[32], c16[16], o[48];
+      a3_trace(tr, 30 + 10 * wg, i);
+      if (p.dbg >= 3) {
+      } else if constexpr (D == 40) {
+        // group wg converts heads wg and wg + 2 : fp32 [40 j, 40 j + 40) -> bf16 [40 j + 16, 40 j + 40)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = wg + 2 * jj;
+          uint32_t a[32], c8[8], o[24];
+          tmem_ld_x32(tslot + 40 * j, a);
+          tmem_ld_x8(tslot + 40 * j + 32, c8);
+          tmem_ld_wait();
+          pack_pairs3<32>(a, o);
+          pack_pairs3<8>(c8, o + 16);
+          o[20] = o[21] = o[22] = o[23] = 0u;          // dims 40..47 pad the K = 48 contraction
+          tmem_st_x16(tslot + 40 * j + 16, o);
+          tmem_st_x8(tslot + 40 * j + 32, o + 16);
+        }
+      } else {
+        // d=80: group wg converts head wg; d=160: dims [80 wg, 80 wg + 80) of the single head.
+        // fp32 [80 wg, 80 wg + 80) -> bf16 [80 wg + 40, 80 wg + 80) (d=80) / [40 + 40 wg, 80 + 40 wg) (d=160)
+        uint32_t a[32], b2[32], c16[16], o[40];
         tmem_ld_x32(tslot + wg * 80, a);
         tmem_ld_x32(tslot + wg * 80 + 32, b2);
         tmem_ld_x16(tslot + wg * 80 + 64, c16);
         tmem_ld_wait();
-        named_bar_sync(1, 256);                     // every fp32 column has been read before any is overwritten
-        if constexpr (D == 40) {
-          // two heads: 20 data words + 4 zero words each (dims 40..47 pad the K = 48 contraction)
-          uint32_t t[40];
-          pack_pairs3<32>(a, t);
-          pack_pairs3<32>(b2, t + 16);
-          pack_pairs3<16>(c16, t + 32);
-#pragma unroll
-          for (int k = 0; k < 20; ++k) { o[k] = t[k]; o[24 + k] = t[20 + k]; }
-#pragma unroll
-          for (int k = 20; k < 24; ++k) { o[k] = 0u; o[24 + k] = 0u; }
-          tmem_st_x16(tslot + wg * 48, o);
-          tmem_st_x16(tslot + wg * 48 + 16, o + 16);
-          tmem_st_x16(tslot + wg * 48 + 32, o + 32);
-        } else {
-          pack_pairs3<32>(a, o);
-          pack_pairs3<32>(b2, o + 16);
-          pack_pairs3<16>(c16, o + 32);
-          tmem_st_x16(tslot + wg * 40, o);
-          tmem_st_x16(tslot + wg * 40 + 16, o + 16);
-          tmem_st_x8(tslot + wg * 40 + 32, o + 32);
-        }
+        pack_pairs3<32>(a, o);
+        pack_pairs3<32>(b2, o + 16);
+        pack_pairs3<16>(c16, o + 32);
+        const uint32_t dstc = tslot + ((D == 80) ? (wg * 80 + 40) : (40 + wg * 40));
+        tmem_st_x16(dstc, o);
+        tmem_st_x16(dstc + 16, o + 16);
+        tmem_st_x8(dstc + 32, o + 32);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&q_ready[slot]);
+      a3_trace(tr, 31 + 10 * wg, i);
+      // this group's last head of the previous unit: its PV ran during the conversion above; draining it now (rather
+      // than after the next softmax) returns the previous slot to the projection pipeline as early as possible
+      if (pend.valid) {
+        drain(pend);
+        tc_fence_before();
+        mbar_arrive(&slot_free[pend.slot]);
+        pend.valid = false;
+        a3_trace(tr, 32 + 10 * wg, i);
+      }
 
+      if (p.dbg >= 4) { mbar_arrive(&slot_free[slot]); continue; }
       const bool row_ok = (m0 + row) < p.S;
-      __nv_bfloat16* orow = p.O + (static_cast<size_t>(b) * p.S + (m0 + row)) * p.C + g * A3_BN;
+      bool had_head = false;
 
 #pragma unroll 1
       for (int j = 0; j < HPC; ++j) {
-        const uint32_t nn = n + j;
-        if (static_cast<int>(nn & 1) != wg) continue;
+        const int nn = i * HPC + j;
+        if ((nn & 1) != wg) continue;
+        had_head = true;
         const uint32_t par = (nn >> 1) & 1;
-        const uint32_t sbuf = tlane + ((D != 160 && wg) ? Cfg::TM_SBUF1 : Cfg::TM_SBUF0);
         mbar_wait(&s_full[wg], par);
         tc_fence_after();
-        float s[A3_KEYS];
+        a3_trace(tr, 33 + 10 * wg, nn);
+        uint32_t sr[A3_KEYS];                    // S row (fp32 bits), later the exponentials
+        if (p.dbg >= 2) {
 #pragma unroll
-        for (int c = 0; c < A3_KEYS / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(sbuf + c * 32, v);
+          for (int k = 0; k < A3_KEYS; ++k) sr[k] = 0u;
+        } else {
+          tmem_ld32_raw(sbuf, sr);
+          tmem_ld32_raw(sbuf + 32, sr + 32);
+          tmem_ld32_raw(sbuf + 64, sr + 64);
           tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) s[c * 32 + k] = __uint_as_float(v[k]);
         }
-        if (Lt < 64) {
+        float fi = 1.f, oscale = 1.f;
+        bool text_on = true;
+        if (p.dbg < 1) {
+        // Key-slot validity.  LT77 (the CLIP context length, every PhotoVerse caller): the text mask is a compile-time
+        // constant, so padding slots 77..79 cost nothing; otherwise it is a per-slot runtime select.  The 16 image
+        // slots are always masked at run time (Li = 1..16).
+        auto tvalid = [&](int c) -> bool { if constexpr (LT77) return c < 77; else return c < Lt; };
+        float mt2[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int k = 0; k < 64; ++k) s[k] = (k < Lt) ? s[k] : -INFINITY;
+        for (int c = 0; c < A3_IMG_OFF; ++c) {
+          if (LT77 && c >= 77) continue;
+          const float v = __uint_as_float(sr[c]);
+          mt2[c & 3] = fmaxf(mt2[c & 3], LT77 ? v : (tvalid(c) ? v : -INFINITY));
         }
+        float mi2[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-        for (int k = 64; k < A3_IMG_OFF; ++k) s[k] = (k < Lt) ? s[k] : -INFINITY;
+        for (int c = 0; c < A3_KEYS - A3_IMG_OFF; ++c)
+          mi2[c & 1] = fmaxf(mi2[c & 1], (c < Li) ? __uint_as_float(sr[A3_IMG_OFF + c]) : -INFINITY);
+        const float mts = fmaxf(fmaxf(mt2[0], mt2[1]), fmaxf(mt2[2], mt2[3])) * cs, mis = fmaxf(mi2[0], mi2[1]) * cs;
+        // exponentials: e = 2^(s * cs - m) -- one FFMA2 per two keys, one MUFU.EX2 per key, one FADD2 per two keys
+        const uint64_t cs2 = f2_pack(cs, cs);
+        const uint64_t nmt2 = f2_pack(-mts, -mts), nmi2 = f2_pack(-mis, -mis);
+        uint64_t lacc[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+        uint64_t iacc = f2_pack(0.f, 0.f);
 #pragma unroll
-        for (int k = A3_IMG_OFF; k < A3_KEYS; ++k) s[k] = (k - A3_IMG_OFF < Li) ? s[k] : -INFINITY;
-        float m4[4] = {s[0], s[1], s[2], s[3]};
-#pragma unroll
-        for (int k = 4; k < A3_IMG_OFF; ++k) m4[k & 3] = fmaxf(m4[k & 3], s[k]);
-        const float mt_ = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        float i4[4] = {s[A3_IMG_OFF], s[A3_IMG_OFF + 1], s[A3_IMG_OFF + 2], s[A3_IMG_OFF + 3]};
-#pragma unroll
-        for (int k = A3_IMG_OFF + 4; k < A3_KEYS; ++k) i4[k & 3] = fmaxf(i4[k & 3], s[k]);
-        const float mi_ = fmaxf(fmaxf(i4[0], i4[1]), fmaxf(i4[2], i4[3]));
-        const float mts = mt_ * cs, mis = mi_ * cs;
-        float l4[4] = {0.f, 0.f, 0.f, 0.f}, li4[2] = {0.f, 0.f};
-#pragma unroll
-        for (int kc = 0; kc < A3_IMG_OFF / 8; ++kc) {
-          if (kc * 8 < Lt) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float e = fast_exp2(fmaf(s[kc * 8 + k], cs, -mts));
-              s[kc * 8 + k] = e;
-              l4[k & 3] += e;
-            }
+        for (int k = 0; k < A3_IMG_OFF / 2; ++k) {
+          const int c = 2 * k;
+          if (LT77 && c >= 77) { sr[c] = 0u; sr[c + 1] = 0u; continue; }
+          float a, b2;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmt2), a, b2);
+          a = fast_exp2(a);
+          b2 = fast_exp2(b2);
+          if constexpr (LT77) {
+            if (c + 1 >= 77) b2 = 0.f;
           } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s[kc * 8 + k] = 0.f;
+            a = tvalid(c) ? a : 0.f;
+            b2 = tvalid(c + 1) ? b2 : 0.f;
           }
+          lacc[k & 1] = f2_add(lacc[k & 1], f2_pack(a, b2));
+          sr[c] = __float_as_uint(a);
+          sr[c + 1] = __float_as_uint(b2);
         }
+        if (Li > 8) {
 #pragma unroll
-        for (int kc = A3_IMG_OFF / 8; kc < A3_KEYS / 8; ++kc) {
-          if ((kc - A3_IMG_OFF / 8) * 8 < Li) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float e = fast_exp2(fmaf(s[kc * 8 + k], cs, -mis));
-              s[kc * 8 + k] = e;
-              li4[k & 1] += e;
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s[kc * 8 + k] = 0.f;
+          for (int k = 0; k < 8; ++k) {
+            const int c = A3_IMG_OFF + 2 * k;
+            float a, b2;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmi2), a, b2);
+            a = (2 * k < Li) ? fast_exp2(a) : 0.f;
+            b2 = (2 * k + 1 < Li) ? fast_exp2(b2) : 0.f;
+            iacc = f2_add(iacc, f2_pack(a, b2));
+            sr[c] = __float_as_uint(a);
+            sr[c + 1] = __float_as_uint(b2);
           }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = A3_IMG_OFF + 2 * k;
+            float a, b2;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmi2), a, b2);
+            a = (2 * k < Li) ? fast_exp2(a) : 0.f;
+            b2 = (2 * k + 1 < Li) ? fast_exp2(b2) : 0.f;
+            iacc = f2_add(iacc, f2_pack(a, b2));
+            sr[c] = __float_as_uint(a);
+            sr[c + 1] = __float_as_uint(b2);
+          }
+#pragma unroll
+          for (int c = A3_IMG_OFF + 8; c < A3_KEYS; ++c) sr[c] = 0u;
         }
-        const float lt = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        const float li = li4[0] + li4[1];
+        float l0, l1, l2, l3, li0, li1;
+        f2_unpack(lacc[0], l0, l1);
+        f2_unpack(lacc[1], l2, l3);
+        f2_unpack(iacc, li0, li1);
+        const float lt = (l0 + l1) + (l2 + l3);
+        const float li = li0 + li1;
         const float at = p.w_text / lt;
         const float ai = p.w_img / li;
         if (p.stats != nullptr && row_ok) {
           const size_t idx = ((static_cast<size_t>(b) * p.H + (g * HPC + j)) * p.S + (m0 + row));
           reinterpret_cast<float4*>(p.stats)[idx] = make_float4(mts, lt, mis, li);
         }
-        float ft, fi, oscale;
-        if (p.w_text != 0.f) { ft = 1.f; fi = ai / at; oscale = at; }
-        else                 { ft = 0.f; fi = 1.f;     oscale = ai; }
+        // P = [e_text | e_img * fi], O row scaled by `oscale` afterwards: the text segment stays unscaled.
+        // w_text == 0 (image-only fusion branch) flips the roles.
+        if (p.w_text != 0.f) { fi = ai / at; oscale = at; }
+        else                 { text_on = false; fi = 1.f; oscale = ai; }
+        }
         uint32_t pk[A3_KEYS / 2];
 #pragma unroll
-        for (int k = 0; k < A3_IMG_OFF / 2; ++k) pk[k] = (ft == 1.f) ? pack_bf16x2(s[2 * k], s[2 * k + 1]) : 0u;
+        for (int k = 0; k < A3_IMG_OFF / 2; ++k)
+          pk[k] = text_on ? pack_bf16x2(__uint_as_float(sr[2 * k]), __uint_as_float(sr[2 * k + 1])) : 0u;
+        {
+          const uint64_t fi2 = f2_pack(fi, fi);
 #pragma unroll
-        for (int k = A3_IMG_OFF / 2; k < A3_KEYS / 2; ++k) pk[k] = pack_bf16x2(s[2 * k] * fi, s[2 * k + 1] * fi);
+          for (int k = A3_IMG_OFF / 2; k < A3_KEYS / 2; ++k) {
+            float a, b2;
+            f2_unpack(f2_mul(f2_pack(__uint_as_float(sr[2 * k]), __uint_as_float(sr[2 * k + 1])), fi2), a, b2);
+            pk[k] = pack_bf16x2(a, b2);
+          }
+        }
+
+        // the previous head of this group: its PV ran while the softmax above was computed.  It must leave TMEM
+        // before P(nn) is published, because PV(nn) overwrites the group's O columns.
+        if (pend.valid) {          // only heads of this same unit reach here (d = 40: the group's first head)
+          drain(pend);
+          pend.valid = false;
+        }
         tmem_st_x16(sbuf, pk);
         tmem_st_x16(sbuf + 16, pk + 16);
         tmem_st_x16(sbuf + 32, pk + 32);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[wg]);
+        a3_trace(tr, 34 + 10 * wg, nn);
 
-        // ---- O_j: TMEM -> registers -> * row scale -> bf16 -> HBM (this thread's row, D*2 contiguous bytes) ----
-        mbar_wait(&o_full[wg], par);
-        tc_fence_after();
-        __nv_bfloat16* dst = orow + j * D;
-        auto emit = [&](const uint32_t* v, int col0, int ncols) {
-          if (!row_ok) return;
-#pragma unroll
-          for (int c = 0; c < ncols / 8; ++c) {
-            const uint32_t* w8 = v + c * 8;
-            st_global_v4(dst + col0 + c * 8,
-                         pack_bf16x2(__uint_as_float(w8[0]) * oscale, __uint_as_float(w8[1]) * oscale),
-                         pack_bf16x2(__uint_as_float(w8[2]) * oscale, __uint_as_float(w8[3]) * oscale),
-                         pack_bf16x2(__uint_as_float(w8[4]) * oscale, __uint_as_float(w8[5]) * oscale),
-                         pack_bf16x2(__uint_as_float(w8[6]) * oscale, __uint_as_float(w8[7]) * oscale));
-          }
-        };
-        const uint32_t o_addr = tslot + Cfg::TM_O_OFF;
-        if constexpr (D == 40) {
-          uint32_t a[32], c8[8];
-          tmem_ld_x32(o_addr, a);
-          tmem_ld_x8(o_addr + 32, c8);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&o_free[wg]);
-          if (j == HPC - 1) mbar_arrive(&slot_free[slot]);
-          emit(a, 0, 32);
-          emit(c8, 32, 8);
-        } else if constexpr (D == 80) {
-          uint32_t a[32], b2[32], c16[16];
-          tmem_ld_x32(o_addr, a);
-          tmem_ld_x32(o_addr + 32, b2);
-          tmem_ld_x16(o_addr + 64, c16);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&o_free[wg]);
-          if (j == HPC - 1) mbar_arrive(&slot_free[slot]);
-          emit(a, 0, 32);
-          emit(b2, 32, 32);
-          emit(c16, 64, 16);
-        } else {
-          const uint32_t ohi = tlane + Cfg::TM_OHI;
-          {
-            uint32_t a[32], b2[32], c16[16];
-            tmem_ld_x32(o_addr, a);
-            tmem_ld_x32(o_addr + 32, b2);
-            tmem_ld_x16(o_addr + 64, c16);
-            tmem_ld_wait();
-            emit(a, 0, 32);
-            emit(b2, 32, 32);
-            emit(c16, 64, 16);
-          }
-          {
-            uint32_t a[32], b2[32], c16[16];
-            tmem_ld_x32(ohi, a);
-            tmem_ld_x32(ohi + 32, b2);
-            tmem_ld_x16(ohi + 64, c16);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&o_free[wg]);
-            mbar_arrive(&slot_free[slot]);
-            emit(a, 80, 32);
-            emit(b2, 112, 32);
-            emit(c16, 144, 16);
-          }
-        }
+        pend.valid = true;
+        pend.c0 = g * A3_BN + j * D;
+        pend.r0 = m0 + q * 32;
+        pend.b = b;
+        pend.taddr = tslot + Cfg::o_col(wg);
+        pend.oscale = oscale;
+        pend.parity = par;
+        pend.slot = slot;
       }
-      n += HPC;
+      if (!had_head) mbar_arrive(&slot_free[slot]);      // d = 160: the other group owns this unit's head
     }
+    if (pend.valid) drain(pend);
+    if (elect_one()) bulk_wait_read<0>();
+    __syncwarp();
+    a3_trace_done(p, tr, 2 + wg);
   }
 
   tc_fence_before();
@@ -487,10 +671,16 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
-template <int D>
-static int launch_attn3(const CUtensorMap& tmX, const CUtensorMap& tmWq, const Attn3Params& p, cudaStream_t stream) {
+extern int g_opt_attn3_dbg;
+extern int g_opt_attn3_stages;
+extern unsigned long long* g_attn3_trace;
+extern int g_attn3_trace_cap;
+
+template <int D, bool LT77>
+static int launch_attn3(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const Attn3Params& p,
+                        cudaStream_t stream) {
   using Cfg = Attn3Cfg<D>;
-  auto kern = dual_attn_fwd_persistent_kernel<D>;
+  auto kern = dual_attn_fwd_persistent_kernel<D, LT77>;
   static bool attr_done = false;
   if (!attr_done) {
     PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -498,7 +688,7 @@ static int launch_attn3(const CUtensorMap& tmX, const CUtensorMap& tmWq, const A
   }
   const long long sms = sm_count();
   const int grid = static_cast<int>(p.units < sms ? p.units : sms);
-  kern<<<grid, A3_THREADS, Cfg::SMEM_BYTES, stream>>>(tmX, tmWq, p);
+  kern<<<grid, A3_THREADS, Cfg::SMEM_BYTES, stream>>>(tmX, tmWq, tmO, p);
   PV_LAUNCHED();
   return PV_OK;
 }
@@ -514,9 +704,10 @@ int dual_attn_core_bf16_persistent(const void* X, const void* Wq, const void* Kp
              "need 1 <= Lt <= %d and 1 <= Li <= %d (Lt=%d Li=%d)", A3_IMG_OFF, A3_KEYS - A3_IMG_OFF, Lt, Li);
   PV_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wq) | reinterpret_cast<uintptr_t>(Kp) |
               reinterpret_cast<uintptr_t>(Vp) | reinterpret_cast<uintptr_t>(O)) % 16 == 0, "pointers must be 16-byte aligned");
-  CUtensorMap tmX, tmWq;
+  CUtensorMap tmX, tmWq, tmO;
   if (make_tmap_3d(&tmX, X, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, A3_BK, A3_BM, 1, Swz::B128)) return PV_ERR_CUDA;
   if (make_tmap_3d(&tmWq, Wq, 2, C, C, 1, C * 2ull, static_cast<uint64_t>(C) * C * 2, A3_BK, A3_BN, 1, Swz::B128)) return PV_ERR_CUDA;
+  if (make_tmap_3d(&tmO, O, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, d == 160 ? 80 : d, 32, 1, Swz::None)) return PV_ERR_CUDA;
   Attn3Params p;
   p.Kp = static_cast<const uint8_t*>(Kp);
   p.Vp = static_cast<const uint8_t*>(Vp);
@@ -528,11 +719,15 @@ int dual_attn_core_bf16_persistent(const void* X, const void* Wq, const void* Kp
   p.units = static_cast<long long>(B) * p.G * p.MT;
   PV_REQUIRE(p.units < (1ll << 30), "too many work units");
   p.w_text = w_text; p.w_img = w_img;
+  p.dbg = g_opt_attn3_dbg;
+  p.dbg_stages = g_opt_attn3_stages;
+  p.trace = g_attn3_trace;
+  p.trace_cap = g_attn3_trace_cap;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(d));
   switch (d) {
-    case 40: return launch_attn3<40>(tmX, tmWq, p, stream);
-    case 80: return launch_attn3<80>(tmX, tmWq, p, stream);
-    default: return launch_attn3<160>(tmX, tmWq, p, stream);
+    case 40: return Lt == 77 ? launch_attn3<40, true>(tmX, tmWq, tmO, p, stream) : launch_attn3<40, false>(tmX, tmWq, tmO, p, stream);
+    case 80: return Lt == 77 ? launch_attn3<80, true>(tmX, tmWq, tmO, p, stream) : launch_attn3<80, false>(tmX, tmWq, tmO, p, stream);
+    default: return Lt == 77 ? launch_attn3<160, true>(tmX, tmWq, tmO, p, stream) : launch_attn3<160, false>(tmX, tmWq, tmO, p, stream);
   }
 }
 

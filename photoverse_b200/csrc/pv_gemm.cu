@@ -78,17 +78,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const int s = kb % Cfg::STAGES;
+      const uint32_t ph = (kb / Cfg::STAGES) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
         uint8_t* w_dst = a_dst + GEMM_A_BYTES;
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
         tma_load_3d(a_dst, &tmA, &full[s], kb * GEMM_BK, m0, batch);
         tma_load_3d(w_dst, &tmW, &full[s], kb * GEMM_BK, n0, w_batched ? batch : 0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -98,7 +99,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t ph = (kb / Cfg::STAGES) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {        // elect.sync, not `lane == 0`: lets the compiler issue the UTCHMMAs back to back
         const uint8_t* a_src = smem + s * Cfg::STAGE_BYTES;
         const uint8_t* w_src = a_src + GEMM_A_BYTES;
         const uint64_t da = umma_desc_sw128(a_src);
@@ -129,7 +130,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tmem_ld_wait();
       uint8_t* buf = stg + (c & 1) * Cfg::EPI_TILE_BYTES;
       if (c >= 2) {                            // the TMA store that last read this buffer must be done
-        if (lane == 0) bulk_wait_read<1>();
+        if (elect_one()) bulk_wait_read<1>();
         __syncwarp();
       }
       float f[32];
@@ -162,12 +163,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         tma_store_3d(&tmD, buf, n0 + c * 32, m0 + q * 32, batch);
         bulk_commit();
       }
+      __syncwarp();
     }
-    if (lane == 0) bulk_wait_read<0>();
+    if (elect_one()) bulk_wait_read<0>();
     __syncwarp();
   }
 

@@ -1,0 +1,56 @@
+"""Timeline of CTA 0 of the persistent attention kernel (debug trace events) for one layer shape."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from photoverse_b200 import _lib, ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+dt = torch.bfloat16
+S, C = int(os.environ.get("PV_S", "4096")), int(os.environ.get("PV_C", "320"))
+ROWS, LI = 16, 1
+g = torch.Generator().manual_seed(0)
+_lib.set_option("attn_variant", 3)
+_lib.set_option("attn3_dbg", int(os.environ.get("PV_DBG", "0")))
+lib = _lib.lib()
+text = torch.randn(ROWS, 77, 768, generator=g).to(dev, dt)
+img = torch.randn(ROWS, LI, 768, generator=g).to(dev, dt)
+wq = (torch.randn(C, C, generator=g) / C ** 0.5).to(dev, dt)
+wkv = (torch.randn(2 * C, 768, generator=g) / 768 ** 0.5).to(dev, dt)
+kv = ops.kv_pack(text, img, wkv, wkv, 8)
+x = torch.randn(ROWS, S, C, device=dev, dtype=dt)
+o = torch.empty_like(x)
+
+
+def run():
+    _lib.check(lib.pv_dual_attn_core_fwd(1, ops._ptr(x), ops._ptr(wq), ops._ptr(kv.Kp), ops._ptr(kv.Vp), ops._ptr(o), None,
+                                         ROWS, S, C, 8, 77, LI, 1.0, 1.0, ops._stream()))
+
+
+for _ in range(3):
+    run()
+cap = 4096
+buf = torch.zeros(4 + 3 * cap, device=dev, dtype=torch.int64)
+_lib.check(lib.pv_debug_trace(ops._ptr(buf), cap))
+run()
+torch.cuda.synchronize()
+_lib.check(lib.pv_debug_trace(None, 0))
+h = buf.cpu().tolist()
+per = cap // 4
+ev = []
+for r in range(4):
+    base = 4 + r * per * 3
+    for k in range(min(h[r], per)):
+        ev.append((h[base + 3 * k + 2], h[base + 3 * k], h[base + 3 * k + 1]))
+ev.sort()
+n = len(ev)
+t0 = ev[0][0]
+names = {12: " qp full", 13: " qp mma issued", 14: " qp committed", 22: "  qk begin", 23: "  qk mmas issued", 25: "  pv wait p_ready", 26: "  pv p_ready ok", 27: "  pv mmas issued", 10: "QP start", 11: "QP issued", 20: "  QK issued", 21: "  PV issued", 29: "    A wait q_full", 30: "    A q_full", 31: "    A conv done",
+         32: "    A slot_free", 33: "    A s_full", 34: "    A p_ready", 39: "        B wait q_full", 40: "        B q_full", 41: "        B conv done",
+         42: "        B slot_free", 43: "        B s_full", 44: "        B p_ready"}
+skip = int(os.environ.get("PV_SKIP", "0"))
+for t, e, i in ev[skip: skip + int(os.environ.get("PV_NEV", "140"))]:
+    print(f"{t - t0:8d}  {names.get(e, e)} {i}")
+print("events", n, "span cycles", ev[-1][0] - t0)
