@@ -116,6 +116,52 @@ int pv_ln_lrelu_fwd(pv_dtype out_dt, const float* x, const float* gamma, const f
 int pv_group_mean_fwd(pv_dtype in_dt, pv_dtype out_dt, const void* x, void* y, int64_t groups, int P, int cols,
                       int64_t ldy, void* stream);
 
+/* ============================== backward (training step, reference train.py:495-538) ==============================
+ * Trainable set of the path: adapters, to_k_ip / to_v_ip, LoRA A/B on attn2.to_q/to_k/to_v (train.py:348-370).  Input
+ * gradients flow through every attn2 layer into the frozen UNet (accelerator.backward, train.py:538).
+ * All reductions are two-pass and deterministic.  Workspaces are caller-owned; sizes from the *_ws_bytes queries.   */
+
+/* W_eff^T[in,out] = (W + scaling * B A)^T in `out_dt`: the weight of an input-gradient GEMM  dX = dY W_eff, which is
+ * pv_linear_fwd(dY, W_eff^T).  (autograd of attention_processor.py:297,304,305,392,393,423 and adapters.py:14-28)     */
+int pv_pack_weight_t(pv_dtype out_dt, const float* W, const float* lora_A, const float* lora_B, float scaling,
+                     void* W_eff_t, int out_features, int in_features, int r, void* stream);
+
+/* out[c, r] = in[r, c]  (in:[rows,cols] row stride ldi; out:[cols, ldo] with columns [rows, ldo) zero-filled).  Turns the
+ * packed forward weights into the weights of the input-gradient GEMMs without touching the fp32 masters again.       */
+int pv_transpose_2d(pv_dtype dt, const void* in, void* out, int64_t rows, int64_t cols, int64_t ldi, int64_t ldo, void* stream);
+
+/* dW[N,K] (fp32, dense) = alpha * sum_m G[m,n] X[m,k] + beta * dW    G:[M,N] (row stride ldg), X:[M,K] (ldx), both dt.
+ * bf16 with M >= 512, N,K >= 128: transposes + tcgen05 GEMM over K' = M; otherwise fp32 SIMT split-M.                */
+int64_t pv_linear_bwd_weight_ws_bytes(pv_dtype dt, int64_t M, int64_t N, int64_t K);
+int pv_linear_bwd_weight(pv_dtype dt, const void* G, const void* X, float* dW, void* ws, int64_t M, int64_t N, int64_t K,
+                         int64_t ldg, int64_t ldx, float alpha, float beta, void* stream);
+
+/* out[n] = sum_m G[m,n]  (bias gradients) */
+int64_t pv_col_sum_ws_bytes(int64_t M, int64_t N);
+int pv_col_sum(pv_dtype dt, const void* G, float* out, void* ws, int64_t M, int64_t N, int64_t ldg, void* stream);
+
+/* Backward of pv_ln_lrelu_fwd.  da, dx:[groups*rows_per_group, cols] (dt, dense); x fp32 pre-normalisation input and
+ * mean / rstd as saved by the forward; gamma/beta:[groups,cols]; dgamma/dbeta:[groups,cols] fp32.  cols == 1024.      */
+int64_t pv_ln_lrelu_bwd_ws_bytes(int64_t groups, int64_t rows_per_group, int cols);
+int pv_ln_lrelu_bwd(pv_dtype dt, const void* da, const float* x, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, void* dx, float* dgamma, float* dbeta, void* ws, int64_t groups,
+                    int64_t rows_per_group, int cols, float slope, void* stream);
+
+/* Backward of pv_group_mean_fwd: dx[g,p,:] = dy[g,:] / P   (dy row stride ldy; dx dense [groups,P,cols]) */
+int pv_group_mean_bwd(pv_dtype dt, const void* dy, void* dx, int64_t groups, int P, int cols, int64_t ldy, void* stream);
+
+/* Backward of the attention core (autograd of attention_processor.py:307-322, 400-420 with the two normalisers).
+ * dO, Q, dQ:[B,S,C] (dt); kv_text:[B*Lt,2C], kv_img:[B*Li,2C] fp32 projections and stats:[B,H,S,4] from the forward;
+ * ws receives per-query-chunk partial dK / dV, reduced by pv_kv_pack_bwd into dkv_text:[B*Lt,2C], dkv_img:[B*Li,2C]
+ * (dt; columns [0,C) dK, [C,2C) dV) together with the backward of the `to_v_ip_norm` side output
+ * (d_v_ip_norm:[B,H,Li] fp32 or NULL; models/unet.py:38-47, train.py:512-513).                                         */
+int64_t pv_dual_attn_bwd_ws_bytes(int B, int S, int C, int H, int Lt, int Li);
+int pv_dual_attn_bwd(pv_dtype dt, const void* dO, const void* Q, const float* kv_text, const float* kv_img,
+                     const float* stats, void* dQ, void* ws, int B, int S, int C, int H, int Lt, int Li, float w_text,
+                     float w_img, void* stream);
+int pv_kv_pack_bwd(pv_dtype dt, const void* ws, const float* kv_img, const float* v_ip_norm, const float* d_v_ip_norm,
+                   void* dkv_text, void* dkv_img, int B, int S, int Lt, int Li, int C, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

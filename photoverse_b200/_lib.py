@@ -34,18 +34,22 @@ _SIGNATURES = {
     "pv_dual_attn_core_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int] * 6 + [c_float, c_float, c_void_p]),
     "pv_ln_lrelu_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     "pv_group_mean_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),
-    "pv_dual_attn_bwd": (c_int, [c_int] + [c_void_p] * 14 + [c_int] * 6 + [c_float, c_float, c_void_p]),
-    "pv_kv_pack_bwd": (c_int, [c_int] + [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
-    "pv_linear_bwd_input": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p] + [c_int64] * 10 + [c_void_p]),
-    "pv_linear_bwd_weight": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 11 + [c_int, c_void_p]),
-    "pv_ln_lrelu_bwd": (c_int, [c_void_p] * 8 + [c_int64, c_int, c_float, c_void_p]),
-    "pv_group_mean_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "pv_pack_weight_t": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pv_transpose_2d": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "pv_linear_bwd_weight_ws_bytes": (c_int64, [c_int, c_int64, c_int64, c_int64]),
+    "pv_linear_bwd_weight": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 5 + [c_float, c_float, c_void_p]),
+    "pv_col_sum_ws_bytes": (c_int64, [c_int64, c_int64]),
+    "pv_col_sum": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "pv_ln_lrelu_bwd_ws_bytes": (c_int64, [c_int64, c_int64, c_int]),
+    "pv_ln_lrelu_bwd": (c_int, [c_int] + [c_void_p] * 10 + [c_int64, c_int64, c_int, c_float, c_void_p]),
+    "pv_group_mean_bwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),
+    "pv_dual_attn_bwd_ws_bytes": (c_int64, [c_int] * 6),
+    "pv_dual_attn_bwd": (c_int, [c_int] + [c_void_p] * 7 + [c_int] * 6 + [c_float, c_float, c_void_p]),
+    "pv_kv_pack_bwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
 }
 
-# symbols every build must export (the rest are added as later ABI revisions land)
-REQUIRED_SYMBOLS = ["pv_version", "pv_last_error", "pv_launch_count", "pv_set_option", "pv_pack_weight",
-                    "pv_linear_fwd", "pv_kv_tile_bytes", "pv_kv_pack_fwd", "pv_dual_attn_fwd", "pv_dual_attn_core_fwd", "pv_ln_lrelu_fwd",
-                    "pv_group_mean_fwd"]
+# every declared symbol must be exported by the build
+REQUIRED_SYMBOLS = list(_SIGNATURES)
 
 
 def lib() -> ctypes.CDLL:

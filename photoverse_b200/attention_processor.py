@@ -58,7 +58,7 @@ class PhotoVerseAttnProcessor(nn.Module):
 
 
 class _PackedWeights:
-    __slots__ = ("key", "wq", "wkv_text", "wkv_img", "wo", "bo")
+    __slots__ = ("key", "wq", "wkv_text", "wkv_img", "wo", "bo", "_t")
 
 
 class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):

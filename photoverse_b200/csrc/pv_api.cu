@@ -37,6 +37,26 @@ int ln_lrelu(bool out_bf16, const float* x, const float* gamma, const float* bet
 int group_mean(bool in_bf16, bool out_bf16, const void* x, void* y, long long groups, int P, int cols, long long ldy,
                cudaStream_t stream);
 
+int pack_weight_t(bool out_bf16, const float* W, const float* A, const float* Bm, float scaling, void* out, int out_f,
+                  int in_f, int r, cudaStream_t stream);
+int transpose_2d(bool bf16, const void* in, void* out, long long R, long long Cc, long long ldi, long long ldo, cudaStream_t stream);
+long long wgrad_ws_bytes(bool bf16, long long M, long long N, long long K);
+int linear_bwd_weight(bool bf16, const void* G, const void* X, float* dW, void* ws, long long M, long long N, long long K,
+                      long long ldg, long long ldx, float alpha, float beta, cudaStream_t stream);
+long long colsum_ws_bytes(long long M, long long N);
+int col_sum(bool bf16, const void* G, float* out, void* ws, long long M, long long N, long long ldg, cudaStream_t stream);
+long long ln_bwd_ws_bytes(long long groups, long long rows_per_group, int cols);
+int ln_lrelu_bwd(bool bf16, const void* da, const float* x, const float* mean, const float* rstd, const float* gamma,
+                 const float* beta, void* dx, float* dgamma, float* dbeta, void* ws, long long groups,
+                 long long rows_per_group, int cols, float slope, cudaStream_t stream);
+int group_mean_bwd(bool bf16, const void* dy, void* dx, long long groups, int P, int cols, long long ldy, cudaStream_t stream);
+int attn_bwd_chunks(int S);
+int dual_attn_bwd(bool bf16, const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats,
+                  void* dQ, float* part, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                  cudaStream_t stream);
+int kv_pack_bwd(bool bf16, const float* part, const float* kv_img, const float* v_ip_norm, const float* d_vnorm,
+                void* dkv_text, void* dkv_img, int nchunk, int B, int Lt, int Li, int C, int H, cudaStream_t stream);
+
 // ---- globals ---------------------------------------------------------------------------------------
 std::atomic<unsigned long long> g_launches{0};
 int g_opt_epi_swizzle = 1;
@@ -269,6 +289,74 @@ int pv_group_mean_fwd(pv_dtype in_dt, pv_dtype out_dt, const void* x, void* y, i
                       int64_t ldy, void* stream) {
   PV_REQUIRE(x && y, "null pointer");
   return group_mean(in_dt == PV_BF16, out_dt == PV_BF16, x, y, groups, P, cols, ldy, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward entry points
+// ---------------------------------------------------------------------------------------------------------
+int pv_pack_weight_t(pv_dtype out_dt, const float* W, const float* lora_A, const float* lora_B, float scaling,
+                     void* W_eff_t, int out_features, int in_features, int r, void* stream) {
+  PV_REQUIRE(W && W_eff_t, "null pointer");
+  return pack_weight_t(out_dt == PV_BF16, W, lora_A, lora_B, scaling, W_eff_t, out_features, in_features, r, as_stream(stream));
+}
+
+int pv_transpose_2d(pv_dtype dt, const void* in, void* out, int64_t rows, int64_t cols, int64_t ldi, int64_t ldo, void* stream) {
+  PV_REQUIRE(in && out, "null pointer");
+  return transpose_2d(dt == PV_BF16, in, out, rows, cols, ldi, ldo, as_stream(stream));
+}
+
+int64_t pv_linear_bwd_weight_ws_bytes(pv_dtype dt, int64_t M, int64_t N, int64_t K) {
+  return wgrad_ws_bytes(dt == PV_BF16, M, N, K);
+}
+
+int pv_linear_bwd_weight(pv_dtype dt, const void* G, const void* X, float* dW, void* ws, int64_t M, int64_t N, int64_t K,
+                         int64_t ldg, int64_t ldx, float alpha, float beta, void* stream) {
+  PV_REQUIRE(G && X && dW, "null pointer");
+  return linear_bwd_weight(dt == PV_BF16, G, X, dW, ws, M, N, K, ldg, ldx, alpha, beta, as_stream(stream));
+}
+
+int64_t pv_col_sum_ws_bytes(int64_t M, int64_t N) { return colsum_ws_bytes(M, N); }
+
+int pv_col_sum(pv_dtype dt, const void* G, float* out, void* ws, int64_t M, int64_t N, int64_t ldg, void* stream) {
+  PV_REQUIRE(G && out, "null pointer");
+  return col_sum(dt == PV_BF16, G, out, ws, M, N, ldg, as_stream(stream));
+}
+
+int64_t pv_ln_lrelu_bwd_ws_bytes(int64_t groups, int64_t rows_per_group, int cols) {
+  return ln_bwd_ws_bytes(groups, rows_per_group, cols);
+}
+
+int pv_ln_lrelu_bwd(pv_dtype dt, const void* da, const float* x, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, void* dx, float* dgamma, float* dbeta, void* ws, int64_t groups,
+                    int64_t rows_per_group, int cols, float slope, void* stream) {
+  PV_REQUIRE(da && x && mean && rstd && gamma && beta && dx && dgamma && dbeta && ws, "null pointer");
+  return ln_lrelu_bwd(dt == PV_BF16, da, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, ws, groups, rows_per_group, cols,
+                      slope, as_stream(stream));
+}
+
+int pv_group_mean_bwd(pv_dtype dt, const void* dy, void* dx, int64_t groups, int P, int cols, int64_t ldy, void* stream) {
+  PV_REQUIRE(dy && dx, "null pointer");
+  return group_mean_bwd(dt == PV_BF16, dy, dx, groups, P, cols, ldy, as_stream(stream));
+}
+
+int64_t pv_dual_attn_bwd_ws_bytes(int B, int S, int C, int H, int Lt, int Li) {
+  if (H <= 0 || C % H != 0) return -1;
+  return static_cast<int64_t>(attn_bwd_chunks(S)) * B * H * 2 * (Lt + Li) * (C / H) * 4;
+}
+
+int pv_dual_attn_bwd(pv_dtype dt, const void* dO, const void* Q, const float* kv_text, const float* kv_img,
+                     const float* stats, void* dQ, void* ws, int B, int S, int C, int H, int Lt, int Li, float w_text,
+                     float w_img, void* stream) {
+  PV_REQUIRE(dO && Q && kv_text && kv_img && stats && dQ && ws, "null pointer");
+  return dual_attn_bwd(dt == PV_BF16, dO, Q, kv_text, kv_img, stats, dQ, static_cast<float*>(ws), B, S, C, H, Lt, Li, w_text,
+                       w_img, as_stream(stream));
+}
+
+int pv_kv_pack_bwd(pv_dtype dt, const void* ws, const float* kv_img, const float* v_ip_norm, const float* d_v_ip_norm,
+                   void* dkv_text, void* dkv_img, int B, int S, int Lt, int Li, int C, int H, void* stream) {
+  PV_REQUIRE(ws && kv_img && v_ip_norm && dkv_text && dkv_img, "null pointer");
+  return kv_pack_bwd(dt == PV_BF16, static_cast<const float*>(ws), kv_img, v_ip_norm, d_v_ip_norm, dkv_text, dkv_img,
+                     attn_bwd_chunks(S), B, Lt, Li, C, H, as_stream(stream));
 }
 
 }  // extern "C"

@@ -176,3 +176,103 @@ def group_mean(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     check(_lib.lib().pv_group_mean_fwd(_dt(x), _dt(out), _ptr(x), _ptr(out), groups, P, cols, out.stride(0),
                                        _stream()), "pv_group_mean_fwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# backward ops (training step)
+# ------------------------------------------------------------------------------------------------------------
+_WS = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (stream-ordered re-use on the current stream)."""
+    key = (device.type, device.index)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
+        _WS[key] = buf
+    return buf
+
+
+def transpose(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c, r] = x[r, c] for a 2-D tensor with contiguous rows."""
+    R, C = x.shape
+    assert x.stride(1) == 1
+    if out is None:
+        out = torch.empty(C, R, device=x.device, dtype=x.dtype)
+    assert out.shape == (C, R) and out.stride(1) == 1
+    check(_lib.lib().pv_transpose_2d(_dt(x), _ptr(x), _ptr(out), R, C, x.stride(0), out.stride(0), _stream()), "pv_transpose_2d")
+    return out
+
+
+def linear_bwd_weight(g: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
+                      beta: float = 0.0) -> torch.Tensor:
+    """dW[N,K] (fp32) = alpha * g^T x + beta * out;  g [M,N], x [M,K] (row-strided ok, same dtype)."""
+    M, N = g.shape
+    K = x.shape[1]
+    assert x.shape[0] == M and g.dtype == x.dtype and g.stride(1) == 1 and x.stride(1) == 1
+    if out is None:
+        assert beta == 0.0
+        out = torch.empty(N, K, device=g.device, dtype=torch.float32)
+    assert out.shape == (N, K) and out.is_contiguous() and out.dtype == torch.float32
+    lib = _lib.lib()
+    ws = _workspace(lib.pv_linear_bwd_weight_ws_bytes(_dt(g), M, N, K), g.device)
+    check(lib.pv_linear_bwd_weight(_dt(g), _ptr(g), _ptr(x), _ptr(out), _ptr(ws), M, N, K, g.stride(0), x.stride(0),
+                                   float(alpha), float(beta), _stream()), "pv_linear_bwd_weight")
+    return out
+
+
+def col_sum(g: torch.Tensor) -> torch.Tensor:
+    M, N = g.shape
+    assert g.stride(1) == 1
+    out = torch.empty(N, device=g.device, dtype=torch.float32)
+    lib = _lib.lib()
+    ws = _workspace(lib.pv_col_sum_ws_bytes(M, N), g.device)
+    check(lib.pv_col_sum(_dt(g), _ptr(g), _ptr(out), _ptr(ws), M, N, g.stride(0), _stream()), "pv_col_sum")
+    return out
+
+
+def ln_lrelu_bwd(da: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
+                 beta: torch.Tensor, groups: int, rows_per_group: int, slope: float = 0.01):
+    """Backward of ln_lrelu: da [rows, cols] (compute dtype, dense), x fp32 [rows, cols] -> (dx, dgamma, dbeta)."""
+    rows, cols = da.shape
+    assert rows == groups * rows_per_group and da.is_contiguous() and x.is_contiguous() and x.dtype == torch.float32
+    dx = torch.empty_like(da)
+    dgamma = torch.empty(groups, cols, device=da.device, dtype=torch.float32)
+    dbeta = torch.empty_like(dgamma)
+    lib = _lib.lib()
+    ws = _workspace(lib.pv_ln_lrelu_bwd_ws_bytes(groups, rows_per_group, cols), da.device)
+    check(lib.pv_ln_lrelu_bwd(_dt(da), _ptr(da), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(dx),
+                              _ptr(dgamma), _ptr(dbeta), _ptr(ws), groups, rows_per_group, cols, float(slope), _stream()),
+          "pv_ln_lrelu_bwd")
+    return dx, dgamma, dbeta
+
+
+def group_mean_bwd(dy: torch.Tensor, P: int) -> torch.Tensor:
+    """dy [groups, cols] (row-strided ok) -> dx [groups, P, cols] = dy / P."""
+    groups, cols = dy.shape
+    assert dy.stride(1) == 1
+    dx = torch.empty(groups, P, cols, device=dy.device, dtype=dy.dtype)
+    check(_lib.lib().pv_group_mean_bwd(_dt(dy), _ptr(dy), _ptr(dx), groups, P, cols, dy.stride(0), _stream()),
+          "pv_group_mean_bwd")
+    return dx
+
+
+def dual_attn_bwd(d_o: torch.Tensor, q: torch.Tensor, kv_text: torch.Tensor, kv_img: torch.Tensor, stats: torch.Tensor,
+                  v_ip_norm: torch.Tensor, d_vnorm: Optional[torch.Tensor], H: int, Lt: int, Li: int, w_text: float,
+                  w_img: float):
+    """(dQ [B,S,C], dkv_text [B*Lt,2C], dkv_img [B*Li,2C]) in the compute dtype."""
+    B, S, C = d_o.shape
+    assert d_o.is_contiguous() and q.is_contiguous() and q.dtype == d_o.dtype and stats.is_contiguous()
+    dq = torch.empty_like(d_o)
+    dkv_text = torch.empty(B * Lt, 2 * C, device=d_o.device, dtype=d_o.dtype)
+    dkv_img = torch.empty(B * Li, 2 * C, device=d_o.device, dtype=d_o.dtype)
+    lib = _lib.lib()
+    ws = _workspace(lib.pv_dual_attn_bwd_ws_bytes(B, S, C, H, Lt, Li), d_o.device)
+    check(lib.pv_dual_attn_bwd(_dt(d_o), _ptr(d_o), _ptr(q), _ptr(kv_text), _ptr(kv_img), _ptr(stats), _ptr(dq), _ptr(ws),
+                               B, S, C, H, Lt, Li, float(w_text), float(w_img), _stream()), "pv_dual_attn_bwd")
+    if d_vnorm is not None:
+        d_vnorm = d_vnorm.to(torch.float32).contiguous()
+    check(lib.pv_kv_pack_bwd(_dt(d_o), _ptr(ws), _ptr(kv_img), _ptr(v_ip_norm), _ptr(d_vnorm), _ptr(dkv_text), _ptr(dkv_img),
+                             B, S, Lt, Li, C, H, _stream()), "pv_kv_pack_bwd")
+    return dq, dkv_text, dkv_img

