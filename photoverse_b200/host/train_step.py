@@ -1,0 +1,80 @@
+"""One PhotoVerse training step around the B200 path (counterpart of reference train.py:463-549, BASELINE config 4).
+
+Scope: the caller of the path.  VAE, CLIP encoders and the tokenizer are outside it: their outputs -- noisy
+latents, timesteps, CLIP ViT-L/14 hidden states, text-encoder states -- are the inputs here (synthetic in the bench).
+What it keeps from the reference:
+  :495,502  text_adapter / image_adapter over all 5 token heads (no token_index)
+  :505      noise_pred = unet(noisy, t, encoder_hidden_states=(text, image_tokens))  -- 16 processors in grad mode:
+            stochastic fusion rule, one torch.rand(1) per layer (attention_processor.py:411-420)
+  :509      L_text = mean |concept_text_embeddings|         :512-513  L_vis = mean ||V_ip|| over the 16 layers
+  :516      L_mse  = MSE(noise_pred, noise)                 :535      loss = L_mse + 0.01 L_text + 0.001 L_vis
+  :538      backward through the frozen UNet into the trainable set
+  :541-544  clip_grad_norm_(1.0) per module group           :547      AdamW
+Data parallel: gradients are allreduced as one flat buffer (photoverse_b200.host.parallel).  The concept-token injection
+into the CLIP text encoder (models/clip.py:17-24) is a NEXT row; until it lands the text adapter is
+trained by L_text alone and ``text`` is a plain input.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from ..unet import get_visual_cross_attention_values_norm
+from .parallel import FlatGradBuffer, trainable_named_parameters
+
+
+@dataclass
+class TrainBatch:
+    noisy_latents: torch.Tensor        # [B,4,h,w]
+    timesteps: torch.Tensor            # [B] float
+    noise: torch.Tensor                # [B,4,h,w] regression target (epsilon prediction)
+    clip_hidden: List[torch.Tensor]    # 5 x [B,257,1024]
+    text: torch.Tensor                 # [B,77,768]
+
+
+def synthetic_train_batch(batch: int, latent: int = 64, seed: int = 0, device="cpu", dtype=torch.float32) -> TrainBatch:
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape):
+        return torch.randn(*shape, generator=g, dtype=torch.float32).to(device=device, dtype=dtype)
+    t = torch.randint(0, 1000, (batch,), generator=g).to(device=device, dtype=torch.float32)
+    return TrainBatch(rn(batch, 4, latent, latent), t, rn(batch, 4, latent, latent), [rn(batch, 257, 1024) for _ in range(5)],
+                      rn(batch, 77, 768))
+
+
+class Trainer:
+    """Persistent state of the training loop: trainable set, flat gradient buffer, AdamW."""
+
+    GROUPS = ("text_adapter.", "image_adapter.", "unet.")
+
+    def __init__(self, unet, image_adapter, text_adapter, lr: float = 1e-4, weight_decay: float = 1e-2, group=None):
+        self.unet, self.image_adapter, self.text_adapter = unet, image_adapter, text_adapter
+        self.named = trainable_named_parameters(unet, image_adapter, text_adapter)
+        if not self.named:
+            raise ValueError("nothing to train: no parameter of the adapters / unet requires grad")
+        self.buf = FlatGradBuffer(self.named)
+        self.opt = torch.optim.AdamW([p for _, p in self.named], lr=lr, betas=(0.9, 0.999), weight_decay=weight_decay,
+                                     eps=1e-8)          # train.py:94-107 defaults
+        self.group = group
+
+    def loss(self, b: TrainBatch):
+        concept = self.text_adapter(b.clip_hidden)                                    # train.py:495
+        img_tokens = self.image_adapter(b.clip_hidden)                                # train.py:502
+        pred = self.unet(b.noisy_latents, b.timesteps, encoder_hidden_states=(b.text, img_tokens)).sample   # :505
+        l_text = concept.float().abs().mean()                                         # :509
+        l_vis = get_visual_cross_attention_values_norm(self.unet).float().mean()      # :512-513
+        l_mse = F.mse_loss(pred.float(), b.noise.float(), reduction="mean")           # :516
+        return l_mse + 0.01 * l_text + 0.001 * l_vis, (l_mse, l_text, l_vis)          # :535
+
+    def step(self, b: TrainBatch, max_grad_norm: float = 1.0):
+        self.opt.zero_grad(set_to_none=True)
+        with torch.enable_grad():
+            loss, parts = self.loss(b)
+        loss.backward()                                                               # :538
+        self.buf.pack()
+        self.buf.allreduce_mean(self.group)                                           # one collective per step
+        self.buf.clip_groups_(self.GROUPS, max_grad_norm)                             # :541-544
+        self.buf.unpack()
+        self.opt.step()                                                               # :547
+        return loss.detach(), tuple(p.detach() for p in parts)
