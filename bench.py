@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="keep the host UNet in NCHW (default: channels_last)")
+    ap.add_argument("--workload", default="generate", choices=["generate", "train"],
+                    help="generate: BASELINE config[1] (the headline line);  train: config[3] training step")
+    ap.add_argument("--train-batch", type=int, default=16, help="samples per GPU per training step (config[3])")
+    ap.add_argument("--lora-rank", type=int, default=8)
     return ap.parse_args()
 
 
@@ -177,27 +181,33 @@ def roofline_leg(device, rows_b, Li, scale):
         os_ = [torch.empty_like(xs[0]) for _ in range(nbuf)]
         ys = [torch.empty_like(xs[0]) for _ in range(nbuf)]
         lib = _lib.lib()
-        st = ops._stream()
 
         def attn_only(i):
             _lib.check(lib.pv_dual_attn_core_fwd(1, ops._ptr(xs[i]), ops._ptr(wq), ops._ptr(kv.Kp), ops._ptr(kv.Vp),
-                                                 ops._ptr(os_[i]), None, rows_b, S, C, H, LT, Li, 1.0, 1.0, st))
+                                                 ops._ptr(os_[i]), None, rows_b, S, C, H, LT, Li, 1.0, 1.0, ops._stream()))
 
         def full(i):
             _lib.check(lib.pv_dual_attn_fwd(1, ops._ptr(xs[i]), ops._ptr(wq), ops._ptr(kv.Kp), ops._ptr(kv.Vp),
                                             ops._ptr(wo), ops._ptr(bo), ops._ptr(ys[i]), None, ops._ptr(os_[i]), None,
-                                            rows_b, S, C, H, LT, Li, 1.0, 1.0, st))
+                                            rows_b, S, C, H, LT, Li, 1.0, 1.0, ops._stream()))
 
         out = {}
         for name, fn in (("attn", attn_only), ("proc", full)):
             for i in range(3):
                 fn(i % nbuf)
             reps = 20
+            torch.cuda.synchronize()
+            # device time: the launches are captured in a CUDA graph (as the generation engine runs them) so that the
+            # Python / ctypes launch rate (~15 us per call) does not bound kernels that are shorter than that
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for i in range(reps):
+                    fn(i % nbuf)
+            gr.replay()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
-            for i in range(reps):
-                fn(i % nbuf)
+            gr.replay()
             e1.record()
             torch.cuda.synchronize()
             out[name + "_us"] = e0.elapsed_time(e1) * 1e3 / reps
@@ -209,12 +219,13 @@ def roofline_leg(device, rows_b, Li, scale):
     f_attn = sum(attn_kernel_flops(rows_b, S, C, Li) for S, C in LAYER_SHAPES)
     f_proc = sum(processor_flops_cached(rows_b, S, C, Li) for S, C in LAYER_SHAPES)
     ach = f_attn / t_attn / 1e12
-    roof = {"bound": "tensor", "kernel": "dual_attn_fwd_tcgen05_kernel (fused Q-proj + dual-branch attention)",
+    roof = {"bound": "tensor", "kernel": "dual_attn_fwd_persistent_kernel (fused Q-proj + dual-branch attention)",
             "achieved": round(ach, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": round(ach / peaks["bf16_tflops"], 4), "peak_source": peaks["source"] + " cuBLAS bf16 burst",
             "traffic": None,
-            "how": f"CUDA events, 20 launches per attn2 layer shape at {rows_b} rows (uncond+cond), inputs rotated "
-                   f"through > L2 of buffers; aggregated over the 16 layers of one UNet evaluation",
+            "how": f"CUDA events around a CUDA graph of 20 launches per attn2 layer shape at {rows_b} rows (uncond+cond), "
+                   f"inputs rotated through > L2 of buffers; aggregated over the 16 layers of one UNet evaluation; "
+                   f"algorithmic FLOPs = 2 rows C^2 + 4 rows C (77 + Li) per launch",
             "per_shape_us": {k: {kk: round(vv, 2) for kk, vv in v.items()} for k, v in fam.items()},
             "processor_tflops": round(f_proc / t_proc / 1e12, 2),
             "processor_frac": round(f_proc / t_proc / 1e12 / peaks["bf16_tflops"], 4),
@@ -268,6 +279,77 @@ def cpu_reference_run(steps, warmup, denoise_steps, latent, token_index, T=5):
                       f"extrapolated as adapters + {denoise_steps} x step; mean of {steps} after {warmup} warm-up"}
 
 
+def run_train(args, rank, world, local_rank):
+    """BASELINE config[3]: one training step = adapters + UNet forward in grad mode (16 processors, stochastic fusion),
+    backward into the trainable set {adapters, to_k_ip/to_v_ip, LoRA A/B}, ONE flat-buffer NCCL allreduce, per-group
+    clipping, AdamW.  bf16 backbone, fp32 masters for the trainable set.  Weak scaling: batch per GPU fixed."""
+    import torch.distributed as dist
+    import photoverse_b200 as pv
+    from photoverse_b200 import _lib
+    from photoverse_b200.host.train_step import Trainer, synthetic_train_batch
+    from photoverse_b200.host.unet_sd15 import UNetSD15
+    from photoverse_b200.lora import inject_lora
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    unet = UNetSD15()
+    pv.set_visual_cross_attention_adapter(unet, num_tokens=(5,))
+    ia, ta = pv.PhotoVerseAdapter(num_tokens=5), pv.PhotoVerseAdapter(num_tokens=5)
+    unet.requires_grad_(False)
+    inject_lora(unet, r=args.lora_rank)
+    unet.to(device=device, dtype=torch.bfloat16).to(memory_format=torch.channels_last)
+    for m in (ia, ta):
+        m.to(device)
+    for n, p in unet.named_parameters():
+        if "to_k_ip" in n or "to_v_ip" in n or "lora_" in n:
+            p.data = p.data.float()                       # fp32 masters for the trainable set
+            p.requires_grad_(True)
+    unet.eval()
+    tr = Trainer(unet, ia, ta)
+    b = synthetic_train_batch(args.train_batch, args.latent, seed=100 + rank, device=device, dtype=torch.bfloat16)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.manual_seed(1000 + rank)
+    for _ in range(args.warmup):
+        tr.step(b)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, _ = tr.step(b)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    if rank == 0:
+        line = {"metric": "training samples/s, adapter + LoRA + to_k_ip/to_v_ip step through dual-branch attention (config[3])",
+                "value": round(args.train_batch * world * args.steps / (ms * 1e-3), 3), "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"config[3]: training step, batch {args.train_batch}/GPU, latent {args.latent}^2, Li=5, LoRA r="
+                                       f"{args.lora_rank} on attn2.to_q/k/v, fwd+bwd through 16 processors + 2 adapters, flat-buffer "
+                                       f"NCCL allreduce of {tr.buf.numel()} fp32 gradients, per-group clip, AdamW",
+                           "batch_per_gpu": args.train_batch, "grad_elements": tr.buf.numel()},
+                "gpu_launches": int(_lib.launch_count() - n0), "clocks": clocks, "final_loss": round(float(loss), 5)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse()
     token_index = args.token_index if args.token_index == "full" else int(args.token_index)
@@ -282,6 +364,8 @@ def main():
               "unet_evals_per_step": "uncond+cond (reference infer.py:103-114)", "image_tokens": Li,
               "token_index": token_index, "l2": "step working set >> L2 (126 MB); roofline leg rotates buffers > L2"}
 
+    if args.workload == "train" and args.impl == "ours":
+        return run_train(args, rank, world, local_rank)
     if args.impl == "reference":
         if rank != 0:
             return 0
