@@ -62,10 +62,13 @@ std::atomic<unsigned long long> g_launches{0};
 int g_opt_epi_swizzle = 1;
 int g_opt_force_bn = 0;
 int g_opt_gemm_two_cta = 1;
+int g_opt_gemm_pair = 1;         // cta_group::2 CTA-pair GEMM (pv_gemm2.cu) for tall projections
 // 1: operands staged in smem (pv_attn.cu)   2: operands in TMEM, 2 CTAs/SM (pv_attn2.cu)
 // 3: persistent, projection / attention / softmax pipelined against each other (pv_attn3.cu)
 int g_opt_attn_variant = 3;
 int g_opt_attn3_stages = 0;
+int g_opt_attn3_prefetch = 0;   // L2 prefetch distance (units) of the X tiles in the persistent attention kernel
+int g_opt_attn3_wstat = 1;      // C = 320: keep the CTA's Wq slice resident in shared memory (A/B switch)
 unsigned long long* g_attn3_trace = nullptr;   // debug timeline buffer (pv_debug_trace)
 int g_attn3_trace_cap = 0;
 int g_opt_attn3_dbg = 0;       // timing experiments on the persistent kernel (results are wrong when != 0)
@@ -178,9 +181,12 @@ int pv_set_option(const char* name, int value) {
   if (!strcmp(name, "epi_swizzle")) { g_opt_epi_swizzle = value; return PV_OK; }
   if (!strcmp(name, "force_bn")) { g_opt_force_bn = value; return PV_OK; }
   if (!strcmp(name, "gemm_two_cta")) { g_opt_gemm_two_cta = value; return PV_OK; }
+  if (!strcmp(name, "gemm_pair")) { g_opt_gemm_pair = value; return PV_OK; }
   if (!strcmp(name, "attn_variant")) { g_opt_attn_variant = value; return PV_OK; }
   if (!strcmp(name, "attn3_dbg")) { g_opt_attn3_dbg = value; return PV_OK; }
   if (!strcmp(name, "attn3_stages")) { g_opt_attn3_stages = value; return PV_OK; }
+  if (!strcmp(name, "attn3_wstat")) { g_opt_attn3_wstat = value; return PV_OK; }
+  if (!strcmp(name, "attn3_prefetch")) { g_opt_attn3_prefetch = value; return PV_OK; }
   PV_FAIL(PV_ERR_INVALID, "unknown option '%s'", name);
 }
 

@@ -35,17 +35,24 @@ constexpr int A3_THREADS = A3_WARPS * 32;
 constexpr int A3_A_BYTES = A3_BM * A3_BK * 2;
 constexpr int A3_W_BYTES = A3_BN * A3_BK * 2;
 constexpr int A3_STAGE_BYTES = A3_A_BYTES + A3_W_BYTES;
-constexpr int A3_STAGES = 3;        // measured on B200: 3, 4, 5 stages give the same projection-pipeline rate
-constexpr int A3_MAX_STAGES = 6;    // timing experiments only (dbg >= 4 lets the ring spill into the unused K/V area)
+constexpr int A3_MAX_STAGES = 4;
+constexpr int A3_KB_WSTAT = 5;      // K-blocks of the resident Wq slice (C = 320)
 
-template <int D>
+// WSTAT (C = 320 only): the CTA's Wq slice [160 x 320] stays resident in shared memory for all of its units and only X
+// is streamed -- 16 KB instead of 36 KB of TMA ingest per K-block.  Measured on B200 (tools/attn_dbg.py, dbg 7): the
+// kernel is bound by per-SM TMA ingest (~44 B/clk), not by the tensor pipe or the softmax warps.
+template <int D, bool WSTAT>
 struct Attn3Cfg {
   static constexpr int HPC = A3_BN / D;
   static constexpr int D_PAD = (D + 15) / 16 * 16;
   static constexpr int QB_COLS = D_PAD / 2;
   static constexpr int KV_TILE_BYTES = A3_KEYS * D_PAD * 2;
   static constexpr int KV_BYTES = HPC * 2 * KV_TILE_BYTES;
-  static constexpr int OFF_KV = A3_STAGES * A3_STAGE_BYTES;
+  static constexpr int STAGES = WSTAT ? 2 : 3;      // measured: 3, 4, 5 stages give the same projection-pipeline rate
+  static constexpr int STAGE_BYTES = WSTAT ? A3_A_BYTES : A3_STAGE_BYTES;
+  static constexpr int OFF_W = STAGES * STAGE_BYTES;
+  static constexpr int W_RES_BYTES = WSTAT ? A3_KB_WSTAT * A3_W_BYTES : 0;
+  static constexpr int OFF_KV = OFF_W + W_RES_BYTES;
   static constexpr int OW = (D == 160) ? 80 : D;                 // channels per O staging tile / TMA store
   static constexpr int OST_WARP_BYTES = 32 * OW * 2;             // one [32 rows x OW] bf16 tile per softmax warp
   static constexpr int OFF_OST = OFF_KV + KV_BYTES;
@@ -71,9 +78,11 @@ struct Attn3Params {
   float* stats;            // optional [B,H,S,4]
   int S, C, H, Lt, Li;
   int G, MT;               // head groups per sample (C/160), row tiles per sample
+  int V;                   // units per head group = B * MT
   long long units;         // B * G * MT
   float w_text, w_img, scale_log2e;
   int dbg_stages;
+  int prefetch;            // X tiles prefetched into L2 this many units ahead (0 = off)
   unsigned long long* trace;   // optional [1 + 3*n] event buffer (CTA 0 only): count, then (event, index, clock) triples
   int trace_cap;
   int dbg;                 // timing experiments only (pv_set_option attn3_dbg): 1 no softmax math, 2 + no S load / O store, 3 + no Q conversion
@@ -159,13 +168,14 @@ __device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
-template <int D, bool LT77>
+template <int D, bool LT77, bool WSTAT>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
                                 const __grid_constant__ CUtensorMap tmO, const Attn3Params p) {
-  using Cfg = Attn3Cfg<D>;
+  using Cfg = Attn3Cfg<D, WSTAT>;
   constexpr int HPC = Cfg::HPC;
   constexpr int D_PAD = Cfg::D_PAD;
+  constexpr int nst = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* kv = smem + Cfg::OFF_KV;
@@ -180,15 +190,19 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
   uint64_t* s_full = slot_free + 2;             // [2] per softmax group
   uint64_t* p_ready = s_full + 2;               // [2]
   uint64_t* o_full = p_ready + 2;               // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* w_full = o_full + 2;                // 1  resident Wq slice loaded (WSTAT)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kblocks = p.C / A3_BK;
-  const int nst_max = Cfg::OFF_BAR / A3_STAGE_BYTES < A3_MAX_STAGES ? Cfg::OFF_BAR / A3_STAGE_BYTES : A3_MAX_STAGES;
-  const int nst = (p.dbg >= 4 && p.dbg_stages > 0) ? (p.dbg_stages < nst_max ? p.dbg_stages : nst_max) : A3_STAGES;
-  const int u0 = static_cast<int>((p.units * blockIdx.x) / gridDim.x);
-  const int u1 = static_cast<int>((p.units * (blockIdx.x + 1)) / gridDim.x);
+  // Static schedule: CTA c serves head group g = c % G (so its Wq slice and, mostly, its K/V tiles never change) and a
+  // contiguous range [u0, u1) of that group's V = B * MT (sample, row tile) units.
+  const int g = blockIdx.x % p.G;
+  const int r_cta = blockIdx.x / p.G;
+  const int ncta_g = (gridDim.x - g + p.G - 1) / p.G;
+  const int u0 = static_cast<int>((static_cast<long long>(p.V) * r_cta) / ncta_g);
+  const int u1 = static_cast<int>((static_cast<long long>(p.V) * (r_cta + 1)) / ncta_g);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -200,6 +214,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     }
     mbar_init(kv_full, 1);
     mbar_init(kv_free, 1);
+    mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_ready[i], 256);
@@ -223,26 +238,48 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     // ===================== TMA producer =====================
     {
       uint32_t it = 0;
-      int prev_bg = -1;
+      int prev_b = -1;
       uint32_t kv_gen = 0;
+      if constexpr (WSTAT) {
+        if (u0 < u1 && elect_one()) {
+          mbar_expect_tx(w_full, Cfg::W_RES_BYTES);
+          for (int kb = 0; kb < A3_KB_WSTAT; ++kb)
+            tma_load_3d(smem + Cfg::OFF_W + kb * A3_W_BYTES, &tmWq, w_full, kb * A3_BK, g * A3_BN, 0);
+        }
+        __syncwarp();
+      }
+      // X tiles are read once, from HBM (~2100 cycles round trip): prefetch them into L2 `pf` units ahead so that the
+      // ring's loads are L2 hits and a short ring is enough
+      const int pf = p.prefetch;
+      auto prefetch_unit = [&](int u) {
+        if (u < u1 && elect_one()) {
+          const int b = u / p.MT;
+          const int mt = u - b * p.MT;
+          for (int kb = 0; kb < kblocks; ++kb) tma_prefetch_3d(&tmX, kb * A3_BK, mt * A3_BM, b);
+        }
+        __syncwarp();
+      };
+      for (int k = 0; k < pf; ++k) prefetch_unit(u0 + k);
       for (int u = u0; u < u1; ++u) {
-        const int bg = u / p.MT;
-        const int mt = u - bg * p.MT;
-        const int b = bg / p.G;
-        const int g = bg - b * p.G;
+        const int b = u / p.MT;
+        const int mt = u - b * p.MT;
+        if (pf > 0) prefetch_unit(u + pf);
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % nst;
           const uint32_t ph = (it / nst) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           if (elect_one()) {
-            uint8_t* a_dst = smem + s * A3_STAGE_BYTES;
-            mbar_expect_tx(&full[s], A3_STAGE_BYTES);
-            tma_load_3d(a_dst, &tmX, &full[s], kb * A3_BK, mt * A3_BM, b);
-            tma_load_3d(a_dst + A3_A_BYTES, &tmWq, &full[s], kb * A3_BK, g * A3_BN, 0);
+            uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+            // timing experiments: dbg 7 streams X only, dbg 8 Wq only (stale operands in the ring; wrong results)
+            const bool ld_x = !(p.dbg == 8 && it >= static_cast<uint32_t>(nst));
+            const bool ld_w = !WSTAT && !(p.dbg == 7 && it >= static_cast<uint32_t>(nst));
+            mbar_expect_tx(&full[s], (ld_x ? A3_A_BYTES : 0) + (ld_w ? A3_W_BYTES : 0));
+            if (ld_x) tma_load_3d(a_dst, &tmX, &full[s], kb * A3_BK, mt * A3_BM, b);
+            if (ld_w) tma_load_3d(a_dst + A3_A_BYTES, &tmWq, &full[s], kb * A3_BK, g * A3_BN, 0);
           }
           __syncwarp();
         }
-        if (bg != prev_bg && p.dbg < 4) {
+        if (b != prev_b && p.dbg < 4) {
           // K / V^T tiles of this (sample, head group): needed only once the projection above has completed
           if (kv_gen > 0) mbar_wait(kv_free, (kv_gen - 1) & 1);
           if (elect_one()) {
@@ -255,7 +292,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
           }
           __syncwarp();
           ++kv_gen;
-          prev_bg = bg;
+          prev_b = b;
         }
       }
     }
@@ -265,6 +302,9 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     A3Trace tr = a3_trace_init(p, 0);
     uint32_t it = 0;
     int i = 0;
+    if constexpr (WSTAT) {
+      if (u0 < u1) mbar_wait(w_full, 0);
+    }
     for (int u = u0; u < u1; ++u, ++i) {
       const int slot = i & 1;
       if (i >= 2) mbar_wait(&slot_free[slot], ((i >> 1) - 1) & 1);
@@ -281,9 +321,9 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
             mbar_arrive(&empty[s]);
             if (kb == kblocks - 1) mbar_arrive(&q_full[slot]);
           } else {
-          const uint8_t* a_src = smem + s * A3_STAGE_BYTES;
+          const uint8_t* a_src = smem + s * Cfg::STAGE_BYTES;
           const uint64_t da = umma_desc_sw128(a_src);
-          const uint64_t dw = umma_desc_sw128(a_src + A3_A_BYTES);
+          const uint64_t dw = umma_desc_sw128(WSTAT ? smem + Cfg::OFF_W + kb * A3_W_BYTES : a_src + A3_A_BYTES);
 #pragma unroll
           for (int k = 0; k < A3_BK / 16; ++k)
             if (p.dbg != 6 || k == 0) umma_bf16_ss(tmem + slot * A3_BN, da + 2 * k, dw + 2 * k, idesc_q, (kb | k) != 0);
@@ -310,7 +350,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     const int nheads = (p.dbg >= 4) ? 0 : (u1 - u0) * HPC;
     int issued_qk = 0;
     uint32_t kv_gen = 0;
-    int kv_bg = -1;                 // (sample, head group) whose K/V tiles are resident
+    int kv_b = -1;                  // sample whose K/V tiles (of this CTA's head group) are resident
     int q_units_ready = 0;          // units [0, q_units_ready) have had their q_ready observed
     auto unit_of = [&](int nn) { return nn / HPC; };
     auto issue_qk = [&](int nn) {
@@ -332,11 +372,11 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
 #pragma unroll 1
     for (int nn = 0; nn < nheads; ++nn) {
       const int i = unit_of(nn), j = nn - i * HPC;
-      const int bg = (u0 + i) / p.MT;
+      const int b = (u0 + i) / p.MT;
       if (issued_qk <= nn) {
         // first head of a unit whose Q was not ready for look-ahead (or new K/V tiles): blocking
         if (q_units_ready <= i) { mbar_wait(&q_ready[i & 1], (i >> 1) & 1); q_units_ready = i + 1; }
-        if (bg != kv_bg) { mbar_wait(kv_full, kv_gen & 1); ++kv_gen; kv_bg = bg; }
+        if (b != kv_b) { mbar_wait(kv_full, kv_gen & 1); ++kv_gen; kv_b = b; }
         tc_fence_after();
         issue_qk(nn);
         issued_qk = nn + 1;
@@ -344,7 +384,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
       if (nn + 1 < nheads && issued_qk == nn + 1) {
         const int i2 = unit_of(nn + 1);
         bool ok = (i2 == i);
-        if (!ok && (u0 + i2) / p.MT == kv_bg) {             // next unit, same K/V: look ahead only if Q is ready
+        if (!ok && (u0 + i2) / p.MT == kv_b) {             // next unit, same K/V: look ahead only if Q is ready
           if (q_units_ready > i2) ok = true;
           else if (mbar_test_wait(&q_ready[i2 & 1], (i2 >> 1) & 1)) { ok = true; q_units_ready = i2 + 1; }
         }
@@ -377,7 +417,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
         }
         umma_commit(&o_full[w]);
         // last head of the last unit that uses the resident K/V tiles -> the producer may overwrite them
-        if (j == HPC - 1 && nn + 1 < nheads && (u0 + i + 1) / p.MT != bg) umma_commit(kv_free);
+        if (j == HPC - 1 && nn + 1 < nheads && (u0 + i + 1) / p.MT != b) umma_commit(kv_free);
       }
       __syncwarp();
       a3_trace(tr, 21, nn);
@@ -455,10 +495,8 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     for (int u = u0; u < u1; ++u, ++i) {
       const int slot = i & 1;
       const uint32_t tslot = tlane + slot * A3_BN;
-      const int bg = u / p.MT;
-      const int mt = u - bg * p.MT;
-      const int b = bg / p.G;
-      const int g = bg - b * p.G;
+      const int b = u / p.MT;
+      const int mt = u - b * p.MT;
       const int m0 = mt * A3_BM;
 
       // ---- Q: fp32 accumulator -> packed bf16, written inside the columns this group has just read ----
@@ -673,14 +711,16 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
 
 extern int g_opt_attn3_dbg;
 extern int g_opt_attn3_stages;
+extern int g_opt_attn3_wstat;
+extern int g_opt_attn3_prefetch;
 extern unsigned long long* g_attn3_trace;
 extern int g_attn3_trace_cap;
 
-template <int D, bool LT77>
+template <int D, bool LT77, bool WSTAT>
 static int launch_attn3(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const Attn3Params& p,
                         cudaStream_t stream) {
-  using Cfg = Attn3Cfg<D>;
-  auto kern = dual_attn_fwd_persistent_kernel<D, LT77>;
+  using Cfg = Attn3Cfg<D, WSTAT>;
+  auto kern = dual_attn_fwd_persistent_kernel<D, LT77, WSTAT>;
   static bool attr_done = false;
   if (!attr_done) {
     PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -716,18 +756,23 @@ int dual_attn_core_bf16_persistent(const void* X, const void* Wq, const void* Kp
   p.S = S; p.C = C; p.H = H; p.Lt = Lt; p.Li = Li;
   p.G = C / A3_BN;
   p.MT = (S + A3_BM - 1) / A3_BM;
+  p.V = B * p.MT;
   p.units = static_cast<long long>(B) * p.G * p.MT;
   PV_REQUIRE(p.units < (1ll << 30), "too many work units");
   p.w_text = w_text; p.w_img = w_img;
   p.dbg = g_opt_attn3_dbg;
   p.dbg_stages = g_opt_attn3_stages;
+  p.prefetch = g_opt_attn3_prefetch;
   p.trace = g_attn3_trace;
   p.trace_cap = g_attn3_trace_cap;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(d));
   switch (d) {
-    case 40: return Lt == 77 ? launch_attn3<40, true>(tmX, tmWq, tmO, p, stream) : launch_attn3<40, false>(tmX, tmWq, tmO, p, stream);
-    case 80: return Lt == 77 ? launch_attn3<80, true>(tmX, tmWq, tmO, p, stream) : launch_attn3<80, false>(tmX, tmWq, tmO, p, stream);
-    default: return Lt == 77 ? launch_attn3<160, true>(tmX, tmWq, tmO, p, stream) : launch_attn3<160, false>(tmX, tmWq, tmO, p, stream);
+    case 40:
+      if (C == A3_KB_WSTAT * A3_BK && g_opt_attn3_wstat)
+        return Lt == 77 ? launch_attn3<40, true, true>(tmX, tmWq, tmO, p, stream) : launch_attn3<40, false, true>(tmX, tmWq, tmO, p, stream);
+      return Lt == 77 ? launch_attn3<40, true, false>(tmX, tmWq, tmO, p, stream) : launch_attn3<40, false, false>(tmX, tmWq, tmO, p, stream);
+    case 80: return Lt == 77 ? launch_attn3<80, true, false>(tmX, tmWq, tmO, p, stream) : launch_attn3<80, false, false>(tmX, tmWq, tmO, p, stream);
+    default: return Lt == 77 ? launch_attn3<160, true, false>(tmX, tmWq, tmO, p, stream) : launch_attn3<160, false, false>(tmX, tmWq, tmO, p, stream);
   }
 }
 

@@ -202,6 +202,10 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUte
 }
 
 extern int g_opt_gemm_two_cta;
+extern int g_opt_gemm_pair;
+int gemm2_bf16(const void* A, const void* W, const float* bias, void* D, bool out_f32, long long M, long long N, long long K,
+               long long batch, long long lda, long long ldw, long long ldd, long long strideA, long long strideW,
+               long long strideBias, long long strideD, cudaStream_t stream);
 
 template <int BN>
 static int launch_bn(bool out_f32, bool swz, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD,
@@ -252,6 +256,9 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* D, bool out
   PV_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(D)) % 16 == 0,
              "pointers must be 16-byte aligned");
   PV_REQUIRE(batch <= 65535 && (M + GEMM_BM - 1) / GEMM_BM <= 65535, "grid too large");
+  // CTA-pair (cta_group::2) kernel for the tall projections of the path: M >= 2048 rows, N a multiple of 32
+  if (g_opt_gemm_pair != 0 && g_opt_force_bn == 0 && M >= 2048 && N >= 160 && N % 32 == 0)
+    return gemm2_bf16(A, W, bias, D, out_f32, M, N, K, batch, lda, ldw, ldd, strideA, strideW, strideBias, strideD, stream);
   const bool two_cta = g_opt_gemm_two_cta != 0 && (K + GEMM_BK - 1) / GEMM_BK <= 8;
   const int bn = pick_bn(M, N, batch, two_cta);
   const bool swz = g_opt_epi_swizzle != 0 || out_f32 || two_cta;

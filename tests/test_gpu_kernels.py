@@ -45,6 +45,27 @@ def test_linear_bf16(cuda_device, M, N, K, bn, out_f32, swz):
     assert _lib_loaded()
 
 
+@pytest.mark.parametrize("pair", [0, 1], ids=["single-cta", "cta-pair"])
+@pytest.mark.parametrize("out_f32", [False, True])
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (2500, 640, 640), (2048, 1280, 1280), (8192, 768, 1024), (3000, 1024, 1024)])
+def test_linear_bf16_tall(cuda_device, M, N, K, out_f32, pair):
+    """Tall projections (out projection / adapter layers): the cta_group::2 CTA-pair kernel vs the single-CTA kernel."""
+    from photoverse_b200 import _lib, ops
+    _lib.set_option("gemm_pair", pair)
+    try:
+        g = torch.Generator().manual_seed(M + N)
+        a = torch.randn(M, K, generator=g).to(cuda_device, torch.bfloat16)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device, torch.bfloat16)
+        b = torch.randn(N, generator=g).to(cuda_device)
+        y = ops.linear(a, w, b, out_dtype=torch.float32 if out_f32 else torch.bfloat16)
+        ref = a.float() @ w.float().t() + b
+        err = (y.float() - ref).abs().max().item()
+        tol = 2e-5 * K ** 0.5 + (0 if out_f32 else 4e-3 * ref.abs().max().item())
+        assert err <= tol, f"max err {err} > {tol}"
+    finally:
+        _lib.set_option("gemm_pair", 1)
+
+
 def test_linear_bf16_batched_strided(cuda_device):
     from photoverse_b200 import ops
     g = torch.Generator().manual_seed(3)

@@ -13,8 +13,13 @@ dt = torch.bfloat16
 g = torch.Generator().manual_seed(0)
 ROWS, LI = 16, int(os.environ.get("PV_LI", "1"))
 _lib.set_option("attn_variant", 3)
+_lib.set_option("attn3_wstat", int(os.environ.get("PV_WSTAT", "1")))
+_lib.set_option("attn3_prefetch", int(os.environ.get("PV_PF", "0")))
 lib = _lib.lib()
-for S, C in [(4096, 320), (1024, 640), (256, 1280), (64, 1280)]:
+SHAPES = [(4096, 320), (1024, 640), (256, 1280), (64, 1280)]
+if os.environ.get("PV_ONLY_A"):
+    SHAPES = SHAPES[:1]
+for S, C in SHAPES:
     text = torch.randn(ROWS, 77, 768, generator=g).to(dev, dt)
     img = torch.randn(ROWS, LI, 768, generator=g).to(dev, dt)
     wq = (torch.randn(C, C, generator=g) / C ** 0.5).to(dev, dt)
