@@ -24,6 +24,8 @@ int dual_attn_core_bf16_ts(const void* X, const void* Wq, const void* Kp, const 
 int dual_attn_core_bf16_persistent(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
                                    int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                                    cudaStream_t stream);
+int dual_attn_core_bf16_pair(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
+                             int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
 int dual_attn_core_f32(const float* Q, const float* Kp, const float* Vp, float* O, float* stats, int B, int S, int C,
                        int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
 int64_t attn_kv_tile_bytes(int d);
@@ -62,10 +64,13 @@ std::atomic<unsigned long long> g_launches{0};
 int g_opt_epi_swizzle = 1;
 int g_opt_force_bn = 0;
 int g_opt_gemm_two_cta = 1;
-int g_opt_gemm_pair = 1;         // cta_group::2 CTA-pair GEMM (pv_gemm2.cu) for tall projections
+int g_opt_gemm_persistent = 1;   // persistent CTA-pair GEMM (pv_gemm3.cu) for the out projection
+int g_opt_gemm_pair = 0;         // cta_group::2 CTA-pair GEMM (pv_gemm2.cu) for tall projections
 // 1: operands staged in smem (pv_attn.cu)   2: operands in TMEM, 2 CTAs/SM (pv_attn2.cu)
 // 3: persistent, projection / attention / softmax pipelined against each other (pv_attn3.cu)
-int g_opt_attn_variant = 3;
+// 4: persistent CTA pairs (cta_group::2), B operands split across the pair (pv_attn4.cu); falls back to 3 when a sample
+//    has a single 128-row tile
+int g_opt_attn_variant = 4;
 int g_opt_attn3_stages = 0;
 int g_opt_attn3_prefetch = 0;   // L2 prefetch distance (units) of the X tiles in the persistent attention kernel
 int g_opt_attn3_wstat = 1;      // C = 320: keep the CTA's Wq slice resident in shared memory (A/B switch)
@@ -161,7 +166,9 @@ static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>
 static int attn_core_bf16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
                           int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t st) {
   if (g_opt_attn_variant == 1) return dual_attn_core_bf16(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
-  if (g_opt_attn_variant == 3)
+  if (g_opt_attn_variant == 4 && S > 128)      // CTA pairs need two row tiles per sample
+    return dual_attn_core_bf16_pair(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+  if (g_opt_attn_variant >= 3)
     return dual_attn_core_bf16_persistent(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
   return dual_attn_core_bf16_ts(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
 }
@@ -182,6 +189,7 @@ int pv_set_option(const char* name, int value) {
   if (!strcmp(name, "force_bn")) { g_opt_force_bn = value; return PV_OK; }
   if (!strcmp(name, "gemm_two_cta")) { g_opt_gemm_two_cta = value; return PV_OK; }
   if (!strcmp(name, "gemm_pair")) { g_opt_gemm_pair = value; return PV_OK; }
+  if (!strcmp(name, "gemm_persistent")) { g_opt_gemm_persistent = value; return PV_OK; }
   if (!strcmp(name, "attn_variant")) { g_opt_attn_variant = value; return PV_OK; }
   if (!strcmp(name, "attn3_dbg")) { g_opt_attn3_dbg = value; return PV_OK; }
   if (!strcmp(name, "attn3_stages")) { g_opt_attn3_stages = value; return PV_OK; }

@@ -20,6 +20,7 @@
 // S/P buffers at [320,416) and [416,512), one per softmax group.  Each group drains its O accumulator only after
 // computing its NEXT softmax, so the PV MMA latency is hidden.
 #include "pv_common.cuh"
+#include "pv_softmax.cuh"
 #include "pv_host.h"
 #include "../../include/photoverse_b200.h"
 
@@ -88,86 +89,6 @@ struct Attn3Params {
   int dbg;                 // timing experiments only (pv_set_option attn3_dbg): 1 no softmax math, 2 + no S load / O store, 3 + no Q conversion
 };
 
-template <int N>
-__device__ __forceinline__ void pack_pairs3(const uint32_t* v, uint32_t* out) {
-#pragma unroll
-  for (int i = 0; i < N / 2; ++i) out[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-}
-
-// A drained-later O accumulator of one softmax group (the PV MMA runs while the group computes its next softmax).
-struct PendingO {
-  uint32_t taddr;          // TMEM address (lane quarter included) of the O accumulator
-  float oscale;
-  uint32_t parity;         // phase parity of o_full[wg]
-  int c0, r0, b;           // TMA store coordinates: first channel, first row of this warp's 32-row slab, sample
-  int slot;
-  bool valid;
-};
-
-// Debug timeline: lane 0 of a role warp of CTA 0 appends (event, index, SM clock) to the role's private region of the
-// trace buffer (no atomics: the stores are fire-and-forget).  Off (trace == nullptr) in production.
-struct A3Trace {
-  unsigned long long* base;
-  int n, cap;
-};
-__device__ __forceinline__ A3Trace a3_trace_init(const Attn3Params& p, int role) {
-  A3Trace t;
-  const int per = p.trace_cap / 4;
-  t.base = (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? p.trace + 4 + static_cast<size_t>(role) * per * 3 : nullptr;
-  t.n = 0;
-  t.cap = per;
-  return t;
-}
-__device__ __forceinline__ void a3_trace(A3Trace& t, int ev, int idx) {
-  if (t.base != nullptr && t.n < t.cap) {
-    t.base[3 * t.n] = static_cast<unsigned long long>(ev);
-    t.base[3 * t.n + 1] = static_cast<unsigned long long>(idx);
-    t.base[3 * t.n + 2] = static_cast<unsigned long long>(clock64());
-    ++t.n;
-  }
-}
-__device__ __forceinline__ void a3_trace_done(const Attn3Params& p, const A3Trace& t, int role) {
-  if (t.base != nullptr) p.trace[role] = static_cast<unsigned long long>(t.n);
-}
-
-// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 -- half the issue slots of the scalar forms)
-__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-// 32 consecutive TMEM columns of this thread's lane into r[0..31] (no wait)
-__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-
 template <int D, bool LT77, bool WSTAT>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
@@ -233,7 +154,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
 
   // register re-distribution (warpgroup granular): the producer / issuer warps need few, the row threads many
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");   // 128*88 + 256*208 == 384*168 (the launch allocation)
   if (warp == 0) {
     // ===================== TMA producer =====================
     {
@@ -299,7 +220,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
   } else if (warp == 1) {
     // ===================== projection MMA issuer: Q(unit) = X Wq^T  (M=128, N=160, K=C) =====================
     constexpr uint32_t idesc_q = umma_idesc_bf16(A3_BM, A3_BN);
-    A3Trace tr = a3_trace_init(p, 0);
+    A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 0);
     uint32_t it = 0;
     int i = 0;
     if constexpr (WSTAT) {
@@ -336,7 +257,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
       }
       a3_trace(tr, 11, i);
     }
-    a3_trace_done(p, tr, 0);
+    a3_trace_done_raw(p.trace, tr, 0);
   } else if (warp == 2) {
     // ===================== attention MMA issuer =====================
     // Flat loop over the heads of all units of this CTA (head nn belongs to softmax group nn & 1 and uses that
@@ -346,7 +267,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     //   the QK^T MMAs that read the packed Q living there.
     constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BM, A3_KEYS);
     constexpr uint32_t idesc_o = umma_idesc_bf16(A3_BM, (D == 160) ? 80 : D_PAD);
-    A3Trace tr = a3_trace_init(p, 1);
+    A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1);
     const int nheads = (p.dbg >= 4) ? 0 : (u1 - u0) * HPC;
     int issued_qk = 0;
     uint32_t kv_gen = 0;
@@ -422,7 +343,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
       __syncwarp();
       a3_trace(tr, 21, nn);
     }
-    a3_trace_done(p, tr, 1);
+    a3_trace_done_raw(p.trace, tr, 1);
   }
   } else {
     // ===================== softmax groups (warps 4..7 and 8..11): one thread per query row =====================
@@ -435,7 +356,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     const int Lt = p.Lt;
     const int Li = p.Li;
     const float cs = p.scale_log2e;
-    A3Trace tr = a3_trace_init(p, 2 + wg);
+    A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 2 + wg);
     if (q != 0) tr.base = nullptr;
     PendingO pend;
     pend.valid = false;
@@ -658,29 +579,32 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
         if (p.w_text != 0.f) { fi = ai / at; oscale = at; }
         else                 { text_on = false; fi = 1.f; oscale = ai; }
         }
-        uint32_t pk[A3_KEYS / 2];
-#pragma unroll
-        for (int k = 0; k < A3_IMG_OFF / 2; ++k)
-          pk[k] = text_on ? pack_bf16x2(__uint_as_float(sr[2 * k]), __uint_as_float(sr[2 * k + 1])) : 0u;
-        {
-          const uint64_t fi2 = f2_pack(fi, fi);
-#pragma unroll
-          for (int k = A3_IMG_OFF / 2; k < A3_KEYS / 2; ++k) {
-            float a, b2;
-            f2_unpack(f2_mul(f2_pack(__uint_as_float(sr[2 * k]), __uint_as_float(sr[2 * k + 1])), fi2), a, b2);
-            pk[k] = pack_bf16x2(a, b2);
-          }
-        }
-
         // the previous head of this group: its PV ran while the softmax above was computed.  It must leave TMEM
         // before P(nn) is published, because PV(nn) overwrites the group's O columns.
         if (pend.valid) {          // only heads of this same unit reach here (d = 40: the group's first head)
           drain(pend);
           pend.valid = false;
         }
-        tmem_st_x16(sbuf, pk);
-        tmem_st_x16(sbuf + 16, pk + 16);
-        tmem_st_x16(sbuf + 32, pk + 32);
+        // P (bf16 pairs) over the first 48 columns of the S buffer, packed and stored 32 keys at a time
+        {
+          const uint64_t fi2 = f2_pack(fi, fi);
+#pragma unroll
+          for (int c = 0; c < A3_KEYS / 32; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int e = 32 * c + 2 * k;
+              if (e < A3_IMG_OFF) {
+                pk[k] = text_on ? pack_bf16x2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])) : 0u;
+              } else {
+                float a, b2;
+                f2_unpack(f2_mul(f2_pack(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), fi2), a, b2);
+                pk[k] = pack_bf16x2(a, b2);
+              }
+            }
+            tmem_st_x16(sbuf + 16 * c, pk);
+          }
+        }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[wg]);
@@ -700,7 +624,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     if (pend.valid) drain(pend);
     if (elect_one()) bulk_wait_read<0>();
     __syncwarp();
-    a3_trace_done(p, tr, 2 + wg);
+    a3_trace_done_raw(p.trace, tr, 2 + wg);
   }
 
   tc_fence_before();

@@ -83,9 +83,10 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must trap (and surface as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (clock64() - t0 > 2000000000LL) {       // ~1 s of SM clocks: no wait on this path is longer than microseconds
 #ifdef PV_MBAR_DEBUG   // the printf costs registers and a stack frame in every waiting role: debug builds only
       printf("photoverse_b200: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n",
              blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
@@ -298,9 +299,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier of another CTA of the cluster (address from mapa_u32)
+// arrive on an mbarrier of another CTA of the cluster (address from mapa_u32).  Default (.release.cta) semantics on
+// purpose: what is handed over lives in TMEM and is ordered by the tcgen05 fences; a .release.cluster arrive makes ptxas
+// emit a cluster-scope fence (L1 invalidate) that costs ~1000 cycles per hand-off (measured with the device trace).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose completion is signalled on an mbarrier given as a shared::cluster address
 // (the leader CTA's barrier): the .cta_group::2 form allows the barrier to live in the peer CTA.

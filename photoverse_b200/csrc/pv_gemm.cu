@@ -203,6 +203,9 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUte
 
 extern int g_opt_gemm_two_cta;
 extern int g_opt_gemm_pair;
+extern int g_opt_gemm_persistent;
+int gemm3_bf16(const void* A, const void* W, const float* bias, void* D, long long M, long long N, long long K, long long lda,
+               long long ldw, long long ldd, cudaStream_t stream);
 int gemm2_bf16(const void* A, const void* W, const float* bias, void* D, bool out_f32, long long M, long long N, long long K,
                long long batch, long long lda, long long ldw, long long ldd, long long strideA, long long strideW,
                long long strideBias, long long strideD, cudaStream_t stream);
@@ -256,6 +259,9 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* D, bool out
   PV_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(D)) % 16 == 0,
              "pointers must be 16-byte aligned");
   PV_REQUIRE(batch <= 65535 && (M + GEMM_BM - 1) / GEMM_BM <= 65535, "grid too large");
+  // persistent CTA-pair kernel (pv_gemm3.cu): the out projection shapes (bf16 out, N % 160 == 0, K % 64 == 0, tall M)
+  if (g_opt_gemm_persistent != 0 && g_opt_force_bn == 0 && !out_f32 && batch == 1 && M >= 512 && N % 160 == 0 && K % 64 == 0)
+    return gemm3_bf16(A, W, bias, D, M, N, K, lda, ldw, ldd, stream);
   // CTA-pair (cta_group::2) kernel for the tall projections of the path: M >= 2048 rows, N a multiple of 32
   if (g_opt_gemm_pair != 0 && g_opt_force_bn == 0 && M >= 2048 && N >= 160 && N % 32 == 0)
     return gemm2_bf16(A, W, bias, D, out_f32, M, N, K, batch, lda, ldw, ldd, strideA, strideW, strideBias, strideD, stream);

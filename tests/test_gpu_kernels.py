@@ -225,7 +225,7 @@ def test_kv_cache_reuses_projection(cuda_device):
     assert n1 - n0 == 2, f"cached call should launch attention + out-proj only, launched {n1 - n0}"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3], ids=["smem-operands", "tmem-operands", "persistent"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4], ids=["smem-operands", "tmem-operands", "persistent", "cta-pair"])
 @pytest.mark.parametrize("S,C,Li,wt,wi", [(384, 320, 5, 1.0, 1.0), (200, 640, 16, 1.0, 1.0), (128, 1280, 1, 1.0, 1.0),
                                           (256, 320, 3, 2.0, 0.0), (256, 640, 5, 0.0, 2.0), (4096, 320, 5, 1.0, 1.0),
                                           (1024, 640, 4, 1.0, 1.0), (300, 1280, 5, 1.0, 1.0)])
@@ -249,4 +249,4 @@ def test_attention_kernel_variants(cuda_device, variant, S, C, Li, wt, wi):
         err = (y.float() - y_ref).abs().max().item()
         assert err <= 2e-2, f"variant {variant}: max-abs {err}"
     finally:
-        _lib.set_option("attn_variant", 3)
+        _lib.set_option("attn_variant", 4)

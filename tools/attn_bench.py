@@ -16,6 +16,7 @@ li = int(os.environ.get("PV_LI", "1"))
 dev = torch.device("cuda:0")
 for v in variants:
     _lib.set_option("attn_variant", v)
+    _lib.set_option("attn3_wstat", int(os.environ.get("PV_WSTAT", "1")))
     r = bench.roofline_leg(dev, rows, li, 1.0)
     print(f"variant {v}: attn {r['achieved']} TFLOP/s frac {r['frac']}  processor {r['processor_tflops']} TFLOP/s "
           f"{r['processor_ms_per_unet_eval']} ms/eval")

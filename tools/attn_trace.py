@@ -12,7 +12,7 @@ dt = torch.bfloat16
 S, C = int(os.environ.get("PV_S", "4096")), int(os.environ.get("PV_C", "320"))
 ROWS, LI = 16, 1
 g = torch.Generator().manual_seed(0)
-_lib.set_option("attn_variant", 3)
+_lib.set_option("attn_variant", int(os.environ.get("PV_ATTN_VARIANT", "3")))
 _lib.set_option("attn3_dbg", int(os.environ.get("PV_DBG", "0")))
 lib = _lib.lib()
 text = torch.randn(ROWS, 77, 768, generator=g).to(dev, dt)
