@@ -45,13 +45,16 @@ def test_linear_bf16(cuda_device, M, N, K, bn, out_f32, swz):
     assert _lib_loaded()
 
 
-@pytest.mark.parametrize("pair", [0, 1], ids=["single-cta", "cta-pair"])
+@pytest.mark.parametrize("kernel", ["single-cta", "cta-pair", "persistent-pair"])
 @pytest.mark.parametrize("out_f32", [False, True])
 @pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (2500, 640, 640), (2048, 1280, 1280), (8192, 768, 1024), (3000, 1024, 1024)])
-def test_linear_bf16_tall(cuda_device, M, N, K, out_f32, pair):
-    """Tall projections (out projection / adapter layers): the cta_group::2 CTA-pair kernel vs the single-CTA kernel."""
+def test_linear_bf16_tall(cuda_device, M, N, K, out_f32, kernel):
+    """Tall projections (out projection / adapter layers) through each GEMM kernel: single-CTA (pv_gemm.cu), CTA pair
+    (pv_gemm2.cu) and the persistent CTA-pair kernel used for the out projection (pv_gemm3.cu; bf16 out, N % 160 == 0 --
+    other shapes fall through to the default kernel)."""
     from photoverse_b200 import _lib, ops
-    _lib.set_option("gemm_pair", pair)
+    _lib.set_option("gemm_pair", int(kernel == "cta-pair"))
+    _lib.set_option("gemm_persistent", int(kernel == "persistent-pair"))
     try:
         g = torch.Generator().manual_seed(M + N)
         a = torch.randn(M, K, generator=g).to(cuda_device, torch.bfloat16)
@@ -63,7 +66,8 @@ def test_linear_bf16_tall(cuda_device, M, N, K, out_f32, pair):
         tol = 2e-5 * K ** 0.5 + (0 if out_f32 else 4e-3 * ref.abs().max().item())
         assert err <= tol, f"max err {err} > {tol}"
     finally:
-        _lib.set_option("gemm_pair", 1)
+        _lib.set_option("gemm_pair", 0)
+        _lib.set_option("gemm_persistent", 1)
 
 
 def test_linear_bf16_batched_strided(cuda_device):
