@@ -162,6 +162,15 @@ int pv_dual_attn_bwd(pv_dtype dt, const void* dO, const void* Q, const float* kv
 int pv_kv_pack_bwd(pv_dtype dt, const void* ws, const float* kv_img, const float* v_ip_norm, const float* d_v_ip_norm,
                    void* dkv_text, void* dkv_img, int B, int S, int Lt, int Li, int C, int H, void* stream);
 
+/* ---- concept-token injection (models/clip.py:17-24 `_inject_concept_embeddings`) -----------------------
+ * out[b,l] = in[b,l] (l < idx_b) | concept[b,l-idx_b] (idx_b <= l < idx_b+T) | in[b,l-T+1] (l >= idx_b+T)
+ * inputs_embeds, out:[B,L,cols]; concept:[B,T,cols] (dt); placeholder_idx:[B] int32 (device), 0 <= idx_b, idx_b + T <= L.
+ * Backward: d_inputs_embeds:[B,L,cols] (zero at the dropped placeholder and at the truncated tail), d_concept:[B,T,cols]. */
+int pv_inject_concept_fwd(pv_dtype dt, const void* inputs_embeds, const void* concept, const int* placeholder_idx,
+                          void* out, int B, int L, int T, int cols, void* stream);
+int pv_inject_concept_bwd(pv_dtype dt, const void* d_out, const int* placeholder_idx, void* d_inputs_embeds,
+                          void* d_concept, int B, int L, int T, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

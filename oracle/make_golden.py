@@ -111,6 +111,17 @@ def main():
                                      "y_rms": float(np.sqrt((out["y_f64"] ** 2).mean()))}
         np.savez_compressed(os.path.join(GOLDEN_DIR, c.name + ".npz"), y=out["y_f64"].astype(np.float32))
 
+    # concept-token injection (models/clip.py:17-24): the verbatim function is compiled from the reference source
+    from . import clip_oracle
+    fn = ref_loader.load_reference_inject_fn()
+    x, cpt, idx = clip_oracle.inject_case()
+    ref = fn(x, cpt, idx)
+    assert torch.equal(ref, clip_oracle.inject_concept_embeddings(x, cpt, idx)), "inject oracle != reference"
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "inject_concept.npz"), y=ref.numpy()[:, :, :32].copy(), idx=np.array(idx))
+    manifest["cases"]["inject_concept"] = {"kind": "inject", "note": "verbatim models/clip.py:_inject_concept_embeddings, "
+                                                                     "first 32 of 768 channels stored"}
+    print("inject_concept                   : oracle == reference (bit exact)")
+
     with open(os.path.join(GOLDEN_DIR, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print("wrote", GOLDEN_DIR)

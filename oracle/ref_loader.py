@@ -160,3 +160,16 @@ def build_reference_layer(weights, dtype=torch.float32):
     attn.processor = proc
     attn.to(dtype)
     return attn, proc
+
+
+def load_reference_inject_fn():
+    """The verbatim ``_inject_concept_embeddings`` of ``models/clip.py`` (:17-24).  The module itself does not import on
+    the installed transformers (it needs 4.40 internals), so only that function's source is compiled, where it lies."""
+    import ast
+    path = os.path.join(REFERENCE_ROOT, "models", "clip.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "_inject_concept_embeddings")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["_inject_concept_embeddings"]

@@ -34,6 +34,8 @@ _SIGNATURES = {
     "pv_dual_attn_core_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int] * 6 + [c_float, c_float, c_void_p]),
     "pv_ln_lrelu_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     "pv_group_mean_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),
+    "pv_inject_concept_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "pv_inject_concept_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pv_pack_weight_t": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pv_transpose_2d": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "pv_linear_bwd_weight_ws_bytes": (c_int64, [c_int, c_int64, c_int64, c_int64]),

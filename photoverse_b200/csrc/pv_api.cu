@@ -59,6 +59,11 @@ int dual_attn_bwd(bool bf16, const void* dO, const void* Q, const float* kv_text
 int kv_pack_bwd(bool bf16, const float* part, const float* kv_img, const float* v_ip_norm, const float* d_vnorm,
                 void* dkv_text, void* dkv_img, int nchunk, int B, int Lt, int Li, int C, int H, cudaStream_t stream);
 
+int inject_concept_fwd(bool bf16, const void* in, const void* concept, const int* idx, void* out, int B, int L, int T,
+                       int cols, cudaStream_t stream);
+int inject_concept_bwd(bool bf16, const void* dout, const int* idx, void* din, void* dconcept, int B, int L, int T, int cols,
+                       cudaStream_t stream);
+
 // ---- globals ---------------------------------------------------------------------------------------
 std::atomic<unsigned long long> g_launches{0};
 int g_opt_epi_swizzle = 1;
@@ -371,6 +376,18 @@ int pv_kv_pack_bwd(pv_dtype dt, const void* ws, const float* kv_img, const float
   PV_REQUIRE(ws && kv_img && v_ip_norm && dkv_text && dkv_img, "null pointer");
   return kv_pack_bwd(dt == PV_BF16, static_cast<const float*>(ws), kv_img, v_ip_norm, d_v_ip_norm, dkv_text, dkv_img,
                      attn_bwd_chunks(S), B, Lt, Li, C, H, as_stream(stream));
+}
+
+int pv_inject_concept_fwd(pv_dtype dt, const void* inputs_embeds, const void* concept, const int* placeholder_idx,
+                          void* out, int B, int L, int T, int cols, void* stream) {
+  PV_REQUIRE(inputs_embeds && concept && placeholder_idx && out, "null pointer");
+  return inject_concept_fwd(dt == PV_BF16, inputs_embeds, concept, placeholder_idx, out, B, L, T, cols, as_stream(stream));
+}
+
+int pv_inject_concept_bwd(pv_dtype dt, const void* d_out, const int* placeholder_idx, void* d_inputs_embeds,
+                          void* d_concept, int B, int L, int T, int cols, void* stream) {
+  PV_REQUIRE(d_out && placeholder_idx && d_inputs_embeds && d_concept, "null pointer");
+  return inject_concept_bwd(dt == PV_BF16, d_out, placeholder_idx, d_inputs_embeds, d_concept, B, L, T, cols, as_stream(stream));
 }
 
 }  // extern "C"

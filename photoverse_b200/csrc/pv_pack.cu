@@ -148,3 +148,80 @@ int kv_pack(bool bf16, const float* kv_text, const float* kv_img, void* Kp, void
 }
 
 }  // namespace pv
+
+// ------------------------------------------------------------------------------------------------
+// Concept-token injection into the CLIP token embeddings (reference models/clip.py:17-24):
+//   out[b, l] = in[b, l]                 l <  idx_b
+//             = concept[b, l - idx_b]    idx_b <= l < idx_b + T
+//             = in[b, l - T + 1]         l >= idx_b + T          (the placeholder token in[b, idx_b] is dropped,
+//                                                                 the tail is shifted right and truncated at L)
+// and its backward (d_in, d_concept from d_out).  16-byte vectors, one thread per vector.
+// ------------------------------------------------------------------------------------------------
+namespace pv {
+
+__global__ void __launch_bounds__(256)
+inject_concept_fwd_kernel(const uint4* __restrict__ in, const uint4* __restrict__ concept, const int* __restrict__ idx,
+                          uint4* __restrict__ out, int L, int T, int vec_per_row) {
+  const int b = blockIdx.z, l = blockIdx.y;
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v >= vec_per_row) return;
+  const int i = idx[b];
+  uint4 val;
+  if (l < i) val = in[(static_cast<size_t>(b) * L + l) * vec_per_row + v];
+  else if (l < i + T) val = concept[(static_cast<size_t>(b) * T + (l - i)) * vec_per_row + v];
+  else val = in[(static_cast<size_t>(b) * L + (l - T + 1)) * vec_per_row + v];
+  out[(static_cast<size_t>(b) * L + l) * vec_per_row + v] = val;
+}
+
+template <typename T2>
+__global__ void __launch_bounds__(256)
+inject_concept_bwd_kernel(const T2* __restrict__ dout, const int* __restrict__ idx, T2* __restrict__ din,
+                          T2* __restrict__ dconcept, int L, int T, int cols) {
+  // grid.y covers L rows of d_in followed by T rows of d_concept
+  const int b = blockIdx.z, r = blockIdx.y;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const int i = idx[b];
+  if (r < L) {
+    const int l = r;
+    float g = 0.f;
+    if (l < i) g = static_cast<float>(dout[(static_cast<size_t>(b) * L + l) * cols + c]);
+    else if (l > i && l + T - 1 < L) g = static_cast<float>(dout[(static_cast<size_t>(b) * L + (l + T - 1)) * cols + c]);
+    din[(static_cast<size_t>(b) * L + l) * cols + c] = static_cast<T2>(g);
+  } else {
+    const int t = r - L;
+    dconcept[(static_cast<size_t>(b) * T + t) * cols + c] = dout[(static_cast<size_t>(b) * L + (i + t)) * cols + c];
+  }
+}
+
+int inject_concept_fwd(bool bf16, const void* in, const void* concept, const int* idx, void* out, int B, int L, int T,
+                       int cols, cudaStream_t stream) {
+  const int eb = bf16 ? 2 : 4;
+  PV_REQUIRE(B > 0 && B <= 65535 && L > 0 && L <= 65535 && T > 0 && T <= L && cols > 0 && (cols * eb) % 16 == 0,
+             "bad shape B=%d L=%d T=%d cols=%d", B, L, T, cols);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(concept) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+             "pointers must be 16-byte aligned");
+  const int vpr = cols * eb / 16;
+  dim3 grid((vpr + 255) / 256, L, B);
+  inject_concept_fwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<const uint4*>(concept), idx,
+                                                      static_cast<uint4*>(out), L, T, vpr);
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
+int inject_concept_bwd(bool bf16, const void* dout, const int* idx, void* din, void* dconcept, int B, int L, int T, int cols,
+                       cudaStream_t stream) {
+  PV_REQUIRE(B > 0 && B <= 65535 && L > 0 && T > 0 && L + T <= 65535 && cols > 0, "bad shape");
+  dim3 grid((cols + 255) / 256, L + T, B);
+  if (bf16)
+    inject_concept_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dout), idx,
+                                                                      static_cast<__nv_bfloat16*>(din),
+                                                                      static_cast<__nv_bfloat16*>(dconcept), L, T, cols);
+  else
+    inject_concept_bwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(dout), idx, static_cast<float*>(din),
+                                                              static_cast<float*>(dconcept), L, T, cols);
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
+}  // namespace pv

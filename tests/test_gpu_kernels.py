@@ -254,3 +254,27 @@ def test_attention_kernel_variants(cuda_device, variant, S, C, Li, wt, wi):
         assert err <= 2e-2, f"variant {variant}: max-abs {err}"
     finally:
         _lib.set_option("attn_variant", 4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_inject_concept_embeddings_forward_backward(cuda_device, dtype):
+    """Concept-token injection (models/clip.py:17-24): bit-exact vs the golden of the verbatim reference function, and
+    its backward vs autograd through the oracle."""
+    from oracle import clip_oracle
+    from photoverse_b200.clip import inject_concept_embeddings
+    x, c, idx = clip_oracle.inject_case()
+    xd = x.to(cuda_device, dtype).requires_grad_(True)
+    cd = c.to(cuda_device, dtype).requires_grad_(True)
+    y = inject_concept_embeddings(xd, cd, idx)
+    ref = clip_oracle.inject_concept_embeddings(x.to(dtype), c.to(dtype), idx)
+    assert torch.equal(y.detach().cpu(), ref)                                     # a gather: exact in any dtype
+    if dtype == torch.float32:
+        assert np.array_equal(y.detach().cpu().numpy()[:, :, :32], golden("inject_concept")["y"])
+    g = torch.Generator().manual_seed(3)
+    gy = torch.randn(y.shape, generator=g).to(dtype)
+    y.backward(gy.to(cuda_device))
+    xr, cr = x.to(dtype).clone().requires_grad_(True), c.to(dtype).clone().requires_grad_(True)
+    clip_oracle.inject_concept_embeddings(xr, cr, idx).backward(gy)
+    assert torch.equal(xd.grad.cpu(), xr.grad) and torch.equal(cd.grad.cpu(), cr.grad)
+    with pytest.raises(ValueError):
+        inject_concept_embeddings(xd, cd, [5, 1, 75])

@@ -142,3 +142,40 @@ def test_ddim_schedule():
     xt = ac[t] ** 0.5 * x0 + (1 - ac[t]) ** 0.5 * eps
     x_prev = s.c_x[-1] * xt + s.c_eps[-1] * eps
     assert abs(x_prev - (ac[0] ** 0.5 * x0 + (1 - ac[0]) ** 0.5 * eps)) < 1e-9
+
+
+def test_checkpoint_wire_format_round_trip(tmp_path):
+    """models/modeling_utils.py:13-50: dict keys, the attn2 key filter, peft-style LoRA keys, lora_config re-injection."""
+    from photoverse_b200.checkpoint import cross_attention_state_dict, load_photoverse_model, save_progress
+    torch.manual_seed(0)
+    unet = UNetSD15(block_out_channels=(320, 640), layers_per_block=1)
+    pv.set_visual_cross_attention_adapter(unet)
+    inject_lora(unet, r=4, lora_alpha=2.0)
+    ia, ta = pv.PhotoVerseAdapter(num_tokens=2), pv.PhotoVerseAdapter(num_tokens=2)
+    with torch.no_grad():
+        for n, p in unet.named_parameters():
+            if "lora_B" in n:
+                p.normal_()
+    cfg = {"r": 4, "lora_alpha": 2.0, "lora_dropout": 0.0, "target_modules": ["attn2.to_k", "attn2.to_v", "attn2.to_q"]}
+    path = save_progress(ia, ta, unet, str(tmp_path), step=7, lora_config=cfg)
+    assert path.endswith("photoverse_000007.pt")
+    sd = torch.load(path, map_location="cpu")
+    assert set(sd) == {"image_adapter", "text_adapter", "cross_attention_adapter", "lora_config"}
+    keys = list(sd["cross_attention_adapter"])
+    assert keys == list(cross_attention_state_dict(unet)) and all("attn2" in k for k in keys)
+    k = "mid_block.attentions.0.transformer_blocks.0.attn2"
+    for suffix in ("processor.to_k_ip.0.weight", "processor.to_v_ip.0.weight", "to_q.base_layer.weight",
+                   "to_q.lora_A.default.weight", "to_q.lora_B.default.weight", "to_v.lora_B.default.weight"):
+        assert f"{k}.{suffix}" in keys
+    assert not any("to_out" in x or "attn1" in x for x in keys)
+    # load into a fresh model WITHOUT LoRA wrappers: the stored lora_config re-injects them (modeling_utils.py:15-18)
+    torch.manual_seed(1)
+    unet2 = UNetSD15(block_out_channels=(320, 640), layers_per_block=1)
+    pv.set_visual_cross_attention_adapter(unet2)
+    ia2, ta2 = pv.PhotoVerseAdapter(num_tokens=2), pv.PhotoVerseAdapter(num_tokens=2)
+    _, _, unet2, cfg2 = load_photoverse_model(path, ia2, ta2, unet2)
+    assert cfg2 == cfg
+    a, b = cross_attention_state_dict(unet), cross_attention_state_dict(unet2)
+    assert list(a) == list(b) and all(torch.equal(a[x], b[x]) for x in a)
+    assert all(torch.equal(p, q) for p, q in zip(ia.state_dict().values(), ia2.state_dict().values()))
+    assert save_progress(ia, ta, unet, str(tmp_path)).endswith("photoverse.pt")

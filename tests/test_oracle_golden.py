@@ -40,9 +40,10 @@ def test_adapter_oracle_matches_golden(case):
 
 def test_manifest_records_reference_noise_floor():
     m = manifest()
-    assert set(c.name for c in cases.PROC_CASES + cases.ADAPTER_CASES) == set(m["cases"])
+    assert set(c.name for c in cases.PROC_CASES + cases.ADAPTER_CASES) | {"inject_concept"} == set(m["cases"])
     for v in m["cases"].values():
-        assert v["ref_f32_vs_f64_maxabs"] < 2e-6
+        if v["kind"] != "inject":                       # the injection is a gather: exact, no noise floor to record
+            assert v["ref_f32_vs_f64_maxabs"] < 2e-6
 
 
 @pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not mounted")
@@ -92,3 +93,23 @@ def test_flop_formula_matches_survey():
     for (S, C), want in (((4096, 320), 2.188), ((1024, 640), 2.054), ((256, 1280), 2.108), ((64, 1280), 0.769)):
         assert abs(processor_flops(1, S, C, 77, 5) / 1e9 - want) < 2e-3
     assert abs(adapter_oracle.adapter_flops(1, 1) / 1e9 - 1.482) < 1e-3
+
+
+def test_inject_oracle_matches_golden_and_live_reference():
+    """Concept-token injection (models/clip.py:17-24): oracle vs the committed output of the verbatim function, and vs
+    the function itself when the reference is mounted."""
+    import numpy as np
+    import torch
+    from oracle import clip_oracle, ref_loader
+    from tests.helpers import golden
+    x, c, idx = clip_oracle.inject_case()
+    y = clip_oracle.inject_concept_embeddings(x, c, idx)
+    g = golden("inject_concept")
+    assert list(g["idx"]) == idx
+    assert np.array_equal(y.numpy()[:, :, :32], g["y"])
+    assert y.shape == x.shape
+    for b, i in enumerate(idx):                       # structural properties of the reference rule
+        assert torch.equal(y[b, :i], x[b, :i]) and torch.equal(y[b, i:i + 5], c[b])
+        assert torch.equal(y[b, i + 5:], x[b, i + 1:i + 1 + (77 - 5 - i)])
+    if ref_loader.reference_available():
+        assert torch.equal(ref_loader.load_reference_inject_fn()(x, c, idx), y)
