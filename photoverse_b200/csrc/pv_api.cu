@@ -69,6 +69,7 @@ std::atomic<unsigned long long> g_launches{0};
 int g_opt_epi_swizzle = 1;
 int g_opt_force_bn = 0;
 int g_opt_gemm_two_cta = 1;
+int g_opt_pdl = 1;               // programmatic dependent launch for the persistent kernels
 int g_opt_gemm_persistent = 1;   // persistent CTA-pair GEMM (pv_gemm3.cu) for the out projection
 int g_opt_gemm_pair = 0;         // cta_group::2 CTA-pair GEMM (pv_gemm2.cu) for tall projections
 // 1: operands staged in smem (pv_attn.cu)   2: operands in TMEM, 2 CTAs/SM (pv_attn2.cu)
@@ -195,6 +196,7 @@ int pv_set_option(const char* name, int value) {
   if (!strcmp(name, "gemm_two_cta")) { g_opt_gemm_two_cta = value; return PV_OK; }
   if (!strcmp(name, "gemm_pair")) { g_opt_gemm_pair = value; return PV_OK; }
   if (!strcmp(name, "gemm_persistent")) { g_opt_gemm_persistent = value; return PV_OK; }
+  if (!strcmp(name, "pdl")) { g_opt_pdl = value; return PV_OK; }
   if (!strcmp(name, "attn_variant")) { g_opt_attn_variant = value; return PV_OK; }
   if (!strcmp(name, "attn3_dbg")) { g_opt_attn3_dbg = value; return PV_OK; }
   if (!strcmp(name, "attn3_stages")) { g_opt_attn3_stages = value; return PV_OK; }

@@ -152,6 +152,9 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  pdl_wait();                 // nothing above touches data a predecessor kernel may have written
+  pdl_launch_dependents();
+
   // register re-distribution (warpgroup granular): the producer / issuer warps need few, the row threads many
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");   // 128*88 + 256*208 == 384*168 (the launch allocation)
@@ -652,7 +655,7 @@ static int launch_attn3(const CUtensorMap& tmX, const CUtensorMap& tmWq, const C
   }
   const long long sms = sm_count();
   const int grid = static_cast<int>(p.units < sms ? p.units : sms);
-  kern<<<grid, A3_THREADS, Cfg::SMEM_BYTES, stream>>>(tmX, tmWq, tmO, p);
+  PV_CUDA(launch_pdl(kern, dim3(grid), dim3(A3_THREADS), Cfg::SMEM_BYTES, stream, tmX, tmWq, tmO, p));
   PV_LAUNCHED();
   return PV_OK;
 }

@@ -140,6 +140,22 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // Everything above reads nothing a predecessor kernel may have written; the resident Wq slice (static weights) is
+  // requested before the wait as well, so launch latency, TMEM allocation and that load overlap the previous kernel's tail.
+  if constexpr (WSTAT) {
+    if (warp == 0) {
+      if (u0 < u1 && elect_one()) {
+        const uint32_t bar = mapa_u32(smem_u32(w_full), 0);
+        if (rank == 0) mbar_expect_tx(w_full, 2 * Cfg::W_RES_BYTES);
+        for (int kb = 0; kb < A4_KB_WSTAT; ++kb)
+          tma_load_3d_2sm(smem + Cfg::OFF_W + kb * A4_WH_BYTES, &tmWq, bar, kb * A4_BK, g * A4_BN + static_cast<int>(rank) * (A4_BN / 2), 0);
+      }
+      __syncwarp();
+    }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+
   // one elected lane per warp arrives on the LEADER CTA's copy of `bar` (after every lane's TMEM traffic is fenced)
   auto arrive_leader = [&](uint64_t* bar) {
     __syncwarp();
@@ -154,15 +170,6 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     uint32_t it = 0;
     int prev_b = -1;
     uint32_t kv_gen = 0;
-    if constexpr (WSTAT) {
-      if (u0 < u1 && elect_one()) {
-        const uint32_t bar = mapa_u32(smem_u32(w_full), 0);
-        if (rank == 0) mbar_expect_tx(w_full, 2 * Cfg::W_RES_BYTES);
-        for (int kb = 0; kb < A4_KB_WSTAT; ++kb)
-          tma_load_3d_2sm(smem + Cfg::OFF_W + kb * A4_WH_BYTES, &tmWq, bar, kb * A4_BK, g * A4_BN + static_cast<int>(rank) * (A4_BN / 2), 0);
-      }
-      __syncwarp();
-    }
     for (int u = u0; u < u1; ++u) {
       const int b = u / p.MTP;
       const int mt = 2 * (u - b * p.MTP) + static_cast<int>(rank);
@@ -652,7 +659,7 @@ static int launch_attn4(const CUtensorMap& tmX, const CUtensorMap& tmWq, const C
   }
   const long long max_pairs = sm_count() / 2;
   const int npairs = static_cast<int>(unit_pairs < max_pairs ? unit_pairs : max_pairs);
-  kern<<<2 * npairs, A4_THREADS, Cfg::SMEM_BYTES, stream>>>(tmX, tmWq, tmO, p);
+  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(A4_THREADS), Cfg::SMEM_BYTES, stream, tmX, tmWq, tmO, p));
   PV_LAUNCHED();
   return PV_OK;
 }

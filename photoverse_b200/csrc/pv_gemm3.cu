@@ -91,11 +91,10 @@ gemm3_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    uint32_t it = 0;
-    if constexpr (WSTAT) {
+  // Everything above (and the resident-W load below, issued before the wait) reads only static weights: it overlaps the
+  // tail of the previous kernel in the stream.  A, D are touched only after the predecessor has completed.
+  if constexpr (WSTAT) {
+    if (warp == 0) {
       if (u0 < u1 && elect_one()) {
         const uint32_t bar = mapa_u32(smem_u32(w_full), 0);
         if (rank == 0) mbar_expect_tx(w_full, 2 * Cfg::W_RES_BYTES);
@@ -104,6 +103,13 @@ gemm3_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       }
       __syncwarp();
     }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    uint32_t it = 0;
     for (int u = u0; u < u1; ++u) {
       const int m0 = (2 * u + static_cast<int>(rank)) * 128;
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
@@ -221,7 +227,7 @@ static int launch_g3(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUten
   const long long units = static_cast<long long>(G) * V;
   const long long max_pairs = sm_count() / 2;
   const int npairs = static_cast<int>(units < max_pairs ? units : max_pairs);
-  kern<<<2 * npairs, G3_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmW, tmD, bias, G, V, K);
+  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(G3_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmW, tmD, bias, G, V, K));
   PV_LAUNCHED();
   return PV_OK;
 }
