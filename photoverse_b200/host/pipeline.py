@@ -23,6 +23,7 @@ import torch
 from .. import _lib
 from ..unet import prepare_kv, set_kv_cache
 from .ddim import make_ddim_schedule
+from .dpm_solver import make_dpmpp_2m_schedule
 
 
 @dataclass
@@ -72,13 +73,15 @@ class _GraphedUNet:
 @torch.no_grad()
 def run_generation(unet, image_adapter, text_adapter, inputs: GenInputs, num_steps: int = 50,
                    guidance_scale: float = 1.0, token_index=0, mode: str = "batched", use_cuda_graph: bool = True,
-                   kv_cache: bool = True, return_aux: bool = False):
+                   kv_cache: bool = True, return_aux: bool = False, scheduler: str = "ddim"):
     """Returns the final latents [B,4,h,w] (and the adapter outputs if ``return_aux``)."""
     assert mode in ("batched", "two_call", "cond_only")
     if mode == "cond_only" and guidance_scale != 1.0:
         raise ValueError("mode='cond_only' drops the unconditional branch: only valid for guidance_scale == 1")
     dev, dtype = inputs.noise.device, inputs.noise.dtype
-    sched = make_ddim_schedule(num_steps)
+    assert scheduler in ("ddim", "dpmpp_2m")          # ddim: BASELINE metric; dpmpp_2m: the reference's sampler (infer.py:39-40)
+    sched = make_ddim_schedule(num_steps) if scheduler == "ddim" else make_dpmpp_2m_schedule(num_steps)
+    x0_prev = None
 
     # ---- adapters: once per generation (infer.py:89-91) ----
     concept_text = text_adapter(inputs.clip_hidden, token_index=token_index) if text_adapter is not None else None
@@ -124,7 +127,14 @@ def run_generation(unet, image_adapter, text_adapter, inputs: GenInputs, num_ste
                 eps = eps_c
             else:
                 eps = eps_u + guidance_scale * (eps_c - eps_u)          # infer.py:116
-            latents = sched.c_x[i] * latents + sched.c_eps[i] * eps     # DDIM step (eta = 0)
+            if scheduler == "ddim":
+                latents = sched.c_x[i] * latents + sched.c_eps[i] * eps     # DDIM step (eta = 0)
+            else:                                                            # DPM-Solver++(2M), data-prediction form
+                x0 = sched.kx[i] * latents + sched.ke[i] * eps
+                nxt = sched.cx[i] * latents + sched.c0[i] * x0
+                if sched.c0p[i] != 0.0:
+                    nxt = nxt + sched.c0p[i] * x0_prev
+                latents, x0_prev = nxt, x0
     finally:
         set_kv_cache(unet, False)
     if return_aux:

@@ -66,3 +66,22 @@ def test_engine_matches_run_generation_and_is_batch_invariant(cuda_device):
                     inp.text_uncond[:1], inp.noise[:1])
     d = run_generation(unet, ia, ta, one, num_steps=8, mode="batched", use_cuda_graph=False)
     assert _cos(d, c[:1]) >= 0.999
+
+
+def test_dpmpp_2m_generation_matches_oracle_arm(cuda_device):
+    """The reference's own sampler (DPM-Solver++(2M), infer.py:39-40) around the CUDA path vs the same loop around the
+    oracle processors: final-latent cosine >= 0.999 (25 steps, latent 32^2, bf16)."""
+    from oracle.host_reference import clone_adapter_as_oracle, clone_with_oracle_processors
+    from photoverse_b200.host.pipeline import run_generation, synthetic_inputs
+    dtype = torch.bfloat16
+    unet, ia, ta = _models(cuda_device, dtype)
+    ref_unet = clone_with_oracle_processors(unet)
+    ref_ia, ref_ta = clone_adapter_as_oracle(ia, cuda_device, dtype), clone_adapter_as_oracle(ta, cuda_device, dtype)
+    inp = synthetic_inputs(1, 32, seed=11, device=cuda_device, dtype=dtype)
+    lat = run_generation(unet, ia, ta, inp, num_steps=25, guidance_scale=3.0, mode="batched", scheduler="dpmpp_2m")
+    ref = run_generation(ref_unet, ref_ia, ref_ta, inp, num_steps=25, guidance_scale=3.0, mode="two_call",
+                         use_cuda_graph=False, kv_cache=False, scheduler="dpmpp_2m")
+    assert torch.isfinite(lat.float()).all()
+    c = _cos(lat, ref)
+    print(f"dpm-solver++(2M) final-latent cosine {c:.6f}")
+    assert c >= 0.999

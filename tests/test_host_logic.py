@@ -179,3 +179,31 @@ def test_checkpoint_wire_format_round_trip(tmp_path):
     assert list(a) == list(b) and all(torch.equal(a[x], b[x]) for x in a)
     assert all(torch.equal(p, q) for p, q in zip(ia.state_dict().values(), ia2.state_dict().values()))
     assert save_progress(ia, ta, unet, str(tmp_path)).endswith("photoverse.pt")
+
+
+def test_dpmpp_2m_schedule_is_exact_for_a_perfect_denoiser():
+    """DPM-Solver++(2M) (reference sampler, infer.py:39-40): with the exact epsilon of a fixed x0 every step must land on
+    alpha_t x0 + sigma_t n exactly (the solver integrates the data-prediction ODE exactly for constant x0), for both the
+    first-order start, the 2M steps and the lower-order final step; coefficients are finite and the grid is descending."""
+    import numpy as np
+    from photoverse_b200.host.dpm_solver import make_dpmpp_2m_schedule
+    betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000) ** 2
+    ac = np.cumprod(1 - betas)
+    for n in (10, 25, 50):
+        s = make_dpmpp_2m_schedule(n)
+        assert len(s.timesteps) == n and s.timesteps[0] == 999 and all(a > b for a, b in zip(s.timesteps, s.timesteps[1:]))
+        assert all(np.isfinite(v) for v in s.cx + s.c0 + s.c0p + s.kx + s.ke)
+        assert s.c0p[0] == 0.0 and all(c != 0.0 for c in s.c0p[1:-1]) and (s.c0p[-1] == 0.0) == (n < 15)
+        x0, noise = 0.7, -1.3
+        nodes = s.timesteps + [0]
+        x = ac[nodes[0]] ** 0.5 * x0 + (1 - ac[nodes[0]]) ** 0.5 * noise
+        x0_prev = None
+        for i in range(n):
+            t = nodes[i]
+            eps = (x - ac[t] ** 0.5 * x0) / (1 - ac[t]) ** 0.5              # the perfect epsilon-prediction
+            d = s.kx[i] * x + s.ke[i] * eps
+            assert abs(d - x0) < 1e-9
+            x = s.cx[i] * x + s.c0[i] * d + (s.c0p[i] * x0_prev if s.c0p[i] != 0.0 else 0.0)
+            x0_prev = d
+            tn = nodes[i + 1]
+            assert abs(x - (ac[tn] ** 0.5 * x0 + (1 - ac[tn]) ** 0.5 * noise)) < 1e-9
