@@ -56,6 +56,8 @@ def parse():
                     help="generate: BASELINE config[1] (the headline line);  train: config[3] training step")
     ap.add_argument("--train-batch", type=int, default=16, help="samples per GPU per training step (config[3])")
     ap.add_argument("--lora-rank", type=int, default=8)
+    ap.add_argument("--lora-dropout", type=float, default=0.0,
+                    help="train workload: peft lora_dropout (reference default 0.1; 0 = SURVEY config 4 parity setting)")
     return ap.parse_args()
 
 
@@ -302,7 +304,7 @@ def run_train(args, rank, world, local_rank):
     pv.set_visual_cross_attention_adapter(unet, num_tokens=(5,))
     ia, ta = pv.PhotoVerseAdapter(num_tokens=5), pv.PhotoVerseAdapter(num_tokens=5)
     unet.requires_grad_(False)
-    inject_lora(unet, r=args.lora_rank)
+    inject_lora(unet, r=args.lora_rank, lora_dropout=args.lora_dropout)
     unet.to(device=device, dtype=torch.bfloat16).to(memory_format=torch.channels_last)
     for m in (ia, ta):
         m.to(device)
@@ -311,6 +313,8 @@ def run_train(args, rank, world, local_rank):
             p.data = p.data.float()                       # fp32 masters for the trainable set
             p.requires_grad_(True)
     unet.eval()
+    if args.lora_dropout > 0:
+        pv.unet.set_cross_attention_layers_to_train(unet)     # train.py:462 (activates the LoRA dropout)
     tr = Trainer(unet, ia, ta)
     b = synthetic_train_batch(args.train_batch, args.latent, seed=100 + rank, device=device, dtype=torch.bfloat16)
 
@@ -343,7 +347,7 @@ def run_train(args, rank, world, local_rank):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"config[3]: training step, batch {args.train_batch}/GPU, latent {args.latent}^2, Li=5, LoRA r="
-                                       f"{args.lora_rank} on attn2.to_q/k/v, fwd+bwd through 16 processors + 2 adapters, flat-buffer "
+                                       f"{args.lora_rank} (dropout {args.lora_dropout}) on attn2.to_q/k/v, fwd+bwd through 16 processors + 2 adapters, flat-buffer "
                                        f"NCCL allreduce of {tr.buf.numel()} fp32 gradients, per-group clip, AdamW",
                            "batch_per_gpu": args.train_batch, "grad_elements": tr.buf.numel()},
                 "gpu_launches": int(_lib.launch_count() - n0), "clocks": clocks, "final_loss": round(float(loss), 5)}

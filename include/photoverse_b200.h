@@ -171,6 +171,13 @@ int pv_inject_concept_fwd(pv_dtype dt, const void* inputs_embeds, const void* co
 int pv_inject_concept_bwd(pv_dtype dt, const void* d_out, const int* placeholder_idx, void* d_inputs_embeds,
                           void* d_concept, int B, int L, int T, int cols, void* stream);
 
+/* ---- LoRA dropout backward (peft==0.10.0 lora.Linear.forward `lora_B(lora_A(dropout(x))) * scaling`, configured at
+ * train.py:264-269, 348-354) --------------------------------------------------------------------------
+ * dst[i] += keep_mask[i] ? alpha * src[i] : 0, alpha = 1/(1-p).  dst, src: n elements (dt), n % 8 == 0;
+ * keep_mask: n bytes (the boolean keep-mask drawn in the forward pass).                                            */
+int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* keep_mask, float alpha, int64_t n,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,11 +57,18 @@ class ProcessorWeights:
             {k: LoraWeights(cv(v.A), cv(v.B), v.scaling) for k, v in self.lora.items()})
 
 
-def lora_linear(x: torch.Tensor, w: torch.Tensor, lora: Optional[LoraWeights]) -> torch.Tensor:
-    """peft 0.10.0 lora.Linear.forward with dropout p=0 (eval / parity configuration)."""
+def lora_linear(x: torch.Tensor, w: torch.Tensor, lora: Optional[LoraWeights],
+                drop: Optional[Tuple[torch.Tensor, float]] = None) -> torch.Tensor:
+    """peft 0.10.0 ``lora.Linear.forward``: ``result = base_layer(x); result += lora_B(lora_A(dropout(x))) * scaling``.
+    ``drop`` = (keep_mask, p) makes the ``nn.Dropout(p)`` of training mode explicit (train.py:264-269 default p = 0.1):
+    dropout(x) = x * keep_mask / (1 - p); None = eval mode / p = 0 (nn.Identity)."""
     y = x @ w.t()
     if lora is not None:
-        y = y + (x @ lora.A.t()) @ lora.B.t() * lora.scaling
+        xd = x
+        if drop is not None:
+            mask, p = drop
+            xd = x * mask.to(x.dtype).view_as(x) / (1.0 - p)
+        y = y + (xd @ lora.A.t()) @ lora.B.t() * lora.scaling
     return y
 
 
@@ -86,15 +93,17 @@ def _sdpa(q, k, v):
 
 
 def dual_branch_attention(x: torch.Tensor, text: torch.Tensor, img: torch.Tensor,
-                          w: ProcessorWeights, w_text: float = 1.0, w_img: float = 1.0):
-    """Returns (Y [B,S,C], to_v_ip_norm [B,H,Li,1])."""
+                          w: ProcessorWeights, w_text: float = 1.0, w_img: float = 1.0,
+                          drop: Optional[Dict[str, Tuple[torch.Tensor, float]]] = None):
+    """Returns (Y [B,S,C], to_v_ip_norm [B,H,Li,1]).  ``drop``: per-projection (keep_mask, p) of the LoRA dropout."""
     B, S, C = x.shape
     H = w.heads
     d = C // H
+    drop = drop or {}
 
-    q = lora_linear(x, w.to_q, w.lora.get("to_q"))                     # :297
-    k = lora_linear(text, w.to_k, w.lora.get("to_k"))                  # :304
-    v = lora_linear(text, w.to_v, w.lora.get("to_v"))                  # :305
+    q = lora_linear(x, w.to_q, w.lora.get("to_q"), drop.get("to_q"))       # :297
+    k = lora_linear(text, w.to_k, w.lora.get("to_k"), drop.get("to_k"))    # :304
+    v = lora_linear(text, w.to_v, w.lora.get("to_v"), drop.get("to_v"))    # :305
 
     def split(t):                                                       # :310-313
         return t.view(B, -1, H, d).transpose(1, 2)

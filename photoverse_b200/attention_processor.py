@@ -61,6 +61,17 @@ class _PackedWeights:
     __slots__ = ("key", "wq", "wkv_text", "wkv_img", "wo", "bo", "_t")
 
 
+class _UnmergedWeights:
+    """Packed weights of the LoRA-dropout training path: the low-rank branch is a K-extension of the base GEMM,
+    ``[x | dropout(x) A^T] @ [W | s B]^T`` (rank columns padded to 8), instead of a merged W + s B A."""
+    __slots__ = ("key", "wq", "wq_aug", "wkv_text", "wkv_text_aug", "wkv_img", "wkv_img_aug", "wo", "bo", "eye",
+                 "ranks", "_t")
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
 class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):
     def __init__(self, hidden_size, cross_attention_dim=None, num_tokens=(5,), scale=2.0, fusion_rules=(1 / 3, 2 / 3)):
         super().__init__(hidden_size, cross_attention_dim, num_tokens, scale, fusion_rules)
@@ -104,9 +115,7 @@ class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):
         wk, ka, kb, ks, kp = linear_parts(attn.to_k)
         wv, va, vb, vs, vp = linear_parts(attn.to_v)
         if max(qp, kp, vp) > 0.0:
-            raise NotImplementedError(
-                "LoRA dropout > 0 in training mode needs the un-merged low-rank path, which is not built yet; "
-                "set lora_dropout=0 (the parity configuration, SURVEY.md §8d config 4)")
+            raise RuntimeError("internal: merged weights requested while LoRA dropout is active")
         wo, bo = attn.to_out[0].weight, attn.to_out[0].bias
         kip, vip = self.to_k_ip[0].weight, self.to_v_ip[0].weight
         tensors = [wq, qa, qb, wk, ka, kb, wv, va, vb, wo, bo, kip, vip]
@@ -138,6 +147,63 @@ class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):
         if self._kv_cache is not None:
             self._kv_cache.clear()
         return pk
+
+    def lora_dropout_active(self, attn) -> bool:
+        """True when a LoRA-wrapped projection of ``attn`` is in training mode with dropout p > 0 (peft applies
+        ``lora_dropout`` to the low-rank branch input only; train.py:264-269, 348-354)."""
+        return any(linear_parts(m)[4] > 0.0 for m in (attn.to_q, attn.to_k, attn.to_v))
+
+    def _weights_unmerged(self, attn, dtype, device):
+        parts = [linear_parts(m) for m in (attn.to_q, attn.to_k, attn.to_v)]
+        (wq, qa, qb, qs, _), (wk, ka, kb, ks, _), (wv, va, vb, vs, _) = parts
+        wo, bo = attn.to_out[0].weight, attn.to_out[0].bias
+        kip, vip = self.to_k_ip[0].weight, self.to_v_ip[0].weight
+        tensors = [wq, qa, qb, wk, ka, kb, wv, va, vb, wo, bo, kip, vip]
+        key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors) + (qs, ks, vs)
+        cache = self._packed.get(("unmerged", dtype))
+        if cache is not None and cache.key == key:
+            return cache
+        for t in tensors:
+            if t is not None and not t.is_cuda:
+                raise RuntimeError(f"photoverse_b200 needs its weights on the CUDA device (got {t.device})")
+        C, Dc = wq.shape[0], wk.shape[1]
+        rq, rk, rv = (0 if a is None else _pad8(a.shape[0]) for a in (qa, ka, va))
+
+        def m(t):
+            return t.detach().float().contiguous()
+
+        def sb(b, s, r8):        # s * B, rank columns zero-padded to r8 (weight layout only, no activation math)
+            out = torch.zeros(C, r8, device=device, dtype=dtype)
+            out[:, :b.shape[1]] = (b.detach().float() * s).to(dtype)
+            return out
+
+        with torch.no_grad():
+            u = _UnmergedWeights()
+            u.key, u.ranks = key, (rq, rk, rv)
+            u.wq = ops.pack_weight(m(wq), torch.empty(C, C, device=device, dtype=dtype))
+            u.wq_aug = torch.cat([u.wq, sb(qb, qs, rq)], 1).contiguous() if rq else u.wq
+            u.wkv_text = torch.empty(2 * C, Dc, device=device, dtype=dtype)
+            ops.pack_weight(m(wk), u.wkv_text[:C])
+            ops.pack_weight(m(wv), u.wkv_text[C:])
+            u.wkv_img = torch.empty(2 * C, Dc, device=device, dtype=dtype)
+            ops.pack_weight(m(kip), u.wkv_img[:C])
+            ops.pack_weight(m(vip), u.wkv_img[C:])
+            if rk or rv:
+                ext = torch.zeros(2 * C, rk + rv, device=device, dtype=dtype)
+                if rk:
+                    ext[:C, :rk] = sb(kb, ks, rk)
+                if rv:
+                    ext[C:, rk:] = sb(vb, vs, rv)
+                u.wkv_text_aug = torch.cat([u.wkv_text, ext], 1).contiguous()
+                u.wkv_img_aug = torch.cat([u.wkv_img, torch.zeros_like(ext)], 1).contiguous()
+            else:
+                u.wkv_text_aug, u.wkv_img_aug = u.wkv_text, u.wkv_img
+            u.wo = ops.pack_weight(m(wo), torch.empty(C, C, device=device, dtype=dtype))
+            u.bo = m(bo) if bo is not None else torch.zeros(C, device=device, dtype=torch.float32)
+            # bf16: the attention kernel always applies a [C,C] projection; the already-projected Q goes through I
+            u.eye = torch.eye(C, device=device, dtype=dtype) if dtype == torch.bfloat16 else None
+        self._packed[("unmerged", dtype)] = u
+        return u
 
     def _fusion_weights(self):
         """(w_text, w_image) -- reference attention_processor.py:411-420, including its RNG draw."""
@@ -203,7 +269,7 @@ class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):
             x.requires_grad or text.requires_grad or img.requires_grad
             or any(p.requires_grad for p in self.parameters())
             or any(p.requires_grad for m in (attn.to_q, attn.to_k, attn.to_v, attn.to_out[0]) for p in m.parameters()))
-        if needs_grad:
+        if needs_grad or self.lora_dropout_active(attn):
             from .autograd import dual_attn_autograd
             y, vnorm = dual_attn_autograd(self, attn, x, text, img, w_text, w_img)
             self.to_v_ip_norm = vnorm.to(dtype).unsqueeze(-1)

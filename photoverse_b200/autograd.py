@@ -25,12 +25,24 @@ def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
-def _skinny_linear(a2d: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """a2d [M,K] @ w[N,K]^T with a small N (LoRA rank): output rows padded to 16 bytes for the TMA store, view [M,N]."""
+def _skinny_linear(a2d: torch.Tensor, w: torch.Tensor, full: bool = False) -> torch.Tensor:
+    """a2d [M,K] @ w[N,K]^T with a small N (LoRA rank): output rows padded to 16 bytes for the TMA store, view [M,N].
+    ``full``: return the zero-padded [M, pad8(N)] buffer (usable as the K operand of a following GEMM)."""
     M, N = a2d.shape[0], w.shape[0]
-    buf = torch.empty(M, _pad8(N), device=a2d.device, dtype=a2d.dtype)
+    alloc = torch.zeros if (full and N % 8) else torch.empty
+    buf = alloc(M, _pad8(N), device=a2d.device, dtype=a2d.dtype)
     out = buf[:, :N]
     ops.linear(a2d, w, out=out)
+    return buf if full else out
+
+
+def _pad_rows8(w: torch.Tensor) -> torch.Tensor:
+    """[r, in] -> [pad8(r), in], zero rows appended (weight layout only)."""
+    r = w.shape[0]
+    if r % 8 == 0:
+        return w.contiguous()
+    out = torch.zeros(_pad8(r), w.shape[1], device=w.device, dtype=w.dtype)
+    out[:r] = w
     return out
 
 
@@ -105,6 +117,140 @@ class _DualAttnFn(torch.autograd.Function):
         return (dx, dtext, dimg, dkip, dvip, *grads, None)
 
 
+class _DualAttnDropoutFn(torch.autograd.Function):
+    """Training step with LoRA dropout p > 0 (the reference default, train.py:264-269): peft's
+    ``W x + s B A dropout(x)`` cannot be merged into one weight, so the low-rank branch rides along as a K-extension of
+    the projection GEMMs: ``Q = [x | dropout(x) A^T] [W | s B]^T`` (same for K_text / V_text, each with its own mask).
+
+    The keep-masks come from ``torch.native_dropout`` -- the kernel ``nn.Dropout`` dispatches to -- drawn in the
+    reference's order (to_q, to_k, to_v; attention_processor.py:297, 304-305) on same-shaped tensors, so a seeded run
+    consumes the CUDA Philox stream exactly like the reference.  Everything downstream of the masks is C-ABI calls."""
+
+    @staticmethod
+    def forward(ctx, x, text, img, w_kip, w_vip, qA, qB, kA, kB, vA, vB, meta):
+        proc, attn = meta["proc"], meta["attn"]
+        dtype, dev = x.dtype, x.device
+        u = proc._weights_unmerged(attn, dtype, dev)
+        B, S, C = x.shape
+        Lt, Li, Dc = text.shape[1], img.shape[1], text.shape[2]
+        H = attn.heads
+        rq, rk, rv = u.ranks
+        pq, pk_, pv = meta["drop"]
+        x2, text2 = x.view(B * S, C), text.view(B * Lt, Dc)
+
+        def drop(t, p, has):
+            if not has:
+                return None, None
+            if p > 0.0:
+                return torch.native_dropout(t, p, True)
+            return t, None
+
+        xd_q, m_q = drop(x2, pq, qA is not None)
+        xd_k, m_k = drop(text2, pk_, kA is not None)
+        xd_v, m_v = drop(text2, pv, vA is not None)
+
+        # Q = [x | xd A^T] [Wq | s B]^T
+        if rq:
+            xa = torch.empty(B * S, C + rq, device=dev, dtype=dtype)
+            xa[:, :C] = x2
+            ops.linear(xd_q, _pad_rows8(qA.detach().to(dtype)), out=xa[:, C:])
+            q = ops.linear(xa, u.wq_aug).view(B, S, C)
+            del xa
+        else:
+            q = ops.linear(x2, u.wq).view(B, S, C)
+        # K/V of the text branch with their low-rank columns, image branch zero-extended to the same width
+        if rk or rv:
+            ta = torch.empty(B, Lt, Dc + rk + rv, device=dev, dtype=dtype)
+            ta[..., :Dc] = text
+            ta2 = ta.view(B * Lt, Dc + rk + rv)
+            if rk:
+                ops.linear(xd_k, _pad_rows8(kA.detach().to(dtype)), out=ta2[:, Dc:Dc + rk])
+            if rv:
+                ops.linear(xd_v, _pad_rows8(vA.detach().to(dtype)), out=ta2[:, Dc + rk:])
+            ia = torch.zeros(B, Li, Dc + rk + rv, device=dev, dtype=dtype)
+            ia[..., :Dc] = img
+        else:
+            ta, ia = text, img
+        kv = ops.kv_pack(ta, ia, u.wkv_text_aug, u.wkv_img_aug, H)
+        o, stats = ops.dual_attn_core(q, u.eye, kv, meta["w_text"], meta["w_img"], want_stats=True)
+        y = ops.linear(o.view(B * S, C), u.wo, u.bo).view(B, S, C)
+
+        ctx.meta, ctx.u = meta, u
+        ctx.dims = (Lt, Li, H)
+        ctx.has = (qA is not None, kA is not None, vA is not None)
+        ctx.masked = (m_q is not None, m_k is not None, m_v is not None)
+        saved = [x, text, img, stats, kv.kv_text, kv.kv_img, kv.v_ip_norm, q]
+        saved += [t for t in (xd_q, xd_k, xd_v) if t is not None]
+        saved += [t for t in (m_q, m_k, m_v) if t is not None]
+        ctx.save_for_backward(*saved, *[t for t in (qA, qB, kA, kB, vA, vB) if t is not None])
+        ctx.pdt = (w_kip.dtype, w_vip.dtype)
+        return y, kv.v_ip_norm.clone()
+
+    @staticmethod
+    def backward(ctx, dy, dvn):
+        meta, u = ctx.meta, ctx.u
+        Lt, Li, H = ctx.dims
+        it = iter(ctx.saved_tensors)
+        x, text, img, stats, kv_text, kv_img, v_ip_norm, q = (next(it) for _ in range(8))
+        xd = [next(it) if h else None for h in ctx.has]
+        masks = [next(it) if mk else None for mk in ctx.masked]
+        lora = [(next(it), next(it)) if h else None for h in ctx.has]
+        dtype = x.dtype
+        B, S, C = x.shape
+        Dc = text.shape[2]
+        img2 = img.view(B * Li, Dc)
+        tw = getattr(u, "_t", None)
+        if tw is None:
+            tw = {"wq_t": ops.transpose(u.wq), "wo_t": ops.transpose(u.wo),
+                  "wkv_text_t": ops.transpose(u.wkv_text), "wkv_img_t": ops.transpose(u.wkv_img)}
+            u._t = tw
+
+        dy2 = dy.contiguous().view(B * S, C).to(dtype)
+        d_o = ops.linear(dy2, tw["wo_t"]).view(B, S, C)
+        d_vn = dvn if (dvn is not None and meta["vnorm_grad"]) else None
+        dq, dkv_text, dkv_img = ops.dual_attn_bwd(d_o, q, kv_text, kv_img, stats, v_ip_norm, d_vn, H, Lt, Li,
+                                                  meta["w_text"], meta["w_img"])
+        dq2 = dq.view(B * S, C)
+        need = ctx.needs_input_grad
+        dx = ops.linear(dq2, tw["wq_t"]) if need[0] else None                    # base-weight terms
+        dtext = ops.linear(dkv_text, tw["wkv_text_t"]) if need[1] else None
+        dimg = ops.linear(dkv_img, tw["wkv_img_t"]).view(B, Li, Dc) if need[2] else None
+        dkip = ops.linear_bwd_weight(dkv_img[:, :C], img2) if need[3] else None
+        dvip = ops.linear_bwd_weight(dkv_img[:, C:], img2) if need[4] else None
+
+        grads = [None] * 6
+        srcs = ((dq2, dx, need[0]), (dkv_text[:, :C], dtext, need[1]), (dkv_text[:, C:], dtext, need[1]))
+        pdrop = meta["drop"]
+        for j, (g, dinp, need_inp) in enumerate(srcs):
+            if not ctx.has[j]:
+                continue
+            A, Bm = lora[j]
+            s = meta["scal"][j]
+            a_c = A.detach().to(dtype).contiguous()                              # [r, in]
+            bt_c = ops.transpose(Bm.detach().to(dtype).contiguous())             # [r, out]
+            inp = xd[j]                                                          # dropout(x): what the branch saw
+            ub = _skinny_linear(g, bt_c, full=True)                              # dY B   [M, pad8(r)], zero-padded
+            r = a_c.shape[0]
+            if need[5 + 2 * j + 1]:
+                t = _skinny_linear(inp, a_c)                                     # dropout(x) A^T   [M, r]
+                grads[2 * j + 1] = ops.linear_bwd_weight(g, t, alpha=s).to(Bm.dtype)          # dB
+            if need[5 + 2 * j]:
+                grads[2 * j] = ops.linear_bwd_weight(ub[:, :r], inp, alpha=s).to(A.dtype)     # dA
+            if need_inp:
+                # d dropout(x) = s (dY B) A, then through the mask:  d x += keep / (1 - p) * that
+                at8 = ops.transpose(_pad_rows8(a_c * s))                         # [in, pad8(r)]
+                v = ops.linear(ub, at8)                                          # [M, in]
+                if masks[j] is not None:
+                    ops.dropout_bwd_acc(dinp, v, masks[j], pdrop[j])
+                else:
+                    ops.dropout_bwd_acc(dinp, v, torch.ones_like(v, dtype=torch.bool), 0.0)
+        dx = None if dx is None else dx.view(B, S, C)
+        dtext = None if dtext is None else dtext.view(B, Lt, Dc)
+        dkip = None if dkip is None else dkip.to(ctx.pdt[0])
+        dvip = None if dvip is None else dvip.to(ctx.pdt[1])
+        return (dx, dtext, dimg, dkip, dvip, *grads, None)
+
+
 def _transposed(pk, dtype):
     """Transposed copies of the packed forward weights (the weights of the input-gradient GEMMs), cached on the pack."""
     tw = getattr(pk, "_t", None)
@@ -125,11 +271,12 @@ def dual_attn_autograd(proc, attn, x, text, img, w_text, w_img):
             "gradients for the base attn2 projections / to_out are not part of the PhotoVerse training set "
             "(train.py:348-370 trains to_k_ip, to_v_ip and LoRA factors only)")
     meta = {"proc": proc, "attn": attn, "w_text": float(w_text), "w_img": float(w_img),
-            "scal": [p[3] for p in parts], "vnorm_grad": True}
+            "scal": [p[3] for p in parts], "drop": [p[4] for p in parts], "vnorm_grad": True}
     lora_args = []
     for p in parts:
         lora_args += [p[1], p[2]]
-    y, vn = _DualAttnFn.apply(x, text, img, proc.to_k_ip[0].weight, proc.to_v_ip[0].weight, *lora_args, meta)
+    fn = _DualAttnDropoutFn if max(meta["drop"]) > 0.0 else _DualAttnFn
+    y, vn = fn.apply(x, text, img, proc.to_k_ip[0].weight, proc.to_v_ip[0].weight, *lora_args, meta)
     return y, vn
 
 

@@ -63,6 +63,8 @@ int inject_concept_fwd(bool bf16, const void* in, const void* concept, const int
                        int cols, cudaStream_t stream);
 int inject_concept_bwd(bool bf16, const void* dout, const int* idx, void* din, void* dconcept, int B, int L, int T, int cols,
                        cudaStream_t stream);
+int dropout_bwd_acc(bool bf16, void* dst, const void* src, const uint8_t* mask, float alpha, long long n,
+                    cudaStream_t stream);
 
 // ---- globals ---------------------------------------------------------------------------------------
 std::atomic<unsigned long long> g_launches{0};
@@ -390,6 +392,12 @@ int pv_inject_concept_bwd(pv_dtype dt, const void* d_out, const int* placeholder
                           void* d_concept, int B, int L, int T, int cols, void* stream) {
   PV_REQUIRE(d_out && placeholder_idx && d_inputs_embeds && d_concept, "null pointer");
   return inject_concept_bwd(dt == PV_BF16, d_out, placeholder_idx, d_inputs_embeds, d_concept, B, L, T, cols, as_stream(stream));
+}
+
+int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* keep_mask, float alpha, int64_t n,
+                       void* stream) {
+  PV_REQUIRE(dst && src && keep_mask, "null pointer");
+  return dropout_bwd_acc(dt == PV_BF16, dst, src, keep_mask, alpha, n, as_stream(stream));
 }
 
 }  // extern "C"

@@ -224,4 +224,61 @@ int inject_concept_bwd(bool bf16, const void* dout, const int* idx, void* din, v
   return PV_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// LoRA dropout backward (peft lora.Linear: y = W x + s B A dropout(x); train.py:264-269, 348-354):
+//   dst[i] += mask[i] ? alpha * src[i] : 0        alpha = 1 / (1 - p)
+// dst is the input gradient that already holds the base-weight term, src = (dY B) A s, mask the keep-mask of the forward
+// dropout (1 byte per element).  8 elements per thread.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_bwd_acc_kernel(T* __restrict__ dst, const T* __restrict__ src, const uint8_t* __restrict__ mask, float alpha,
+                       long long n) {
+  const long long base = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (base >= n) return;
+  if (base + 8 <= n) {
+    const uint2 m = *reinterpret_cast<const uint2*>(mask + base);
+    const uint8_t* mb = reinterpret_cast<const uint8_t*>(&m);
+    T d[8], v[8];
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(dst + base);
+      *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(src + base);
+    } else {
+      reinterpret_cast<uint4*>(d)[0] = reinterpret_cast<const uint4*>(dst + base)[0];
+      reinterpret_cast<uint4*>(d)[1] = reinterpret_cast<const uint4*>(dst + base)[1];
+      reinterpret_cast<uint4*>(v)[0] = reinterpret_cast<const uint4*>(src + base)[0];
+      reinterpret_cast<uint4*>(v)[1] = reinterpret_cast<const uint4*>(src + base)[1];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (mb[j]) d[j] = static_cast<T>(static_cast<float>(d[j]) + alpha * static_cast<float>(v[j]));
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(dst + base) = *reinterpret_cast<uint4*>(d);
+    } else {
+      reinterpret_cast<uint4*>(dst + base)[0] = reinterpret_cast<uint4*>(d)[0];
+      reinterpret_cast<uint4*>(dst + base)[1] = reinterpret_cast<uint4*>(d)[1];
+    }
+  } else {
+    for (long long i = base; i < n; ++i)
+      if (mask[i]) dst[i] = static_cast<T>(static_cast<float>(dst[i]) + alpha * static_cast<float>(src[i]));
+  }
+}
+
+int dropout_bwd_acc(bool bf16, void* dst, const void* src, const uint8_t* mask, float alpha, long long n,
+                    cudaStream_t stream) {
+  PV_REQUIRE(n > 0 && n % 8 == 0, "element count must be a positive multiple of 8 (n=%lld)", n);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(mask) % 8 == 0, "pointers must be 16-byte (mask: 8-byte) aligned");
+  const long long blocks = (n / 8 + 255) / 256;
+  PV_REQUIRE(blocks <= 0x7fffffffLL, "too many elements");
+  if (bf16)
+    dropout_bwd_acc_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        static_cast<__nv_bfloat16*>(dst), static_cast<const __nv_bfloat16*>(src), mask, alpha, n);
+  else
+    dropout_bwd_acc_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        static_cast<float*>(dst), static_cast<const float*>(src), mask, alpha, n);
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
 }  // namespace pv

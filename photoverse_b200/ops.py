@@ -153,6 +153,22 @@ def dual_attn(x: torch.Tensor, wq: torch.Tensor, kv: PackedKV, wo: torch.Tensor,
     return y, o, stats, q
 
 
+def dual_attn_core(x_or_q: torch.Tensor, wq: Optional[torch.Tensor], kv: PackedKV, w_text: float = 1.0,
+                   w_img: float = 1.0, want_stats: bool = False):
+    """The attention kernel alone (no out projection).  bf16: ``x_or_q`` = X and ``wq`` is applied inside the kernel;
+    fp32: ``x_or_q`` = Q (already projected), ``wq`` ignored.  Returns (O [B,S,C], stats|None)."""
+    B, S, C = x_or_q.shape
+    assert x_or_q.is_contiguous() and x_or_q.dtype == kv.dtype and (kv.B, kv.C) == (B, C)
+    if x_or_q.dtype == torch.bfloat16:
+        assert wq is not None and wq.is_contiguous() and wq.dtype == torch.bfloat16 and wq.shape == (C, C)
+    o = torch.empty_like(x_or_q)
+    stats = torch.empty(B, kv.H, S, 4, device=o.device, dtype=torch.float32) if want_stats else None
+    check(_lib.lib().pv_dual_attn_core_fwd(_dt(x_or_q), _ptr(x_or_q), _ptr(wq), _ptr(kv.Kp), _ptr(kv.Vp), _ptr(o),
+                                           _ptr(stats), B, S, C, kv.H, kv.Lt, kv.Li, float(w_text), float(w_img),
+                                           _stream()), "pv_dual_attn_core_fwd")
+    return o, stats
+
+
 def ln_lrelu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor,
              rows_per_group: int = 0, eps: float = 1e-5, slope: float = 0.01, save_stats: bool = False):
     """out = leaky_relu(layer_norm(x) * gamma + beta); x fp32 [rows, cols] (row-strided ok), out bf16|fp32."""
@@ -276,3 +292,12 @@ def dual_attn_bwd(d_o: torch.Tensor, q: torch.Tensor, kv_text: torch.Tensor, kv_
     check(lib.pv_kv_pack_bwd(_dt(d_o), _ptr(ws), _ptr(kv_img), _ptr(v_ip_norm), _ptr(d_vnorm), _ptr(dkv_text), _ptr(dkv_img),
                              B, S, Lt, Li, C, H, _stream()), "pv_kv_pack_bwd")
     return dq, dkv_text, dkv_img
+
+
+def dropout_bwd_acc(dst: torch.Tensor, src: torch.Tensor, keep_mask: torch.Tensor, p: float) -> torch.Tensor:
+    """dst += keep_mask * src / (1 - p): the input-gradient term of peft's LoRA dropout (in place on ``dst``)."""
+    assert dst.is_contiguous() and src.is_contiguous() and keep_mask.is_contiguous()
+    assert dst.shape == src.shape == keep_mask.shape and dst.dtype == src.dtype and keep_mask.dtype == torch.bool
+    check(_lib.lib().pv_dropout_bwd_acc(_dt(dst), _ptr(dst), _ptr(src), _ptr(keep_mask), 1.0 / (1.0 - float(p)),
+                                        dst.numel(), _stream()), "pv_dropout_bwd_acc")
+    return dst

@@ -22,7 +22,7 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def _oracle_grads(case, x, text, img, gy, gv, wt, wi):
+def _oracle_grads(case, x, text, img, gy, gv, wt, wi, drop=None):
     w = cases.proc_weights(case, torch.float64)
     leaves = {"x": x.double().clone().requires_grad_(True), "text": text.double().clone().requires_grad_(True),
               "img": img.double().clone().requires_grad_(True)}
@@ -31,7 +31,7 @@ def _oracle_grads(case, x, text, img, gy, gv, wt, wi):
     for lw in w.lora.values():
         lw.A.requires_grad_(True)
         lw.B.requires_grad_(True)
-    y, vn = dual_branch_attention(leaves["x"], leaves["text"], leaves["img"], w, wt, wi)
+    y, vn = dual_branch_attention(leaves["x"], leaves["text"], leaves["img"], w, wt, wi, drop)
     loss = (y * gy.double()).sum() + (vn.squeeze(-1) * gv.double()).sum()
     loss.backward()
     out = {k: v.grad for k, v in leaves.items()}
@@ -83,6 +83,74 @@ def test_processor_backward_matches_oracle_autograd(cuda_device, case, dtype):
         assert got[k] is not None, f"no gradient for {k}"
         e = _rel(got[k], r)
         assert e <= REL[dtype], f"{k}: relative error {e:.3e} > {REL[dtype]}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", [
+    cases.ProcCase("drop_c320", B=2, S=200, C=320, Li=5, lora_r=8, seed=76),
+    cases.ProcCase("drop_c640_r4_textonly", B=1, S=256, C=640, Li=1, lora_r=4, w_text=2.0, w_img=0.0, seed=77),
+    cases.ProcCase("drop_c1280", B=1, S=64, C=1280, Li=3, lora_r=16, seed=78),
+], ids=lambda c: c.name)
+def test_processor_lora_dropout_training_matches_oracle(cuda_device, case, dtype):
+    """LoRA dropout p = 0.1 in training mode (the reference default, train.py:264-269): forward and every gradient vs
+    the oracle evaluated with the SAME keep-masks.  The masks are re-drawn here with ``torch.native_dropout`` from the
+    same CUDA generator state in the reference's call order (to_q, to_k, to_v), which also pins the RNG contract."""
+    p_drop = 0.1
+    attn, proc = build_product_layer(case, cuda_device)
+    for name in ("to_q", "to_k", "to_v"):
+        getattr(attn, name).lora_dropout["default"] = torch.nn.Dropout(p_drop)
+    attn.train()
+    for p in attn.parameters():
+        p.requires_grad_(False)
+    trainable = {"to_k_ip": proc.to_k_ip[0].weight, "to_v_ip": proc.to_v_ip[0].weight}
+    for name in ("to_q", "to_k", "to_v"):
+        m = getattr(attn, name)
+        trainable[name + ".A"] = m.lora_A["default"].weight
+        trainable[name + ".B"] = m.lora_B["default"].weight
+    for p in trainable.values():
+        p.requires_grad_(True)
+    assert proc.lora_dropout_active(attn)
+    x, text, img = cases.proc_inputs(case, torch.float32)
+    g = torch.Generator().manual_seed(case.seed)
+    gy = torch.randn(case.B, case.S, case.C, generator=g)
+    gv = torch.randn(case.B, case.H, case.Li, generator=g)
+    xd, td, im = (t.to(cuda_device, dtype).requires_grad_(True) for t in (x, text, img))
+    force_fusion_seed(case.w_text, case.w_img)
+    torch.cuda.manual_seed(1000 + case.seed)
+    with torch.enable_grad():
+        y = attn(xd, encoder_hidden_states=(td, im))
+        vn = proc.to_v_ip_norm
+        loss = (y.float() * gy.to(cuda_device)).sum() + (vn.float().squeeze(-1) * gv.to(cuda_device)).sum()
+    loss.backward()
+    # the reference's draws: nn.Dropout on to_q's input, then to_k's, then to_v's
+    torch.cuda.manual_seed(1000 + case.seed)
+    drop = {}
+    for name, t in (("to_q", xd), ("to_k", td), ("to_v", td)):
+        _, mask = torch.native_dropout(t.detach(), p_drop, True)
+        drop[name] = (mask.cpu(), p_drop)
+    assert not torch.equal(drop["to_k"][0], drop["to_v"][0])
+    y_ref, vn_ref, ref = _oracle_grads(case, x, text, img, gy, gv, case.w_text, case.w_img, drop)
+    assert (y.detach().float().cpu() - y_ref.float()).abs().max().item() <= (1e-4 if dtype == torch.float32 else 2e-2)
+    # and the masks matter: the no-dropout oracle is measurably different
+    y_nodrop, _, _ = _oracle_grads(case, x, text, img, gy, gv, case.w_text, case.w_img, None)
+    assert (y_nodrop - y_ref).abs().max().item() > 1e-3
+    got = {"x": xd.grad, "text": td.grad, "img": im.grad}
+    got.update({k: p.grad for k, p in trainable.items()})
+    for k, r in ref.items():
+        if r is None or r.abs().max() == 0:
+            assert got[k] is None or got[k].abs().max().item() <= 1e-6
+            continue
+        assert got[k] is not None, f"no gradient for {k}"
+        e = _rel(got[k], r)
+        assert e <= REL[dtype], f"{k}: relative error {e:.3e} > {REL[dtype]}"
+    # eval mode: dropout is the identity and the merged-weight fast path is taken again
+    attn.eval()
+    assert not proc.lora_dropout_active(attn)
+    with torch.no_grad():
+        y_eval = attn(xd.detach(), encoder_hidden_states=(td.detach(), im.detach()))
+    w = cases.proc_weights(case, torch.float64)
+    y_eval_ref, _ = dual_branch_attention(x.double(), text.double(), img.double(), w, 1.0, 1.0)
+    assert (y_eval.float().cpu() - y_eval_ref.float()).abs().max().item() <= (1e-4 if dtype == torch.float32 else 2e-2)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])

@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _build(device, dtype, seed=0):
+def _build(device, dtype, seed=0, lora_dropout=0.0):
     import photoverse_b200 as pv
     from photoverse_b200.host.unet_sd15 import UNetSD15
     from photoverse_b200.lora import inject_lora
@@ -16,7 +16,7 @@ def _build(device, dtype, seed=0):
     pv.set_visual_cross_attention_adapter(unet, num_tokens=(5,))
     ia, ta = pv.PhotoVerseAdapter(num_tokens=5), pv.PhotoVerseAdapter(num_tokens=5)
     unet.requires_grad_(False)
-    inject_lora(unet, r=8)
+    inject_lora(unet, r=8, lora_dropout=lora_dropout)
     g = torch.Generator().manual_seed(seed + 1)
     for n, p in unet.named_parameters():
         if "to_k_ip" in n or "to_v_ip" in n:
@@ -28,6 +28,8 @@ def _build(device, dtype, seed=0):
         m.to(device=device, dtype=torch.float32)
     unet.to(dtype)                              # bf16 run: bf16 backbone (adapters keep fp32 masters)
     unet.eval()
+    if lora_dropout > 0:
+        pv.unet.set_cross_attention_layers_to_train(unet)      # train.py:462: activates the LoRA dropout
     return unet, ia, ta
 
 
@@ -87,9 +89,10 @@ def test_train_step_gradients_match_oracle_arm(cuda_device, dtype):
     assert checked > 100
 
 
-def test_trainer_step_updates_only_the_trainable_set(cuda_device):
+@pytest.mark.parametrize("lora_dropout", [0.0, 0.1], ids=["p0", "p0.1"])
+def test_trainer_step_updates_only_the_trainable_set(cuda_device, lora_dropout):
     from photoverse_b200.host.train_step import Trainer, synthetic_train_batch
-    unet, ia, ta = _build(cuda_device, torch.float32, seed=5)
+    unet, ia, ta = _build(cuda_device, torch.float32, seed=5, lora_dropout=lora_dropout)
     frozen_before = {n: p.detach().clone() for n, p in unet.named_parameters() if not p.requires_grad}
     train_before = {n: p.detach().clone() for n, p in unet.named_parameters() if p.requires_grad}
     tr = Trainer(unet, ia, ta, lr=1e-3)

@@ -113,3 +113,22 @@ def test_inject_oracle_matches_golden_and_live_reference():
         assert torch.equal(y[b, i + 5:], x[b, i + 1:i + 1 + (77 - 5 - i)])
     if ref_loader.reference_available():
         assert torch.equal(ref_loader.load_reference_inject_fn()(x, c, idx), y)
+
+
+def test_lora_dropout_oracle_matches_torch_dropout_module():
+    """peft's ``lora_B(lora_A(dropout(x))) * scaling`` with ``nn.Dropout`` (train.py:264-269, p = 0.1 by default): the
+    oracle's explicit keep-mask form equals the module form when the mask comes from the same generator state."""
+    import torch
+    from oracle.processor_oracle import LoraWeights, lora_linear
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 11, 32, generator=g, dtype=torch.float64)
+    w = torch.randn(24, 32, generator=g, dtype=torch.float64)
+    lw = LoraWeights(torch.randn(4, 32, generator=g, dtype=torch.float64),
+                     torch.randn(24, 4, generator=g, dtype=torch.float64), 0.25)
+    torch.manual_seed(123)
+    ref = x @ w.t() + torch.nn.Dropout(0.1)(x) @ lw.A.t() @ lw.B.t() * lw.scaling
+    torch.manual_seed(123)
+    _, mask = torch.native_dropout(x, 0.1, True)
+    assert 0.8 < mask.double().mean().item() < 0.97
+    assert (lora_linear(x, w, lw, (mask, 0.1)) - ref).abs().max().item() <= 1e-12
+    assert torch.equal(lora_linear(x, w, lw, None), x @ w.t() + x @ lw.A.t() @ lw.B.t() * lw.scaling)
