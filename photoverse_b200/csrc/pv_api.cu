@@ -24,6 +24,11 @@ int dual_attn_core_bf16_ts(const void* X, const void* Wq, const void* Kp, const 
 int dual_attn_core_bf16_persistent(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
                                    int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                                    cudaStream_t stream);
+int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
+                                   int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                                   cudaStream_t stream);
+int dual_attn_core_bf16_pair16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
+                               int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
 int dual_attn_core_bf16_pair(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
                              int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
 int dual_attn_core_f32(const float* Q, const float* Kp, const float* Vp, float* O, float* stats, int B, int S, int C,
@@ -78,7 +83,7 @@ int g_opt_gemm_pair = 0;         // cta_group::2 CTA-pair GEMM (pv_gemm2.cu) for
 // 3: persistent, projection / attention / softmax pipelined against each other (pv_attn3.cu)
 // 4: persistent CTA pairs (cta_group::2), B operands split across the pair (pv_attn4.cu); falls back to 3 when a sample
 //    has a single 128-row tile
-int g_opt_attn_variant = 4;
+int g_opt_attn_variant = 6;
 int g_opt_attn3_stages = 0;
 int g_opt_attn3_prefetch = 0;   // L2 prefetch distance (units) of the X tiles in the persistent attention kernel
 int g_opt_attn3_wstat = 1;      // C = 320: keep the CTA's Wq slice resident in shared memory (A/B switch)
@@ -174,6 +179,13 @@ static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>
 static int attn_core_bf16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
                           int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t st) {
   if (g_opt_attn_variant == 1) return dual_attn_core_bf16(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+  if (g_opt_attn_variant == 6 && S > 128) {    // CTA pairs with decoupled roles for C = 320 / head_dim 40, else variant 4
+    if (C == 320 && H > 0 && C / H == 40)
+      return dual_attn_core_bf16_pair_roles(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+    return dual_attn_core_bf16_pair(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+  }
+  if (g_opt_attn_variant == 5 && S > 128)      // CTA pairs, key-split softmax groups (16 softmax warps)
+    return dual_attn_core_bf16_pair16(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
   if (g_opt_attn_variant == 4 && S > 128)      // CTA pairs need two row tiles per sample
     return dual_attn_core_bf16_pair(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
   if (g_opt_attn_variant >= 3)

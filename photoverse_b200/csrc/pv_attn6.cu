@@ -1,0 +1,644 @@
+// photoverse_b200 -- fused Q-projection + dual-branch cross-attention, variant 6: the C = 320 (head_dim 40) layers on
+// persistent CTA pairs with DECOUPLED roles.
+//
+// The device timelines of variants 4 / 5 (tools/attn_trace.py) showed that at C = 320 the kernel is
+// bound by the CUDA-core side, not by the tensor pipe or the TMA ingest: a softmax group spent ~2200 cycles on the
+// softmax of a head, ~1000 on draining the previous O accumulator, ~400 per unit on converting Q, and idled ~40 % of
+// the time on the chain P(n) -> PV(n) -> QK^T(n+2) -> S(n+2), whose every hop costs a few hundred cycles because the
+// single issuer warp shares its scheduler and the SM's MIO path (mbarrier probes ~150-300 cycles) with the softmax warps.
+// This variant removes every one of those serialisations:
+//   * P goes to SHARED memory (12 key chunks x 128 rows x 16 B, canonical K-major no-swizzle layout) instead of over S in
+//     tensor memory: an S buffer is free again as soon as its logits are in registers (`s_free`), so QK^T(n+2) is issued
+//     while softmax(n) is still running and S(n+2) is waiting when the group comes back.  PV is an SS-form MMA.
+//   * TWO issuer warps: warp 2 issues QK^T (waits q_ready / s_free only), warp 3 issues PV (waits p_ready / o_free only).
+//     No ordering between the two streams is needed: every hazard is covered by a barrier (see the role comments).
+//   * FOUR epilogue warps (one per TMEM lane quarter) convert Q (fp32 accumulator -> packed bf16, in place) and drain
+//     the O accumulators (row scale from shared memory, bf16, staging tile, TMA store); they own q_ready / o_free /
+//     slot_free.  The eight softmax warps do nothing but softmax.
+// Shared-memory operands, TMEM maps, the pair protocol (cta_group::2, leader-side barriers, multicast commits) and the
+// softmax arithmetic are those of pv_attn4.cu.
+#include "pv_common.cuh"
+#include "pv_softmax.cuh"
+#include "pv_host.h"
+#include "../../include/photoverse_b200.h"
+
+namespace pv {
+
+constexpr int A6_BM = 128;
+constexpr int A6_BN = 160;
+constexpr int A6_BK = 64;
+constexpr int A6_D = 40;
+constexpr int A6_DPAD = 48;
+constexpr int A6_HPC = 4;                 // heads per 160-column head group
+constexpr int A6_KB = 5;                  // K-blocks of the projection (C = 320)
+constexpr int A6_KEYS = PV_KEYS_PAD;
+constexpr int A6_IMG_OFF = PV_IMG_KEY_OFFSET;
+constexpr int A6_THREADS = 512;           // 0 TMA, 1 projection MMA, 2 QK^T MMA, 3 PV MMA + K/V relay, 4..11 softmax, 12..15 epilogue
+constexpr int A6_STAGES = 4;
+constexpr int A6_A_BYTES = A6_BM * A6_BK * 2;                 // one X stage (this CTA's 128 rows)
+constexpr int A6_WH_BYTES = (A6_BN / 2) * A6_BK * 2;          // this CTA's half of a Wq K-block
+constexpr int A6_KH_BYTES = (A6_KEYS / 2) * A6_DPAD * 2;      // 48 keys of a K tile
+constexpr int A6_VH_BYTES = (A6_DPAD / 2) * A6_KEYS * 2;      // 24 dims of a V^T tile
+constexpr int A6_KV_HEAD_BYTES = A6_KH_BYTES + A6_VH_BYTES;
+constexpr int A6_KV_BYTES = A6_HPC * A6_KV_HEAD_BYTES;
+constexpr int A6_P_BYTES = A6_BM * A6_KEYS * 2;               // one group's P tile
+constexpr int A6_OST_BYTES = 32 * A6_D * 2;                   // one staging slab: 32 rows x 40 channels
+constexpr int A6_OFF_W = A6_STAGES * A6_A_BYTES;
+constexpr int A6_OFF_KV = A6_OFF_W + A6_KB * A6_WH_BYTES;
+constexpr int A6_OFF_OST = A6_OFF_KV + A6_KV_BYTES;           // [epilogue warp][group] slabs
+constexpr int A6_OFF_P = A6_OFF_OST + 4 * 2 * A6_OST_BYTES;
+constexpr int A6_OFF_OSC = A6_OFF_P + 2 * A6_P_BYTES;         // O row scales [group][parity][128] fp32
+constexpr int A6_OFF_BAR = A6_OFF_OSC + 2 * 2 * A6_BM * 4;
+constexpr int A6_SMEM_BYTES = A6_OFF_BAR + 512 + 1024;
+static_assert(A6_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(A6_KEYS == 96 && A6_IMG_OFF == 80, "written for 80 text + 16 image key slots");
+constexpr uint32_t A6_TM_SBUF0 = 320;
+constexpr uint32_t A6_TM_SBUF1 = 416;
+__host__ __device__ constexpr uint32_t a6_q_col(int j) { return 40 * j + 16; }   // packed bf16 Q of head j inside a slot
+__host__ __device__ constexpr uint32_t a6_o_col(int w) { return 48 * w; }        // O accumulator of softmax group w
+
+struct Attn6Params {
+  const uint8_t* Kp;
+  const uint8_t* Vp;
+  float* stats;            // optional [B,H,S,4]
+  int S, C, H, Lt, Li;
+  int G, MTP;              // head groups per sample (C/160), row-tile PAIRS per sample
+  int V;                   // units per head group = B * MTP
+  float w_text, w_img, scale_log2e;
+  unsigned long long* trace;
+  int trace_cap;
+  int dbg;                 // timing experiments only (pv_set_option attn3_dbg): 1 = exponentials on the FMA pipe (wrong results)
+};
+
+template <bool LT77>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(A6_THREADS, 1)
+dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
+                                const __grid_constant__ CUtensorMap tmO, const Attn6Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* kv = smem + A6_OFF_KV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A6_OFF_BAR);
+  uint64_t* full = bars;                        // [STAGES] (leader) both CTAs' X stages landed
+  uint64_t* empty = full + A6_STAGES;           // [STAGES] multicast commit
+  uint64_t* w_full = empty + A6_STAGES;         // 1  (leader) both halves of the resident Wq slice landed
+  uint64_t* kv_full = w_full + 1;               // 1  local: this CTA's K/V halves landed
+  uint64_t* kv_both = kv_full + 1;              // 1  (leader) count 2
+  uint64_t* kv_free = kv_both + 1;              // 1  multicast commit after the last PV of a sample
+  uint64_t* q_full = kv_free + 1;               // [2] multicast commit: Q accumulators of a slot complete
+  uint64_t* q_ready = q_full + 2;               // [2] (leader) packed bf16 Q in both CTAs' TMEM     count 8 (epilogue warps)
+  uint64_t* slot_free = q_ready + 2;            // [2] (leader) every O of the unit has left TMEM      count 8 (epilogue warps)
+  uint64_t* s_full = slot_free + 2;             // [2] multicast commit, per softmax group
+  uint64_t* s_free = s_full + 2;                // [2] (leader) S buffer in registers in both CTAs     count 8 (softmax warps)
+  uint64_t* p_ready = s_free + 2;               // [2] (leader) P tile + row scales in shared memory   count 8 (softmax warps)
+  uint64_t* o_full = p_ready + 2;               // [2] multicast commit: PV complete
+  uint64_t* o_free = o_full + 2;                // [2] (leader) O accumulator in registers             count 8 (epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  // Static schedule (as pv_attn4.cu): pair c serves head group g = c % G and units [u0, u1) of that group's V = B * MTP
+  // (sample, row-tile pair) units; CTA `rank` owns row tile 2 * pair_index + rank.
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int g = pair % p.G;
+  const int r_pair = pair / p.G;
+  const int npair_g = (npairs - g + p.G - 1) / p.G;
+  const int u0 = static_cast<int>((static_cast<long long>(p.V) * r_pair) / npair_g);
+  const int u1 = static_cast<int>((static_cast<long long>(p.V) * (r_pair + 1)) / npair_g);
+  const int nunits = u1 - u0;
+  const int nheads = nunits * A6_HPC;
+  // K/V of one sample serve MTP consecutive units: first unit (relative to u0) of the second sample this pair touches
+  const int first_end = (u0 / p.MTP + 1) * p.MTP - u0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWq);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < A6_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_both, 2);
+    mbar_init(kv_free, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_ready[i], 8);
+      mbar_init(&slot_free[i], 8);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 8);
+      mbar_init(&p_ready[i], 8);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // Nothing above reads what a predecessor kernel may have written; the resident Wq slice (static weights) is requested
+  // before the dependency wait as well.
+  if (warp == 0) {
+    if (nunits > 0 && elect_one()) {
+      const uint32_t bar = mapa_u32(smem_u32(w_full), 0);
+      if (rank == 0) mbar_expect_tx(w_full, 2 * A6_KB * A6_WH_BYTES);
+      for (int kb = 0; kb < A6_KB; ++kb)
+        tma_load_3d_2sm(smem + A6_OFF_W + kb * A6_WH_BYTES, &tmWq, bar, kb * A6_BK, g * A6_BN + static_cast<int>(rank) * (A6_BN / 2), 0);
+    }
+    __syncwarp();
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // one elected lane per warp arrives on the LEADER CTA's copy of `bar`
+  auto arrive_leader = [&](uint64_t* bar) {
+    __syncwarp();
+    if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
+    __syncwarp();
+  };
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // 128*56 + 256*192 + 128*72 == 512*128 (the launch allocation)
+    if (warp == 0) {
+      // ===================== TMA producer (both CTAs: own X rows, own halves of K / V^T) =====================
+      uint32_t it = 0;
+      uint32_t kv_gen = 0;
+      int kv_end = 0;
+      for (int i = 0; i < nunits; ++i) {
+        const int u = u0 + i;
+        const int b = u / p.MTP;
+        const int mt = 2 * (u - b * p.MTP) + static_cast<int>(rank);
+        for (int kb = 0; kb < A6_KB; ++kb, ++it) {
+          const int s = it % A6_STAGES;
+          const uint32_t ph = (it / A6_STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (elect_one()) {
+            const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * A6_A_BYTES);
+            tma_load_3d_2sm(smem + s * A6_A_BYTES, &tmX, bar, kb * A6_BK, mt * A6_BM, b);
+          }
+          __syncwarp();
+        }
+        if (i >= kv_end) {
+          // this CTA's halves of the K / V^T tiles of (sample b, head group g): keys [48 rank, +48) of K, dims
+          // [24 rank, +24) of V^T -- contiguous pieces of the packed UMMA images
+          if (kv_gen > 0) mbar_wait(kv_free, (kv_gen - 1) & 1);
+          if (elect_one()) {
+            mbar_expect_tx(kv_full, A6_KV_BYTES);
+            for (int j = 0; j < A6_HPC; ++j) {
+              const size_t tile = (static_cast<size_t>(b) * p.H + (g * A6_HPC + j)) * (A6_KEYS * A6_DPAD * 2);
+              uint8_t* kd = kv + j * A6_KV_HEAD_BYTES;
+              for (int kc = 0; kc < A6_DPAD / 8; ++kc)
+                bulk_load_1d(kd + kc * (48 * 16), p.Kp + tile + (static_cast<size_t>(kc) * A6_KEYS + 48 * rank) * 16, 48 * 16, kv_full);
+              uint8_t* vd = kd + A6_KH_BYTES;
+              for (int kc = 0; kc < A6_KEYS / 8; ++kc)
+                bulk_load_1d(vd + kc * (24 * 16), p.Vp + tile + (static_cast<size_t>(kc) * A6_DPAD + 24 * rank) * 16, 24 * 16, kv_full);
+            }
+          }
+          __syncwarp();
+          ++kv_gen;
+          kv_end = (kv_end == 0) ? first_end : kv_end + p.MTP;
+        }
+      }
+    } else if (warp == 1) {
+      if (rank == 0) {
+        // ===================== projection MMA issuer (leader): Q = X Wq^T for BOTH CTAs, M = 256, N = 160 =====================
+        constexpr uint32_t idesc_q = umma_idesc_bf16(2 * A6_BM, A6_BN);
+        A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 0);
+        uint32_t it = 0;
+        if (nunits > 0) mbar_wait(w_full, 0);
+        for (int i = 0; i < nunits; ++i) {
+          const int slot = i & 1;
+          if (i >= 2) mbar_wait(&slot_free[slot], ((i >> 1) - 1) & 1);
+          tc_fence_after();
+          a3_trace(tr, 10, i);
+          for (int kb = 0; kb < A6_KB; ++kb, ++it) {
+            const int s = it % A6_STAGES;
+            const uint32_t ph = (it / A6_STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da = umma_desc_sw128(smem + s * A6_A_BYTES);
+              const uint64_t dw = umma_desc_sw128(smem + A6_OFF_W + kb * A6_WH_BYTES);
+#pragma unroll
+              for (int k = 0; k < A6_BK / 16; ++k)
+                umma_bf16_ss_2sm(tmem + slot * A6_BN, da + 2 * k, dw + 2 * k, idesc_q, (kb | k) != 0);
+              umma_commit_2sm(&empty[s]);
+              if (kb == A6_KB - 1) umma_commit_2sm(&q_full[slot]);
+            }
+            __syncwarp();
+          }
+          a3_trace(tr, 11, i);
+        }
+        a3_trace_done_raw(p.trace, tr, 0);
+      }
+    } else if (warp == 2) {
+      if (rank == 0) {
+        // ===================== QK^T issuer (leader): S(nn) = Q_head K_head^T, one head ahead of each softmax group ============
+        // Needs: packed bf16 Q of the unit (q_ready), the sample's K/V (kv_both), S buffer nn & 1 read out (s_free).
+        constexpr uint32_t idesc_s = umma_idesc_bf16(2 * A6_BM, A6_KEYS);
+        A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1);
+        const uint64_t kdesc0 = umma_desc(smem_u32(kv), 48 * 16, 128, UMMA_LAYOUT_NONE);
+        uint32_t kv_gen = 0;
+        int kv_end = 0;
+#pragma unroll 1
+        for (int i = 0; i < nunits; ++i) {
+          mbar_wait(&q_ready[i & 1], (i >> 1) & 1);
+          if (i >= kv_end) {
+            mbar_wait(kv_both, kv_gen & 1);
+            ++kv_gen;
+            kv_end = (kv_end == 0) ? first_end : kv_end + p.MTP;
+          }
+          const uint32_t tslot = tmem + (i & 1) * A6_BN;
+#pragma unroll 1
+          for (int j = 0; j < A6_HPC; ++j) {
+            const int nn = i * A6_HPC + j;
+            if (nn >= 2) mbar_wait(&s_free[j & 1], ((nn - 2) >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t kd = kdesc0 + static_cast<uint32_t>(j * (A6_KV_HEAD_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < A6_DPAD / 16; ++k)
+                umma_bf16_ts_2sm(tmem + ((j & 1) ? A6_TM_SBUF1 : A6_TM_SBUF0), tslot + a6_q_col(j) + k * 8,
+                                 kd + k * ((2 * 48 * 16) >> 4), idesc_s, k != 0);
+              umma_commit_2sm(&s_full[j & 1]);
+            }
+            __syncwarp();
+            a3_trace(tr, 20, nn);
+          }
+        }
+        a3_trace_done_raw(p.trace, tr, 1);
+      }
+    } else {
+      // ===================== K/V relay (both CTAs) + PV issuer (leader): O(nn) = P(nn) V_head =====================
+      // Needs: P tile + row scales in shared memory (p_ready), the group's O accumulator drained (o_free).  PV(nn)
+      // overwrites TMEM columns that held the packed Q of heads 0 / 1 of the slot: their QK^T completed before the
+      // softmax group could read S, i.e. before p_ready.
+      constexpr uint32_t idesc_o = umma_idesc_bf16(2 * A6_BM, A6_DPAD);
+      const uint64_t vdesc0 = umma_desc(smem_u32(kv + A6_KH_BYTES), 24 * 16, 128, UMMA_LAYOUT_NONE);
+      const uint64_t pdesc0 = umma_desc(smem_u32(smem + A6_OFF_P), A6_BM * 16, 128, UMMA_LAYOUT_NONE);
+      A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1);
+      tr.base = nullptr;
+      uint32_t kv_gen = 0;
+      int kv_end = 0;
+#pragma unroll 1
+      for (int i = 0; i < nunits; ++i) {
+        if (i >= kv_end) {
+          mbar_wait(kv_full, kv_gen & 1);                       // my halves of the sample's K / V^T have landed
+          if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(kv_both), 0));
+          __syncwarp();
+          ++kv_gen;
+          kv_end = (kv_end == 0) ? first_end : kv_end + p.MTP;
+        }
+        if (rank != 0) continue;
+        const uint32_t tslot = tmem + (i & 1) * A6_BN;
+#pragma unroll 1
+        for (int j = 0; j < A6_HPC; ++j) {
+          const int nn = i * A6_HPC + j;
+          const uint32_t w = j & 1;
+          mbar_wait(&p_ready[w], (nn >> 1) & 1);
+          if (nn >= 2) mbar_wait(&o_free[w], ((nn - 2) >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t pd = pdesc0 + static_cast<uint32_t>(w * (A6_P_BYTES >> 4));
+            const uint64_t vd = vdesc0 + static_cast<uint32_t>(j * (A6_KV_HEAD_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < A6_KEYS / 16; ++k)
+              umma_bf16_ss_2sm(tslot + a6_o_col(w), pd + k * ((2 * A6_BM * 16) >> 4), vd + k * ((2 * 24 * 16) >> 4), idesc_o, k != 0);
+            umma_commit_2sm(&o_full[w]);
+            // the next unit belongs to another sample: its K/V tiles may replace these once this PV has read them
+            if (j == A6_HPC - 1 && i + 1 < nunits && i + 1 == kv_end) umma_commit_2sm(kv_free);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 12) {
+    // ===================== softmax groups (warps 4..7 and 8..11) of BOTH CTAs: one thread per query row =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t sbuf = tlane + (wg ? A6_TM_SBUF1 : A6_TM_SBUF0);
+    uint8_t* ptile = smem + A6_OFF_P + wg * A6_P_BYTES + row * 16;
+    float* osc = reinterpret_cast<float*>(smem + A6_OFF_OSC) + wg * 2 * A6_BM + row;
+    const int Lt = p.Lt;
+    const int Li = p.Li;
+    const float cs = p.scale_log2e;
+    A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 2 + wg);
+    if (q != 0) tr.base = nullptr;
+    int kv_end = 0;                                  // only to track the sample index of a unit without dividing per head
+    int b = u0 / p.MTP - 1;
+
+#pragma unroll 1
+    for (int i = 0; i < nunits; ++i) {
+      if (i >= kv_end) {
+        ++b;
+        kv_end = (kv_end == 0) ? first_end : kv_end + p.MTP;
+      }
+      const int mt = 2 * (u0 + i - b * p.MTP) + static_cast<int>(rank);
+      const int m0 = mt * A6_BM;
+      const bool row_ok = (m0 + row) < p.S;
+#pragma unroll 1
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = wg + 2 * jj;                   // this group's heads of the unit
+        const int nn = i * A6_HPC + j;
+        const uint32_t par = (nn >> 1) & 1;
+        mbar_wait(&s_full[wg], par);
+        tc_fence_after();
+        a3_trace(tr, 33 + 10 * wg, nn);
+        uint32_t sr[A6_KEYS];                        // S row (fp32 bits), later the exponentials
+        tmem_ld32_raw(sbuf, sr);
+        tmem_ld32_raw(sbuf + 32, sr + 32);
+        tmem_ld32_raw(sbuf + 64, sr + 64);
+        tmem_ld_wait();
+        tc_fence_before();
+        arrive_leader(&s_free[wg]);                  // QK^T(nn + 2) may overwrite the S buffer from here on
+        float fi = 1.f, oscale = 1.f;
+        bool text_on = true;
+        {
+          auto tvalid = [&](int c) -> bool { if constexpr (LT77) return c < 77; else return c < Lt; };
+          float mt2[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < A6_IMG_OFF; ++c) {
+            if (LT77 && c >= 77) continue;
+            const float v = __uint_as_float(sr[c]);
+            mt2[c & 3] = fmaxf(mt2[c & 3], LT77 ? v : (tvalid(c) ? v : -INFINITY));
+          }
+          float mi2[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < A6_KEYS - A6_IMG_OFF; ++c)
+            mi2[c & 1] = fmaxf(mi2[c & 1], (c < Li) ? __uint_as_float(sr[A6_IMG_OFF + c]) : -INFINITY);
+          const float mts = fmaxf(fmaxf(mt2[0], mt2[1]), fmaxf(mt2[2], mt2[3])) * cs, mis = fmaxf(mi2[0], mi2[1]) * cs;
+          const uint64_t cs2 = f2_pack(cs, cs);
+          const uint64_t nmt2 = f2_pack(-mts, -mts), nmi2 = f2_pack(-mis, -mis);
+          uint64_t lacc[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
+          uint64_t iacc = f2_pack(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < A6_IMG_OFF / 2; ++k) {
+            const int c = 2 * k;
+            if (LT77 && c >= 77) { sr[c] = 0u; sr[c + 1] = 0u; continue; }
+            float a, b2;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmt2), a, b2);
+            if (p.dbg == 1) { a = a * a; b2 = b2 * b2; } else {
+            a = fast_exp2(a);
+            b2 = fast_exp2(b2);
+            }
+            if constexpr (LT77) {
+              if (c + 1 >= 77) b2 = 0.f;
+            } else {
+              a = tvalid(c) ? a : 0.f;
+              b2 = tvalid(c + 1) ? b2 : 0.f;
+            }
+            lacc[k & 1] = f2_add(lacc[k & 1], f2_pack(a, b2));
+            sr[c] = __float_as_uint(a);
+            sr[c + 1] = __float_as_uint(b2);
+          }
+          if (Li > 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int c = A6_IMG_OFF + 2 * k;
+              float a, b2;
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmi2), a, b2);
+              a = (2 * k < Li) ? fast_exp2(a) : 0.f;
+              b2 = (2 * k + 1 < Li) ? fast_exp2(b2) : 0.f;
+              iacc = f2_add(iacc, f2_pack(a, b2));
+              sr[c] = __float_as_uint(a);
+              sr[c + 1] = __float_as_uint(b2);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = A6_IMG_OFF + 2 * k;
+              float a, b2;
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmi2), a, b2);
+              a = (2 * k < Li) ? fast_exp2(a) : 0.f;
+              b2 = (2 * k + 1 < Li) ? fast_exp2(b2) : 0.f;
+              iacc = f2_add(iacc, f2_pack(a, b2));
+              sr[c] = __float_as_uint(a);
+              sr[c + 1] = __float_as_uint(b2);
+            }
+#pragma unroll
+            for (int c = A6_IMG_OFF + 8; c < A6_KEYS; ++c) sr[c] = 0u;
+          }
+          float l0, l1, l2, l3, li0, li1;
+          f2_unpack(lacc[0], l0, l1);
+          f2_unpack(lacc[1], l2, l3);
+          f2_unpack(iacc, li0, li1);
+          const float lt = (l0 + l1) + (l2 + l3);
+          const float li = li0 + li1;
+          const float at = p.w_text / lt;
+          const float ai = p.w_img / li;
+          if (p.stats != nullptr && row_ok) {
+            const size_t idx = ((static_cast<size_t>(b) * p.H + (g * A6_HPC + j)) * p.S + (m0 + row));
+            reinterpret_cast<float4*>(p.stats)[idx] = make_float4(mts, lt, mis, li);
+          }
+          // P = [e_text | e_img * fi], O row scaled by `oscale` when it is drained: the text segment stays unscaled.
+          // w_text == 0 (image-only fusion branch) flips the roles.
+          if (p.w_text != 0.f) { fi = ai / at; oscale = at; }
+          else                 { text_on = false; fi = 1.f; oscale = ai; }
+        }
+        a3_trace(tr, 36 + 10 * wg, nn);
+        // the P tile and the row-scale slot of this parity are re-used: PV(nn - 2) has read the tile once o_full(nn - 2)
+        // completed, and the epilogue has read the scales of head nn - 4 long before (it drained O(nn - 2) since).
+        if (nn >= 2) mbar_wait(&o_full[wg], par ^ 1);
+        osc[par * A6_BM] = oscale;
+        {
+          const uint64_t fi2 = f2_pack(fi, fi);
+#pragma unroll
+          for (int c = 0; c < A6_KEYS / 8; ++c) {    // key chunk c: 8 keys = 16 bytes of this row
+            uint32_t pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = 8 * c + 2 * k;
+              if (e < A6_IMG_OFF) {
+                pk[k] = text_on ? pack_bf16x2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])) : 0u;
+              } else {
+                float a, b2;
+                f2_unpack(f2_mul(f2_pack(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), fi2), a, b2);
+                pk[k] = pack_bf16x2(a, b2);
+              }
+            }
+            st_shared_v4(ptile + c * (A6_BM * 16), pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        fence_proxy_async_smem();                    // generic-proxy stores -> visible to the tensor core's operand reads
+        arrive_leader(&p_ready[wg]);
+        a3_trace(tr, 34 + 10 * wg, nn);
+      }
+    }
+    a3_trace_done_raw(p.trace, tr, 2 + wg);
+  } else {
+    // ===================== epilogue warps 12..15 of BOTH CTAs: Q conversion + O drain for lane quarter q =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int q = warp & 3;
+    const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* ost = smem + A6_OFF_OST + q * (2 * A6_OST_BYTES);
+    const float* osc = reinterpret_cast<const float*>(smem + A6_OFF_OSC) + q * 32 + lane;
+    int converted = 0, drained = 0;
+    int kv_end_d = 0;                                // sample tracking for the drain stream
+    int b_d = u0 / p.MTP - 1;
+    int m0_d = 0;
+
+    // Q of unit iu: fp32 [40 j, 40 j + 40) -> packed bf16 [40 j + 16, 40 j + 40), dims 40..47 zero (K = 48 contraction)
+    auto convert_unit = [&](int iu) {
+      const uint32_t tslot = tlane + (iu & 1) * A6_BN;
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < A6_HPC; ++j) {
+        uint32_t a[32], c8[8], o[24];
+        tmem_ld_x32(tslot + 40 * j, a);
+        tmem_ld_x8(tslot + 40 * j + 32, c8);
+        tmem_ld_wait();
+        pack_pairs3<32>(a, o);
+        pack_pairs3<8>(c8, o + 16);
+        o[20] = o[21] = o[22] = o[23] = 0u;
+        tmem_st_x16(tslot + 40 * j + 16, o);
+        tmem_st_x8(tslot + 40 * j + 32, o + 16);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      arrive_leader(&q_ready[iu & 1]);
+    };
+    // O(nn): TMEM -> registers (accumulator released at once) -> * row scale -> bf16 -> staging slab -> TMA store
+    auto drain_head = [&](int nn) {
+      const int i = nn >> 2, j = nn & 3;
+      const uint32_t w = j & 1;
+      const uint32_t par = (nn >> 1) & 1;
+      if (j == 0) {                                  // first head of a unit: where its rows live
+        if (i >= kv_end_d) {
+          ++b_d;
+          kv_end_d = (kv_end_d == 0) ? first_end : kv_end_d + p.MTP;
+        }
+        m0_d = (2 * (u0 + i - b_d * p.MTP) + static_cast<int>(rank)) * A6_BM;
+      }
+      tc_fence_after();
+      uint32_t a[32], c8[8];
+      const uint32_t taddr = tlane + (i & 1) * A6_BN + a6_o_col(w);
+      tmem_ld_x32(taddr, a);
+      tmem_ld_x8(taddr + 32, c8);
+      tmem_ld_wait();
+      const float oscale = osc[(w * 2 + par) * A6_BM];   // read before the release below: the slot is rewritten two heads on
+      tc_fence_before();
+      arrive_leader(&o_free[w]);                     // PV(nn + 2) may overwrite the accumulator
+      if (j == A6_HPC - 1) arrive_leader(&slot_free[i & 1]);   // ... and the projection of unit i + 2 the whole slot
+      uint8_t* slab = ost + w * A6_OST_BYTES;
+      if (elect_one()) bulk_wait_read<1>();          // the store that last read this slab (two drains ago) has finished
+      __syncwarp();
+      const uint64_t sc2 = f2_pack(oscale, oscale);
+      auto stage = [&](const uint32_t* v, int col0, int ncols) {
+#pragma unroll
+        for (int c = 0; c < ncols / 8; ++c) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float x0, x1;
+            f2_unpack(f2_mul(f2_pack(__uint_as_float(v[c * 8 + 2 * k]), __uint_as_float(v[c * 8 + 2 * k + 1])), sc2), x0, x1);
+            w4[k] = pack_bf16x2(x0, x1);
+          }
+          st_shared_v4(slab + lane * (A6_D * 2) + (col0 + c * 8) * 2, w4[0], w4[1], w4[2], w4[3]);
+        }
+      };
+      stage(a, 0, 32);
+      stage(c8, 32, 8);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        tma_store_3d(&tmO, slab, g * A6_BN + j * A6_D, m0_d + q * 32, b_d);
+        bulk_commit();
+      }
+      __syncwarp();
+    };
+
+    while (drained < nheads) {
+      const int du = drained >> 2;                   // unit of the next head to drain
+      if (converted <= du) {                         // its Q is not even converted yet: nothing else can make progress
+        mbar_wait(&q_full[converted & 1], (converted >> 1) & 1);
+        convert_unit(converted);
+        ++converted;
+        continue;
+      }
+      if (converted < nunits && mbar_test_wait(&q_full[converted & 1], (converted >> 1) & 1)) {
+        convert_unit(converted);                     // the next unit's projection has finished: convert ahead
+        ++converted;
+        continue;
+      }
+      const uint32_t w = drained & 1;
+      if (mbar_try_wait_hint(&o_full[w], (drained >> 1) & 1, 400u)) {
+        drain_head(drained);
+        ++drained;
+      }
+    }
+    if (elect_one()) bulk_wait_read<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // neither CTA frees TMEM / exits while pair-wide MMAs or remote signals are in flight
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc_2sm<512>(tmem);
+}
+
+extern unsigned long long* g_attn3_trace;
+extern int g_attn3_trace_cap;
+extern int g_opt_attn3_dbg;
+
+template <bool LT77>
+static int launch_attn6(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const Attn6Params& p,
+                        long long unit_pairs, cudaStream_t stream) {
+  auto kern = dual_attn_fwd_pair_roles_kernel<LT77>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM_BYTES));
+    attr_done = true;
+  }
+  const long long max_pairs = sm_count() / 2;
+  const int npairs = static_cast<int>(unit_pairs < max_pairs ? unit_pairs : max_pairs);
+  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(A6_THREADS), A6_SMEM_BYTES, stream, tmX, tmWq, tmO, p));
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
+// Same contract as dual_attn_core_bf16_pair (pv_attn4.cu), for C = 320 with head_dim 40 and at least two row tiles per sample.
+int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
+                                   int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                                   cudaStream_t stream) {
+  PV_REQUIRE(B > 0 && S > A6_BM && H > 0 && C == A6_KB * A6_BK && C / H == A6_D, "needs C=320, head_dim 40, S>128 (B=%d S=%d C=%d H=%d)",
+             B, S, C, H);
+  PV_REQUIRE(Lt >= 1 && Lt <= A6_IMG_OFF && Li >= 1 && Li <= A6_KEYS - A6_IMG_OFF,
+             "need 1 <= Lt <= %d and 1 <= Li <= %d (Lt=%d Li=%d)", A6_IMG_OFF, A6_KEYS - A6_IMG_OFF, Lt, Li);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wq) | reinterpret_cast<uintptr_t>(Kp) |
+              reinterpret_cast<uintptr_t>(Vp) | reinterpret_cast<uintptr_t>(O)) % 16 == 0, "pointers must be 16-byte aligned");
+  CUtensorMap tmX, tmWq, tmO;
+  if (make_tmap_3d(&tmX, X, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, A6_BK, A6_BM, 1, Swz::B128)) return PV_ERR_CUDA;
+  if (make_tmap_3d(&tmWq, Wq, 2, C, C, 1, C * 2ull, static_cast<uint64_t>(C) * C * 2, A6_BK, A6_BN / 2, 1, Swz::B128)) return PV_ERR_CUDA;
+  if (make_tmap_3d(&tmO, O, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, A6_D, 32, 1, Swz::None)) return PV_ERR_CUDA;
+  Attn6Params p;
+  p.Kp = static_cast<const uint8_t*>(Kp);
+  p.Vp = static_cast<const uint8_t*>(Vp);
+  p.stats = stats;
+  p.S = S; p.C = C; p.H = H; p.Lt = Lt; p.Li = Li;
+  p.G = C / A6_BN;
+  const int MT = (S + A6_BM - 1) / A6_BM;
+  p.MTP = (MT + 1) / 2;
+  p.V = B * p.MTP;
+  const long long unit_pairs = static_cast<long long>(p.V) * p.G;
+  PV_REQUIRE(unit_pairs < (1ll << 28), "too many work units");
+  p.w_text = w_text; p.w_img = w_img;
+  p.trace = g_attn3_trace;
+  p.trace_cap = g_attn3_trace_cap;
+  p.dbg = g_opt_attn3_dbg;
+  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(A6_D));
+  return Lt == 77 ? launch_attn6<true>(tmX, tmWq, tmO, p, unit_pairs, stream)
+                  : launch_attn6<false>(tmX, tmWq, tmO, p, unit_pairs, stream);
+}
+
+}  // namespace pv

@@ -87,12 +87,28 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or `ns` elapse) instead of
+// spinning -- a spinning waiter costs issue slots that the working warps of the same scheduler need.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+#ifndef PV_MBAR_HINT_NS
+#define PV_MBAR_HINT_NS 20000u
+#endif
 // Bounded wait: a protocol bug must trap (and surface as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) {       // ~1 s of SM clocks: no wait on this path is longer than microseconds
+  uint32_t tries = 0;
+  while (!mbar_try_wait_hint(bar, parity, PV_MBAR_HINT_NS)) {
+    if (++tries > 4000000u) {                  // >= 0.1 s even if every probe returned at once: no wait here exceeds microseconds
 #ifdef PV_MBAR_DEBUG   // the printf costs registers and a stack frame in every waiting role: debug builds only
       printf("photoverse_b200: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n",
              blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);

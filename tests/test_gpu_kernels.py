@@ -12,6 +12,8 @@ from tests.helpers import build_product_layer, force_fusion_seed, golden
 
 pytestmark = pytest.mark.gpu
 
+DEFAULT_ATTN_VARIANT = 6          # g_opt_attn_variant in csrc/pv_api.cu
+
 TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
 
 
@@ -229,7 +231,8 @@ def test_kv_cache_reuses_projection(cuda_device):
     assert n1 - n0 == 2, f"cached call should launch attention + out-proj only, launched {n1 - n0}"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4], ids=["smem-operands", "tmem-operands", "persistent", "cta-pair"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6],
+                         ids=["smem-operands", "tmem-operands", "persistent", "cta-pair", "cta-pair16", "cta-pair-roles"])
 @pytest.mark.parametrize("S,C,Li,wt,wi", [(384, 320, 5, 1.0, 1.0), (200, 640, 16, 1.0, 1.0), (128, 1280, 1, 1.0, 1.0),
                                           (256, 320, 3, 2.0, 0.0), (256, 640, 5, 0.0, 2.0), (4096, 320, 5, 1.0, 1.0),
                                           (1024, 640, 4, 1.0, 1.0), (300, 1280, 5, 1.0, 1.0)])
@@ -253,7 +256,28 @@ def test_attention_kernel_variants(cuda_device, variant, S, C, Li, wt, wi):
         err = (y.float() - y_ref).abs().max().item()
         assert err <= 2e-2, f"variant {variant}: max-abs {err}"
     finally:
-        _lib.set_option("attn_variant", 4)
+        _lib.set_option("attn_variant", DEFAULT_ATTN_VARIANT)
+
+
+@pytest.mark.parametrize("variant", [2, 3, 4, 5, 6], ids=["tmem-operands", "persistent", "cta-pair", "cta-pair16", "cta-pair-roles"])
+@pytest.mark.parametrize("Lt,S,C,Li", [(20, 256, 320, 5), (48, 256, 640, 1), (50, 384, 320, 16), (80, 256, 1280, 3), (1, 256, 320, 1)])
+def test_attention_kernel_other_text_lengths(cuda_device, variant, Lt, S, C, Li):
+    """Text contexts other than CLIP's 77 tokens (the run-time key mask of the kernels; 1 <= Lt <= 80)."""
+    from photoverse_b200 import _lib
+    case = cases.ProcCase(f"lt_{Lt}_{C}", B=2, S=S, C=C, Li=Li, Lt=Lt, seed=80 + Lt)
+    _lib.set_option("attn_variant", variant)
+    try:
+        attn, proc = build_product_layer(case, cuda_device)
+        x, text, img = cases.proc_inputs(case, torch.float32)
+        with torch.no_grad():
+            y = attn(x.to(cuda_device, torch.bfloat16), encoder_hidden_states=(text.to(cuda_device, torch.bfloat16),
+                                                                              img.to(cuda_device, torch.bfloat16)))
+            w = cases.proc_weights(case).to(device=cuda_device)
+            y_ref, _ = dual_branch_attention(x.to(cuda_device), text.to(cuda_device), img.to(cuda_device), w, 1.0, 1.0)
+        err = (y.float() - y_ref).abs().max().item()
+        assert err <= 2e-2, f"variant {variant} Lt={Lt}: max-abs {err}"
+    finally:
+        _lib.set_option("attn_variant", DEFAULT_ATTN_VARIANT)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])

@@ -12,7 +12,7 @@ dev = torch.device("cuda:0")
 dt = torch.bfloat16
 g = torch.Generator().manual_seed(0)
 ROWS, LI = 16, int(os.environ.get("PV_LI", "1"))
-_lib.set_option("attn_variant", 3)
+_lib.set_option("attn_variant", int(os.environ.get("PV_ATTN_VARIANT", "3")))
 _lib.set_option("attn3_wstat", int(os.environ.get("PV_WSTAT", "1")))
 _lib.set_option("attn3_prefetch", int(os.environ.get("PV_PF", "0")))
 lib = _lib.lib()

@@ -1,0 +1,6 @@
+#!/bin/bash
+cd /root/repo
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "cta-pair or golden" 2>&1 | tail -5
+timeout 300 python tools/attn_bench.py 4 5 2>&1 | tail -8
+PV_ATTN_VARIANT=4 PV_TRACE_OUT=gpurun_out/trace_v4p_A.json PV_NEV=5 timeout 120 python tools/attn_trace.py | tail -2

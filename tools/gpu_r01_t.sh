@@ -1,0 +1,4 @@
+#!/bin/bash
+cd /root/repo
+mkdir -p gpurun_out
+PV_ATTN_VARIANT=4 PV_TRACE_OUT=gpurun_out/trace_v4f_A.json PV_NEV=5 timeout 120 python tools/attn_trace.py | tail -2
