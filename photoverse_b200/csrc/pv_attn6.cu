@@ -67,7 +67,6 @@ struct Attn6Params {
   float w_text, w_img, scale_log2e;
   unsigned long long* trace;
   int trace_cap;
-  int dbg;                 // timing experiments only (pv_set_option attn3_dbg): 1 = exponentials on the FMA pipe (wrong results)
 };
 
 template <bool LT77>
@@ -327,8 +326,12 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sbuf = tlane + (wg ? A6_TM_SBUF1 : A6_TM_SBUF0);
-    uint8_t* ptile = smem + A6_OFF_P + wg * A6_P_BYTES + row * 16;
-    float* osc = reinterpret_cast<float*>(smem + A6_OFF_OSC) + wg * 2 * A6_BM + row;
+    // 32-bit shared addresses kept in registers: barrier / tile addresses are used several times per head
+    const uint32_t ptile_a = smem_u32(smem + A6_OFF_P + wg * A6_P_BYTES + row * 16);
+    const uint32_t osc_a = smem_u32(smem + A6_OFF_OSC) + (wg * 2 * A6_BM + row) * 4;
+    const uint32_t s_full_a = smem_u32(&s_full[wg]), o_full_a = smem_u32(&o_full[wg]);
+    const uint32_t s_free_l = mapa_u32(smem_u32(&s_free[wg]), 0), p_ready_l = mapa_u32(smem_u32(&p_ready[wg]), 0);
+    const bool text_on = (p.w_text != 0.f);        // image-only fusion branch: the text part of P is zero
     const int Lt = p.Lt;
     const int Li = p.Li;
     const float cs = p.scale_log2e;
@@ -351,7 +354,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         const int j = wg + 2 * jj;                   // this group's heads of the unit
         const int nn = i * A6_HPC + j;
         const uint32_t par = (nn >> 1) & 1;
-        mbar_wait(&s_full[wg], par);
+        mbar_wait_a(s_full_a, par);
         tc_fence_after();
         a3_trace(tr, 33 + 10 * wg, nn);
         uint32_t sr[A6_KEYS];                        // S row (fp32 bits), later the exponentials
@@ -360,9 +363,9 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         tmem_ld32_raw(sbuf + 64, sr + 64);
         tmem_ld_wait();
         tc_fence_before();
-        arrive_leader(&s_free[wg]);                  // QK^T(nn + 2) may overwrite the S buffer from here on
+        __syncwarp();
+        if (elect_one()) mbar_arrive_cluster(s_free_l);   // QK^T(nn + 2) may overwrite the S buffer from here on
         float fi = 1.f, oscale = 1.f;
-        bool text_on = true;
         {
           auto tvalid = [&](int c) -> bool { if constexpr (LT77) return c < 77; else return c < Lt; };
           float mt2[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -373,9 +376,14 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
             mt2[c & 3] = fmaxf(mt2[c & 3], LT77 ? v : (tvalid(c) ? v : -INFINITY));
           }
           float mi2[2] = {-INFINITY, -INFINITY};
+          if (Li <= 2) {
+            mi2[0] = __uint_as_float(sr[A6_IMG_OFF]);
+            if (Li > 1) mi2[1] = __uint_as_float(sr[A6_IMG_OFF + 1]);
+          } else {
 #pragma unroll
-          for (int c = 0; c < A6_KEYS - A6_IMG_OFF; ++c)
-            mi2[c & 1] = fmaxf(mi2[c & 1], (c < Li) ? __uint_as_float(sr[A6_IMG_OFF + c]) : -INFINITY);
+            for (int c = 0; c < A6_KEYS - A6_IMG_OFF; ++c)
+              mi2[c & 1] = fmaxf(mi2[c & 1], (c < Li) ? __uint_as_float(sr[A6_IMG_OFF + c]) : -INFINITY);
+          }
           const float mts = fmaxf(fmaxf(mt2[0], mt2[1]), fmaxf(mt2[2], mt2[3])) * cs, mis = fmaxf(mi2[0], mi2[1]) * cs;
           const uint64_t cs2 = f2_pack(cs, cs);
           const uint64_t nmt2 = f2_pack(-mts, -mts), nmi2 = f2_pack(-mis, -mis);
@@ -387,10 +395,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
             if (LT77 && c >= 77) { sr[c] = 0u; sr[c + 1] = 0u; continue; }
             float a, b2;
             f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmt2), a, b2);
-            if (p.dbg == 1) { a = a * a; b2 = b2 * b2; } else {
             a = fast_exp2(a);
             b2 = fast_exp2(b2);
-            }
             if constexpr (LT77) {
               if (c + 1 >= 77) b2 = 0.f;
             } else {
@@ -413,6 +419,17 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
               sr[c] = __float_as_uint(a);
               sr[c + 1] = __float_as_uint(b2);
             }
+          } else if (Li <= 2) {                      // one image token (`token_index` given, the generate.py default) or two
+            const int c = A6_IMG_OFF;
+            float a, b2;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmi2), a, b2);
+            a = fast_exp2(a);
+            b2 = (Li > 1) ? fast_exp2(b2) : 0.f;
+            iacc = f2_pack(a, b2);
+            sr[c] = __float_as_uint(a);
+            sr[c + 1] = __float_as_uint(b2);
+#pragma unroll
+            for (int cc = A6_IMG_OFF + 2; cc < A6_KEYS; ++cc) sr[cc] = 0u;
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -434,43 +451,52 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
           f2_unpack(iacc, li0, li1);
           const float lt = (l0 + l1) + (l2 + l3);
           const float li = li0 + li1;
-          const float at = p.w_text / lt;
-          const float ai = p.w_img / li;
+          const float at = __fdividef(p.w_text, lt);      // l >= 1 (the max term), far from the ranges where the fast
+          const float ai = __fdividef(p.w_img, li);       // division loses accuracy
           if (p.stats != nullptr && row_ok) {
             const size_t idx = ((static_cast<size_t>(b) * p.H + (g * A6_HPC + j)) * p.S + (m0 + row));
             reinterpret_cast<float4*>(p.stats)[idx] = make_float4(mts, lt, mis, li);
           }
           // P = [e_text | e_img * fi], O row scaled by `oscale` when it is drained: the text segment stays unscaled.
           // w_text == 0 (image-only fusion branch) flips the roles.
-          if (p.w_text != 0.f) { fi = ai / at; oscale = at; }
-          else                 { text_on = false; fi = 1.f; oscale = ai; }
+          if (text_on) { fi = __fdividef(ai, at); oscale = at; }
+          else         { fi = 1.f; oscale = ai; }
         }
         a3_trace(tr, 36 + 10 * wg, nn);
         // the P tile and the row-scale slot of this parity are re-used: PV(nn - 2) has read the tile once o_full(nn - 2)
         // completed, and the epilogue has read the scales of head nn - 4 long before (it drained O(nn - 2) since).
-        if (nn >= 2) mbar_wait(&o_full[wg], par ^ 1);
-        osc[par * A6_BM] = oscale;
+        if (nn >= 2) mbar_wait_a(o_full_a, par ^ 1);
+        st_shared_f32_a(osc_a + par * (A6_BM * 4), oscale);
+        if (text_on) {
+#pragma unroll
+          for (int c = 0; c < A6_IMG_OFF / 8; ++c) {   // key chunk c: 8 keys = 16 bytes of this row
+            uint32_t pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              pk[k] = pack_bf16x2(__uint_as_float(sr[8 * c + 2 * k]), __uint_as_float(sr[8 * c + 2 * k + 1]));
+            st_shared_v4_a(ptile_a + c * (A6_BM * 16), pk[0], pk[1], pk[2], pk[3]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < A6_IMG_OFF / 8; ++c) st_shared_v4_a(ptile_a + c * (A6_BM * 16), 0u, 0u, 0u, 0u);
+        }
         {
           const uint64_t fi2 = f2_pack(fi, fi);
 #pragma unroll
-          for (int c = 0; c < A6_KEYS / 8; ++c) {    // key chunk c: 8 keys = 16 bytes of this row
+          for (int c = A6_IMG_OFF / 8; c < A6_KEYS / 8; ++c) {
             uint32_t pk[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int e = 8 * c + 2 * k;
-              if (e < A6_IMG_OFF) {
-                pk[k] = text_on ? pack_bf16x2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])) : 0u;
-              } else {
-                float a, b2;
-                f2_unpack(f2_mul(f2_pack(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), fi2), a, b2);
-                pk[k] = pack_bf16x2(a, b2);
-              }
+              float a, b2;
+              f2_unpack(f2_mul(f2_pack(__uint_as_float(sr[8 * c + 2 * k]), __uint_as_float(sr[8 * c + 2 * k + 1])), fi2), a, b2);
+              pk[k] = pack_bf16x2(a, b2);
             }
-            st_shared_v4(ptile + c * (A6_BM * 16), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4_a(ptile_a + c * (A6_BM * 16), pk[0], pk[1], pk[2], pk[3]);
           }
         }
         fence_proxy_async_smem();                    // generic-proxy stores -> visible to the tensor core's operand reads
-        arrive_leader(&p_ready[wg]);
+        __syncwarp();
+        if (elect_one()) mbar_arrive_cluster(p_ready_l);
         a3_trace(tr, 34 + 10 * wg, nn);
       }
     }
@@ -481,7 +507,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     const int q = warp & 3;
     const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* ost = smem + A6_OFF_OST + q * (2 * A6_OST_BYTES);
-    const float* osc = reinterpret_cast<const float*>(smem + A6_OFF_OSC) + q * 32 + lane;
+    const uint32_t osc_a = smem_u32(smem + A6_OFF_OSC) + (q * 32 + lane) * 4;
     int converted = 0, drained = 0;
     int kv_end_d = 0;                                // sample tracking for the drain stream
     int b_d = u0 / p.MTP - 1;
@@ -525,7 +551,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       tmem_ld_x32(taddr, a);
       tmem_ld_x8(taddr + 32, c8);
       tmem_ld_wait();
-      const float oscale = osc[(w * 2 + par) * A6_BM];   // read before the release below: the slot is rewritten two heads on
+      const float oscale = ld_shared_f32_a(osc_a + (w * 2 + par) * (A6_BM * 4));   // read before the release below: the slot is rewritten two heads on
       tc_fence_before();
       arrive_leader(&o_free[w]);                     // PV(nn + 2) may overwrite the accumulator
       if (j == A6_HPC - 1) arrive_leader(&slot_free[i & 1]);   // ... and the projection of unit i + 2 the whole slot
@@ -589,7 +615,6 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
 
 extern unsigned long long* g_attn3_trace;
 extern int g_attn3_trace_cap;
-extern int g_opt_attn3_dbg;
 
 template <bool LT77>
 static int launch_attn6(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const Attn6Params& p,
@@ -635,7 +660,6 @@ int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp
   p.w_text = w_text; p.w_img = w_img;
   p.trace = g_attn3_trace;
   p.trace_cap = g_attn3_trace_cap;
-  p.dbg = g_opt_attn3_dbg;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(A6_D));
   return Lt == 77 ? launch_attn6<true>(tmX, tmWq, tmO, p, unit_pairs, stream)
                   : launch_attn6<false>(tmX, tmWq, tmO, p, unit_pairs, stream);
