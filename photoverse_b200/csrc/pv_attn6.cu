@@ -389,6 +389,11 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
           const uint64_t nmt2 = f2_pack(-mts, -mts), nmi2 = f2_pack(-mis, -mis);
           uint64_t lacc[2] = {f2_pack(0.f, 0.f), f2_pack(0.f, 0.f)};
           uint64_t iacc = f2_pack(0.f, 0.f);
+          // The exponentials are MUFU-bound (8 cycles per warp instruction) and the two groups' warps of a lane quarter
+          // share one scheduler: a token (two producer/consumer named barriers) makes them take turns, so that one
+          // warp's exponentials overlap the other's TMEM loads, max pass, packing and stores instead of its exponentials.
+          if (wg == 0) { if (nn >= 2) named_bar_sync(5 + q, 64); }
+          else         { named_bar_sync(1 + q, 64); }
 #pragma unroll
           for (int k = 0; k < A6_IMG_OFF / 2; ++k) {
             const int c = 2 * k;
@@ -445,6 +450,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
 #pragma unroll
             for (int c = A6_IMG_OFF + 8; c < A6_KEYS; ++c) sr[c] = 0u;
           }
+          if (wg == 0) { named_bar_arrive(1 + q, 64); }
+          else         { if (nn + 2 < nheads) named_bar_arrive(5 + q, 64); }
           float l0, l1, l2, l3, li0, li1;
           f2_unpack(lacc[0], l0, l1);
           f2_unpack(lacc[1], l2, l3);
@@ -597,7 +604,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         continue;
       }
       const uint32_t w = drained & 1;
-      if (mbar_try_wait_hint(&o_full[w], (drained >> 1) & 1, 400u)) {
+      if (mbar_try_wait_hint(&o_full[w], (drained >> 1) & 1, 64u)) {
         drain_head(drained);
         ++drained;
       }

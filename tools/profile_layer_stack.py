@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 ROWS = int(os.environ.get("PV_ROWS", "16"))
 LI = int(os.environ.get("PV_LI", "1"))
 REPS = int(os.environ.get("PV_REPS", "3"))
-_lib.set_option("attn_variant", int(os.environ.get("PV_ATTN_VARIANT", "4")))
+_lib.set_option("attn_variant", int(os.environ.get("PV_ATTN_VARIANT", "6")))
 _lib.set_option("gemm_two_cta", int(os.environ.get("PV_GEMM_TWO_CTA", "1")))
 SHAPES = [(4096, 320), (1024, 640), (256, 1280), (64, 1280)]
 g = torch.Generator().manual_seed(0)
