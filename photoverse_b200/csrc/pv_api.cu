@@ -24,6 +24,7 @@ int dual_attn_core_bf16_ts(const void* X, const void* Wq, const void* Kp, const 
 int dual_attn_core_bf16_persistent(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
                                    int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                                    cudaStream_t stream);
+bool dual_attn_pair_roles_supported(int S, int C, int H);
 int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
                                    int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                                    cudaStream_t stream);
@@ -179,8 +180,8 @@ static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>
 static int attn_core_bf16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
                           int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t st) {
   if (g_opt_attn_variant == 1) return dual_attn_core_bf16(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
-  if (g_opt_attn_variant == 6 && S > 128) {    // CTA pairs with decoupled roles for C = 320 / head_dim 40, else variant 4
-    if (C == 320 && H > 0 && C / H == 40)
+  if (g_opt_attn_variant == 6 && S > 128) {    // CTA pairs with decoupled roles (head_dim 40 at C = 320, head_dim 80), else variant 4
+    if (dual_attn_pair_roles_supported(S, C, H))
       return dual_attn_core_bf16_pair_roles(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
     return dual_attn_core_bf16_pair(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
   }

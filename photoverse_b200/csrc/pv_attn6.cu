@@ -27,35 +27,44 @@ namespace pv {
 constexpr int A6_BM = 128;
 constexpr int A6_BN = 160;
 constexpr int A6_BK = 64;
-constexpr int A6_D = 40;
-constexpr int A6_DPAD = 48;
-constexpr int A6_HPC = 4;                 // heads per 160-column head group
-constexpr int A6_KB = 5;                  // K-blocks of the projection (C = 320)
 constexpr int A6_KEYS = PV_KEYS_PAD;
 constexpr int A6_IMG_OFF = PV_IMG_KEY_OFFSET;
 constexpr int A6_THREADS = 512;           // 0 TMA, 1 projection MMA, 2 QK^T MMA, 3 PV MMA + K/V relay, 4..11 softmax, 12..15 epilogue
 constexpr int A6_STAGES = 4;
 constexpr int A6_A_BYTES = A6_BM * A6_BK * 2;                 // one X stage (this CTA's 128 rows)
 constexpr int A6_WH_BYTES = (A6_BN / 2) * A6_BK * 2;          // this CTA's half of a Wq K-block
-constexpr int A6_KH_BYTES = (A6_KEYS / 2) * A6_DPAD * 2;      // 48 keys of a K tile
-constexpr int A6_VH_BYTES = (A6_DPAD / 2) * A6_KEYS * 2;      // 24 dims of a V^T tile
-constexpr int A6_KV_HEAD_BYTES = A6_KH_BYTES + A6_VH_BYTES;
-constexpr int A6_KV_BYTES = A6_HPC * A6_KV_HEAD_BYTES;
 constexpr int A6_P_BYTES = A6_BM * A6_KEYS * 2;               // one group's P tile
-constexpr int A6_OST_BYTES = 32 * A6_D * 2;                   // one staging slab: 32 rows x 40 channels
-constexpr int A6_OFF_W = A6_STAGES * A6_A_BYTES;
-constexpr int A6_OFF_KV = A6_OFF_W + A6_KB * A6_WH_BYTES;
-constexpr int A6_OFF_OST = A6_OFF_KV + A6_KV_BYTES;           // [epilogue warp][group] slabs
-constexpr int A6_OFF_P = A6_OFF_OST + 4 * 2 * A6_OST_BYTES;
-constexpr int A6_OFF_OSC = A6_OFF_P + 2 * A6_P_BYTES;         // O row scales [group][parity][128] fp32
-constexpr int A6_OFF_BAR = A6_OFF_OSC + 2 * 2 * A6_BM * 4;
-constexpr int A6_SMEM_BYTES = A6_OFF_BAR + 512 + 1024;
-static_assert(A6_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(A6_KEYS == 96 && A6_IMG_OFF == 80, "written for 80 text + 16 image key slots");
 constexpr uint32_t A6_TM_SBUF0 = 320;
 constexpr uint32_t A6_TM_SBUF1 = 416;
-__host__ __device__ constexpr uint32_t a6_q_col(int j) { return 40 * j + 16; }   // packed bf16 Q of head j inside a slot
-__host__ __device__ constexpr uint32_t a6_o_col(int w) { return 48 * w; }        // O accumulator of softmax group w
+
+// D = 40 (C = 320): 4 heads per 160-column group, the Wq slice of the group is RESIDENT (5 K-blocks) and only X streams.
+// D = 80: 2 heads per group, X and the CTA's half of the Wq K-block stream together (26 KB per stage).
+template <int D>
+struct Attn6Cfg {
+  static_assert(D == 40 || D == 80, "head_dim 40 or 80");
+  static constexpr bool WSTAT = (D == 40);
+  static constexpr int HPC = A6_BN / D;
+  static constexpr int DPAD = (D + 15) / 16 * 16;
+  static constexpr int KB_RES = 5;                                  // resident K-blocks (WSTAT: C = 320)
+  static constexpr int STAGE_BYTES = WSTAT ? A6_A_BYTES : A6_A_BYTES + A6_WH_BYTES;
+  static constexpr int KH_BYTES = (A6_KEYS / 2) * DPAD * 2;         // 48 keys of a K tile
+  static constexpr int VH_BYTES = (DPAD / 2) * A6_KEYS * 2;         // DPAD/2 dims of a V^T tile
+  static constexpr int KV_HEAD_BYTES = KH_BYTES + VH_BYTES;
+  static constexpr int KV_BYTES = HPC * KV_HEAD_BYTES;
+  static constexpr int OST_BYTES = 32 * D * 2;                      // one staging slab: 32 rows x D channels
+  static constexpr int OFF_W = A6_STAGES * STAGE_BYTES;
+  static constexpr int OFF_KV = OFF_W + (WSTAT ? KB_RES * A6_WH_BYTES : 0);
+  static constexpr int OFF_OST = OFF_KV + KV_BYTES;                 // [epilogue warp][group] slabs
+  static constexpr int OFF_P = OFF_OST + 4 * 2 * OST_BYTES;
+  static constexpr int OFF_OSC = OFF_P + 2 * A6_P_BYTES;            // O row scales [group][parity][128] fp32
+  static constexpr int OFF_BAR = OFF_OSC + 2 * 2 * A6_BM * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  // TMEM: packed bf16 Q of head j / O accumulator of softmax group w inside a 160-column slot
+  __host__ __device__ static constexpr uint32_t q_col(int j) { return D == 40 ? 40 * j + 16 : 80 * j + 40; }
+  __host__ __device__ static constexpr uint32_t o_col(int w) { return D == 40 ? 48 * w : 80 * w; }
+};
 
 struct Attn6Params {
   const uint8_t* Kp;
@@ -69,10 +78,19 @@ struct Attn6Params {
   int trace_cap;
 };
 
-template <bool LT77>
+template <int D, bool LT77>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(A6_THREADS, 1)
 dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
                                 const __grid_constant__ CUtensorMap tmO, const Attn6Params p) {
+  using Cfg = Attn6Cfg<D>;
+  constexpr int A6_HPC = Cfg::HPC;
+  constexpr int A6_DPAD = Cfg::DPAD;
+  constexpr int A6_D = D;
+  constexpr int A6_OFF_W = Cfg::OFF_W, A6_OFF_KV = Cfg::OFF_KV, A6_OFF_OST = Cfg::OFF_OST, A6_OFF_P = Cfg::OFF_P;
+  constexpr int A6_OFF_OSC = Cfg::OFF_OSC, A6_OFF_BAR = Cfg::OFF_BAR;
+  constexpr int A6_KH_BYTES = Cfg::KH_BYTES, A6_KV_HEAD_BYTES = Cfg::KV_HEAD_BYTES, A6_KV_BYTES = Cfg::KV_BYTES;
+  constexpr int A6_OST_BYTES = Cfg::OST_BYTES;
+  const int A6_KB = p.C / A6_BK;                  // K-blocks of the projection
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* kv = smem + A6_OFF_KV;
@@ -143,14 +161,16 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
 
   // Nothing above reads what a predecessor kernel may have written; the resident Wq slice (static weights) is requested
   // before the dependency wait as well.
-  if (warp == 0) {
-    if (nunits > 0 && elect_one()) {
-      const uint32_t bar = mapa_u32(smem_u32(w_full), 0);
-      if (rank == 0) mbar_expect_tx(w_full, 2 * A6_KB * A6_WH_BYTES);
-      for (int kb = 0; kb < A6_KB; ++kb)
-        tma_load_3d_2sm(smem + A6_OFF_W + kb * A6_WH_BYTES, &tmWq, bar, kb * A6_BK, g * A6_BN + static_cast<int>(rank) * (A6_BN / 2), 0);
+  if constexpr (Cfg::WSTAT) {
+    if (warp == 0) {
+      if (nunits > 0 && elect_one()) {
+        const uint32_t bar = mapa_u32(smem_u32(w_full), 0);
+        if (rank == 0) mbar_expect_tx(w_full, 2 * Cfg::KB_RES * A6_WH_BYTES);
+        for (int kb = 0; kb < Cfg::KB_RES; ++kb)
+          tma_load_3d_2sm(smem + A6_OFF_W + kb * A6_WH_BYTES, &tmWq, bar, kb * A6_BK, g * A6_BN + static_cast<int>(rank) * (A6_BN / 2), 0);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   pdl_wait();
   pdl_launch_dependents();
@@ -179,8 +199,11 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
           mbar_wait(&empty[s], ph ^ 1);
           if (elect_one()) {
             const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
-            if (rank == 0) mbar_expect_tx(&full[s], 2 * A6_A_BYTES);
-            tma_load_3d_2sm(smem + s * A6_A_BYTES, &tmX, bar, kb * A6_BK, mt * A6_BM, b);
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+            tma_load_3d_2sm(smem + s * Cfg::STAGE_BYTES, &tmX, bar, kb * A6_BK, mt * A6_BM, b);
+            if constexpr (!Cfg::WSTAT)
+              tma_load_3d_2sm(smem + s * Cfg::STAGE_BYTES + A6_A_BYTES, &tmWq, bar, kb * A6_BK,
+                              g * A6_BN + static_cast<int>(rank) * (A6_BN / 2), 0);
           }
           __syncwarp();
         }
@@ -197,7 +220,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
                 bulk_load_1d(kd + kc * (48 * 16), p.Kp + tile + (static_cast<size_t>(kc) * A6_KEYS + 48 * rank) * 16, 48 * 16, kv_full);
               uint8_t* vd = kd + A6_KH_BYTES;
               for (int kc = 0; kc < A6_KEYS / 8; ++kc)
-                bulk_load_1d(vd + kc * (24 * 16), p.Vp + tile + (static_cast<size_t>(kc) * A6_DPAD + 24 * rank) * 16, 24 * 16, kv_full);
+                bulk_load_1d(vd + kc * ((A6_DPAD / 2) * 16),
+                             p.Vp + tile + (static_cast<size_t>(kc) * A6_DPAD + (A6_DPAD / 2) * rank) * 16, (A6_DPAD / 2) * 16, kv_full);
             }
           }
           __syncwarp();
@@ -211,7 +235,9 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         constexpr uint32_t idesc_q = umma_idesc_bf16(2 * A6_BM, A6_BN);
         A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 0);
         uint32_t it = 0;
-        if (nunits > 0) mbar_wait(w_full, 0);
+        if constexpr (Cfg::WSTAT) {
+          if (nunits > 0) mbar_wait(w_full, 0);
+        }
         for (int i = 0; i < nunits; ++i) {
           const int slot = i & 1;
           if (i >= 2) mbar_wait(&slot_free[slot], ((i >> 1) - 1) & 1);
@@ -223,8 +249,9 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
             mbar_wait(&full[s], ph);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t da = umma_desc_sw128(smem + s * A6_A_BYTES);
-              const uint64_t dw = umma_desc_sw128(smem + A6_OFF_W + kb * A6_WH_BYTES);
+              const uint64_t da = umma_desc_sw128(smem + s * Cfg::STAGE_BYTES);
+              const uint64_t dw = umma_desc_sw128(Cfg::WSTAT ? smem + A6_OFF_W + kb * A6_WH_BYTES
+                                                             : smem + s * Cfg::STAGE_BYTES + A6_A_BYTES);
 #pragma unroll
               for (int k = 0; k < A6_BK / 16; ++k)
                 umma_bf16_ss_2sm(tmem + slot * A6_BN, da + 2 * k, dw + 2 * k, idesc_q, (kb | k) != 0);
@@ -264,7 +291,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
               const uint64_t kd = kdesc0 + static_cast<uint32_t>(j * (A6_KV_HEAD_BYTES >> 4));
 #pragma unroll
               for (int k = 0; k < A6_DPAD / 16; ++k)
-                umma_bf16_ts_2sm(tmem + ((j & 1) ? A6_TM_SBUF1 : A6_TM_SBUF0), tslot + a6_q_col(j) + k * 8,
+                umma_bf16_ts_2sm(tmem + ((j & 1) ? A6_TM_SBUF1 : A6_TM_SBUF0), tslot + Cfg::q_col(j) + k * 8,
                                  kd + k * ((2 * 48 * 16) >> 4), idesc_s, k != 0);
               umma_commit_2sm(&s_full[j & 1]);
             }
@@ -280,7 +307,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       // overwrites TMEM columns that held the packed Q of heads 0 / 1 of the slot: their QK^T completed before the
       // softmax group could read S, i.e. before p_ready.
       constexpr uint32_t idesc_o = umma_idesc_bf16(2 * A6_BM, A6_DPAD);
-      const uint64_t vdesc0 = umma_desc(smem_u32(kv + A6_KH_BYTES), 24 * 16, 128, UMMA_LAYOUT_NONE);
+      const uint64_t vdesc0 = umma_desc(smem_u32(kv + A6_KH_BYTES), (A6_DPAD / 2) * 16, 128, UMMA_LAYOUT_NONE);
       const uint64_t pdesc0 = umma_desc(smem_u32(smem + A6_OFF_P), A6_BM * 16, 128, UMMA_LAYOUT_NONE);
       A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1);
       tr.base = nullptr;
@@ -309,7 +336,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
             const uint64_t vd = vdesc0 + static_cast<uint32_t>(j * (A6_KV_HEAD_BYTES >> 4));
 #pragma unroll
             for (int k = 0; k < A6_KEYS / 16; ++k)
-              umma_bf16_ss_2sm(tslot + a6_o_col(w), pd + k * ((2 * A6_BM * 16) >> 4), vd + k * ((2 * 24 * 16) >> 4), idesc_o, k != 0);
+              umma_bf16_ss_2sm(tslot + Cfg::o_col(w), pd + k * ((2 * A6_BM * 16) >> 4), vd + k * ((2 * (A6_DPAD / 2) * 16) >> 4), idesc_o, k != 0);
             umma_commit_2sm(&o_full[w]);
             // the next unit belongs to another sample: its K/V tiles may replace these once this PV has read them
             if (j == A6_HPC - 1 && i + 1 < nunits && i + 1 == kv_end) umma_commit_2sm(kv_free);
@@ -350,7 +377,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       const int m0 = mt * A6_BM;
       const bool row_ok = (m0 + row) < p.S;
 #pragma unroll 1
-      for (int jj = 0; jj < 2; ++jj) {
+      for (int jj = 0; jj < A6_HPC / 2; ++jj) {
         const int j = wg + 2 * jj;                   // this group's heads of the unit
         const int nn = i * A6_HPC + j;
         const uint32_t par = (nn >> 1) & 1;
@@ -392,8 +419,11 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
           // The exponentials are MUFU-bound (8 cycles per warp instruction) and the two groups' warps of a lane quarter
           // share one scheduler: a token (two producer/consumer named barriers) makes them take turns, so that one
           // warp's exponentials overlap the other's TMEM loads, max pass, packing and stores instead of its exponentials.
-          if (wg == 0) { if (nn >= 2) named_bar_sync(5 + q, 64); }
-          else         { named_bar_sync(1 + q, 64); }
+          // (d = 80 has one head per group and unit: there the unit's latency matters, not the MUFU throughput.)
+          if constexpr (D == 40) {
+            if (wg == 0) { if (nn >= 2) named_bar_sync(5 + q, 64); }
+            else         { named_bar_sync(1 + q, 64); }
+          }
 #pragma unroll
           for (int k = 0; k < A6_IMG_OFF / 2; ++k) {
             const int c = 2 * k;
@@ -450,8 +480,10 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
 #pragma unroll
             for (int c = A6_IMG_OFF + 8; c < A6_KEYS; ++c) sr[c] = 0u;
           }
-          if (wg == 0) { named_bar_arrive(1 + q, 64); }
-          else         { if (nn + 2 < nheads) named_bar_arrive(5 + q, 64); }
+          if constexpr (D == 40) {
+            if (wg == 0) { named_bar_arrive(1 + q, 64); }
+            else         { if (nn + 2 < nheads) named_bar_arrive(5 + q, 64); }
+          }
           float l0, l1, l2, l3, li0, li1;
           f2_unpack(lacc[0], l0, l1);
           f2_unpack(lacc[1], l2, l3);
@@ -520,21 +552,37 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     int b_d = u0 / p.MTP - 1;
     int m0_d = 0;
 
-    // Q of unit iu: fp32 [40 j, 40 j + 40) -> packed bf16 [40 j + 16, 40 j + 40), dims 40..47 zero (K = 48 contraction)
+    // Q of unit iu, fp32 accumulator -> packed bf16 in place.  d = 40: [40 j, +40) -> [40 j + 16, 40 j + 40), dims 40..47
+    // zero (K = 48 contraction).  d = 80: [80 j, +80) -> [80 j + 40, 80 j + 80), upper half first so that every store
+    // lands on columns whose fp32 source is already in registers.
     auto convert_unit = [&](int iu) {
       const uint32_t tslot = tlane + (iu & 1) * A6_BN;
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < A6_HPC; ++j) {
-        uint32_t a[32], c8[8], o[24];
-        tmem_ld_x32(tslot + 40 * j, a);
-        tmem_ld_x8(tslot + 40 * j + 32, c8);
-        tmem_ld_wait();
-        pack_pairs3<32>(a, o);
-        pack_pairs3<8>(c8, o + 16);
-        o[20] = o[21] = o[22] = o[23] = 0u;
-        tmem_st_x16(tslot + 40 * j + 16, o);
-        tmem_st_x8(tslot + 40 * j + 32, o + 16);
+        if constexpr (D == 40) {
+          uint32_t a[32], c8[8], o[24];
+          tmem_ld_x32(tslot + 40 * j, a);
+          tmem_ld_x8(tslot + 40 * j + 32, c8);
+          tmem_ld_wait();
+          pack_pairs3<32>(a, o);
+          pack_pairs3<8>(c8, o + 16);
+          o[20] = o[21] = o[22] = o[23] = 0u;
+          tmem_st_x16(tslot + 40 * j + 16, o);
+          tmem_st_x8(tslot + 40 * j + 32, o + 16);
+        } else {
+#pragma unroll
+          for (int hh = 1; hh >= 0; --hh) {
+            uint32_t a[32], c8[8], o[20];
+            tmem_ld_x32(tslot + 80 * j + 40 * hh, a);
+            tmem_ld_x8(tslot + 80 * j + 40 * hh + 32, c8);
+            tmem_ld_wait();
+            pack_pairs3<32>(a, o);
+            pack_pairs3<8>(c8, o + 16);
+            tmem_st_x16(tslot + 80 * j + 40 + 20 * hh, o);
+            tmem_st_x4(tslot + 80 * j + 40 + 20 * hh + 16, o + 16);
+          }
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -542,7 +590,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     };
     // O(nn): TMEM -> registers (accumulator released at once) -> * row scale -> bf16 -> staging slab -> TMA store
     auto drain_head = [&](int nn) {
-      const int i = nn >> 2, j = nn & 3;
+      const int i = nn / A6_HPC, j = nn % A6_HPC;
       const uint32_t w = j & 1;
       const uint32_t par = (nn >> 1) & 1;
       if (j == 0) {                                  // first head of a unit: where its rows live
@@ -553,15 +601,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         m0_d = (2 * (u0 + i - b_d * p.MTP) + static_cast<int>(rank)) * A6_BM;
       }
       tc_fence_after();
-      uint32_t a[32], c8[8];
-      const uint32_t taddr = tlane + (i & 1) * A6_BN + a6_o_col(w);
-      tmem_ld_x32(taddr, a);
-      tmem_ld_x8(taddr + 32, c8);
-      tmem_ld_wait();
+      const uint32_t taddr = tlane + (i & 1) * A6_BN + Cfg::o_col(w);
       const float oscale = ld_shared_f32_a(osc_a + (w * 2 + par) * (A6_BM * 4));   // read before the release below: the slot is rewritten two heads on
-      tc_fence_before();
-      arrive_leader(&o_free[w]);                     // PV(nn + 2) may overwrite the accumulator
-      if (j == A6_HPC - 1) arrive_leader(&slot_free[i & 1]);   // ... and the projection of unit i + 2 the whole slot
       uint8_t* slab = ost + w * A6_OST_BYTES;
       if (elect_one()) bulk_wait_read<1>();          // the store that last read this slab (two drains ago) has finished
       __syncwarp();
@@ -579,8 +620,21 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
           st_shared_v4(slab + lane * (A6_D * 2) + (col0 + c * 8) * 2, w4[0], w4[1], w4[2], w4[3]);
         }
       };
-      stage(a, 0, 32);
-      stage(c8, 32, 8);
+      auto release = [&]() {
+        tc_fence_before();
+        arrive_leader(&o_free[w]);                   // PV(nn + 2) may overwrite the accumulator
+        if (j == A6_HPC - 1) arrive_leader(&slot_free[i & 1]);   // ... and the projection of unit i + 2 the whole slot
+      };
+#pragma unroll
+      for (int ch = 0; ch < D / 40; ++ch) {          // 40 accumulator columns at a time
+        uint32_t a[32], c8[8];
+        tmem_ld_x32(taddr + 40 * ch, a);
+        tmem_ld_x8(taddr + 40 * ch + 32, c8);
+        tmem_ld_wait();
+        if (ch == D / 40 - 1) release();
+        stage(a, 40 * ch, 32);
+        stage(c8, 40 * ch + 32, 8);
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (elect_one()) {
@@ -591,7 +645,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     };
 
     while (drained < nheads) {
-      const int du = drained >> 2;                   // unit of the next head to drain
+      const int du = drained / A6_HPC;                   // unit of the next head to drain
       if (converted <= du) {                         // its Q is not even converted yet: nothing else can make progress
         mbar_wait(&q_full[converted & 1], (converted >> 1) & 1);
         convert_unit(converted);
@@ -623,28 +677,36 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
 extern unsigned long long* g_attn3_trace;
 extern int g_attn3_trace_cap;
 
-template <bool LT77>
+template <int D, bool LT77>
 static int launch_attn6(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const Attn6Params& p,
                         long long unit_pairs, cudaStream_t stream) {
-  auto kern = dual_attn_fwd_pair_roles_kernel<LT77>;
+  auto kern = dual_attn_fwd_pair_roles_kernel<D, LT77>;
   static bool attr_done = false;
   if (!attr_done) {
-    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM_BYTES));
+    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn6Cfg<D>::SMEM_BYTES));
     attr_done = true;
   }
   const long long max_pairs = sm_count() / 2;
   const int npairs = static_cast<int>(unit_pairs < max_pairs ? unit_pairs : max_pairs);
-  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(A6_THREADS), A6_SMEM_BYTES, stream, tmX, tmWq, tmO, p));
+  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(A6_THREADS), Attn6Cfg<D>::SMEM_BYTES, stream, tmX, tmWq, tmO, p));
   PV_LAUNCHED();
   return PV_OK;
 }
 
-// Same contract as dual_attn_core_bf16_pair (pv_attn4.cu), for C = 320 with head_dim 40 and at least two row tiles per sample.
+// Same contract as dual_attn_core_bf16_pair (pv_attn4.cu), for head_dim 40 with C = 320 (resident Wq slice) and for
+// head_dim 80, with at least two row tiles per sample.
+bool dual_attn_pair_roles_supported(int S, int C, int H) {
+  if (H <= 0 || C % H != 0 || S <= A6_BM || C % A6_BN != 0 || C % A6_BK != 0) return false;
+  const int d = C / H;
+  return (d == 40 && C == Attn6Cfg<40>::KB_RES * A6_BK) || d == 80;
+}
+
 int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
                                    int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                                    cudaStream_t stream) {
-  PV_REQUIRE(B > 0 && S > A6_BM && H > 0 && C == A6_KB * A6_BK && C / H == A6_D, "needs C=320, head_dim 40, S>128 (B=%d S=%d C=%d H=%d)",
+  PV_REQUIRE(B > 0 && dual_attn_pair_roles_supported(S, C, H), "needs head_dim 40 with C=320 or head_dim 80, S>128 (B=%d S=%d C=%d H=%d)",
              B, S, C, H);
+  const int d = C / H;
   PV_REQUIRE(Lt >= 1 && Lt <= A6_IMG_OFF && Li >= 1 && Li <= A6_KEYS - A6_IMG_OFF,
              "need 1 <= Lt <= %d and 1 <= Li <= %d (Lt=%d Li=%d)", A6_IMG_OFF, A6_KEYS - A6_IMG_OFF, Lt, Li);
   PV_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wq) | reinterpret_cast<uintptr_t>(Kp) |
@@ -652,7 +714,7 @@ int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp
   CUtensorMap tmX, tmWq, tmO;
   if (make_tmap_3d(&tmX, X, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, A6_BK, A6_BM, 1, Swz::B128)) return PV_ERR_CUDA;
   if (make_tmap_3d(&tmWq, Wq, 2, C, C, 1, C * 2ull, static_cast<uint64_t>(C) * C * 2, A6_BK, A6_BN / 2, 1, Swz::B128)) return PV_ERR_CUDA;
-  if (make_tmap_3d(&tmO, O, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, A6_D, 32, 1, Swz::None)) return PV_ERR_CUDA;
+  if (make_tmap_3d(&tmO, O, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, d, 32, 1, Swz::None)) return PV_ERR_CUDA;
   Attn6Params p;
   p.Kp = static_cast<const uint8_t*>(Kp);
   p.Vp = static_cast<const uint8_t*>(Vp);
@@ -667,9 +729,12 @@ int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp
   p.w_text = w_text; p.w_img = w_img;
   p.trace = g_attn3_trace;
   p.trace_cap = g_attn3_trace_cap;
-  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(A6_D));
-  return Lt == 77 ? launch_attn6<true>(tmX, tmWq, tmO, p, unit_pairs, stream)
-                  : launch_attn6<false>(tmX, tmWq, tmO, p, unit_pairs, stream);
+  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(d));
+  if (d == 40)
+    return Lt == 77 ? launch_attn6<40, true>(tmX, tmWq, tmO, p, unit_pairs, stream)
+                    : launch_attn6<40, false>(tmX, tmWq, tmO, p, unit_pairs, stream);
+  return Lt == 77 ? launch_attn6<80, true>(tmX, tmWq, tmO, p, unit_pairs, stream)
+                  : launch_attn6<80, false>(tmX, tmWq, tmO, p, unit_pairs, stream);
 }
 
 }  // namespace pv
