@@ -111,6 +111,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
   uint64_t* o_free = o_full + 2;                // [2] (leader) O accumulator in registers             count 8 (epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
+  const long long t_entry = clock64();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -158,6 +159,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
   cluster_sync_all();                 // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const long long t_sync = clock64();
 
   // Nothing above reads what a predecessor kernel may have written; the resident Wq slice (static weights) is requested
   // before the dependency wait as well.
@@ -174,6 +176,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
   }
   pdl_wait();
   pdl_launch_dependents();
+  const long long t_pdl = clock64();
 
   // one elected lane per warp arrives on the LEADER CTA's copy of `bar`
   auto arrive_leader = [&](uint64_t* bar) {
@@ -234,6 +237,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         // ===================== projection MMA issuer (leader): Q = X Wq^T for BOTH CTAs, M = 256, N = 160 =====================
         constexpr uint32_t idesc_q = umma_idesc_bf16(2 * A6_BM, A6_BN);
         A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 0);
+        a3_trace(tr, 1, static_cast<int>(t_sync - t_entry));      // prologue: barrier init, TMEM allocation, cluster sync
+        a3_trace(tr, 2, static_cast<int>(t_pdl - t_entry));       // ... + wait for the predecessor grid
         uint32_t it = 0;
         if constexpr (Cfg::WSTAT) {
           if (nunits > 0) mbar_wait(w_full, 0);

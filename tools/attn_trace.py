@@ -47,7 +47,7 @@ for r in range(4):
 ev.sort()
 n = len(ev)
 t0 = ev[0][0]
-names = {12: " qp full", 13: " qp mma issued", 14: " qp committed", 22: "  qk begin", 23: "  qk mmas issued", 25: "  pv wait p_ready", 26: "  pv p_ready ok", 27: "  pv mmas issued", 10: "QP start", 11: "QP issued", 20: "  QK issued", 21: "  PV issued", 29: "    A wait q_full", 30: "    A q_full", 31: "    A conv done",
+names = {1: "prologue cycles (entry -> cluster sync) =", 2: "entry -> after griddepcontrol.wait =", 12: " qp full", 13: " qp mma issued", 14: " qp committed", 22: "  qk begin", 23: "  qk mmas issued", 25: "  pv wait p_ready", 26: "  pv p_ready ok", 27: "  pv mmas issued", 10: "QP start", 11: "QP issued", 20: "  QK issued", 21: "  PV issued", 29: "    A wait q_full", 30: "    A q_full", 31: "    A conv done",
          32: "    A slot_free", 33: "    A s_full", 34: "    A p_ready", 35: "    A S loaded", 36: "    A exps done", 37: "    A exchanged", 38: "    A drained",
          45: "        B S loaded", 46: "        B exps done", 47: "        B exchanged", 48: "        B drained", 39: "        B wait q_full", 40: "        B q_full", 41: "        B conv done",
          42: "        B slot_free", 43: "        B s_full", 44: "        B p_ready"}
