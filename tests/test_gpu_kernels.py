@@ -162,9 +162,11 @@ def test_processor_matches_golden(cuda_device, case, dtype):
 
 
 @pytest.mark.parametrize("S,C,Li,B", [(4096, 320, 5, 2), (1024, 640, 1, 2), (256, 1280, 16, 2), (64, 1280, 5, 3),
-                                      (2304, 640, 4, 1), (576, 1280, 8, 1)])
+                                      (2304, 640, 4, 1), (576, 1280, 8, 1), (9216, 320, 16, 1), (144, 1280, 4, 2),
+                                      (1024, 320, 8, 2), (256, 640, 16, 2), (16, 1280, 5, 4), (130, 320, 1, 3)])
 def test_processor_bf16_full_size_vs_oracle(cuda_device, S, C, Li, B):
-    """BASELINE shapes (latent 64^2 and 96^2): CUDA bf16 path vs the fp32 oracle evaluated on the same inputs."""
+    """BASELINE config 2 / config 5 shapes (latent 32^2, 64^2 and 96^2 at all four UNet resolutions, Li in 1..16, ragged
+    last tiles): CUDA bf16 path vs the fp32 oracle evaluated on the same inputs."""
     case = cases.ProcCase(f"full_{S}_{C}", B=B, S=S, C=C, Li=Li, seed=40 + Li)
     attn, proc = build_product_layer(case, cuda_device)
     x, text, img = cases.proc_inputs(case, torch.float32)
