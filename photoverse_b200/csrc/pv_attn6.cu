@@ -76,6 +76,7 @@ struct Attn6Params {
   float w_text, w_img, scale_log2e;
   unsigned long long* trace;
   int trace_cap;
+  int trace_block;         // which (leader) CTA writes the debug timeline (pv_set_option attn3_dbg; default 0)
 };
 
 template <int D, bool LT77>
@@ -236,7 +237,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       if (rank == 0) {
         // ===================== projection MMA issuer (leader): Q = X Wq^T for BOTH CTAs, M = 256, N = 160 =====================
         constexpr uint32_t idesc_q = umma_idesc_bf16(2 * A6_BM, A6_BN);
-        A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 0);
+        A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 0, p.trace_block);
         a3_trace(tr, 1, static_cast<int>(t_sync - t_entry));      // prologue: barrier init, TMEM allocation, cluster sync
         a3_trace(tr, 2, static_cast<int>(t_pdl - t_entry));       // ... + wait for the predecessor grid
         uint32_t it = 0;
@@ -274,7 +275,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         // ===================== QK^T issuer (leader): S(nn) = Q_head K_head^T, one head ahead of each softmax group ============
         // Needs: packed bf16 Q of the unit (q_ready), the sample's K/V (kv_both), S buffer nn & 1 read out (s_free).
         constexpr uint32_t idesc_s = umma_idesc_bf16(2 * A6_BM, A6_KEYS);
-        A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1);
+        A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1, p.trace_block);
         const uint64_t kdesc0 = umma_desc(smem_u32(kv), 48 * 16, 128, UMMA_LAYOUT_NONE);
         uint32_t kv_gen = 0;
         int kv_end = 0;
@@ -314,7 +315,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       constexpr uint32_t idesc_o = umma_idesc_bf16(2 * A6_BM, A6_DPAD);
       const uint64_t vdesc0 = umma_desc(smem_u32(kv + A6_KH_BYTES), (A6_DPAD / 2) * 16, 128, UMMA_LAYOUT_NONE);
       const uint64_t pdesc0 = umma_desc(smem_u32(smem + A6_OFF_P), A6_BM * 16, 128, UMMA_LAYOUT_NONE);
-      A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1);
+      A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1, p.trace_block);
       tr.base = nullptr;
       uint32_t kv_gen = 0;
       int kv_end = 0;
@@ -367,7 +368,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     const int Lt = p.Lt;
     const int Li = p.Li;
     const float cs = p.scale_log2e;
-    A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 2 + wg);
+    A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 2 + wg, p.trace_block);
     if (q != 0) tr.base = nullptr;
     int kv_end = 0;                                  // only to track the sample index of a unit without dividing per head
     int b = u0 / p.MTP - 1;
@@ -681,6 +682,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
 
 extern unsigned long long* g_attn3_trace;
 extern int g_attn3_trace_cap;
+extern int g_opt_attn3_dbg;
 
 template <int D, bool LT77>
 static int launch_attn6(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const Attn6Params& p,
@@ -734,6 +736,7 @@ int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp
   p.w_text = w_text; p.w_img = w_img;
   p.trace = g_attn3_trace;
   p.trace_cap = g_attn3_trace_cap;
+  p.trace_block = g_opt_attn3_dbg;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(d));
   if (d == 40)
     return Lt == 77 ? launch_attn6<40, true>(tmX, tmWq, tmO, p, unit_pairs, stream)

@@ -81,10 +81,10 @@ struct A3Trace {
   unsigned long long* base;
   int n, cap;
 };
-__device__ __forceinline__ A3Trace a3_trace_init_raw(unsigned long long* trace, int trace_cap, int role) {
+__device__ __forceinline__ A3Trace a3_trace_init_raw(unsigned long long* trace, int trace_cap, int role, int block = 0) {
   A3Trace t;
   const int per = trace_cap / 4;
-  t.base = (trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? trace + 4 + static_cast<size_t>(role) * per * 3 : nullptr;
+  t.base = (trace != nullptr && static_cast<int>(blockIdx.x) == block && (threadIdx.x & 31) == 0) ? trace + 4 + static_cast<size_t>(role) * per * 3 : nullptr;
   t.n = 0;
   t.cap = per;
   return t;

@@ -1,5 +1,5 @@
 #!/bin/bash
 cd /root/repo
-mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "full_size" 2>&1 | tail -4
-PV_SWEEP_OUT=gpurun_out/micro_sweep_r01.json timeout 600 python tools/micro_sweep.py 2>&1 | tail -75
+for blk in 0 2 72 74 146; do
+PV_ATTN_VARIANT=6 PV_DBG=$blk PV_TRACE_OUT=gpurun_out/trace_v6_blk$blk.json PV_NEV=3 timeout 120 python tools/attn_trace.py | tail -1
+done
