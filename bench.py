@@ -221,13 +221,13 @@ def roofline_leg(device, rows_b, Li, scale):
     f_attn = sum(attn_kernel_flops(rows_b, S, C, Li) for S, C in LAYER_SHAPES)
     f_proc = sum(processor_flops_cached(rows_b, S, C, Li) for S, C in LAYER_SHAPES)
     ach = f_attn / t_attn / 1e12
-    roof = {"bound": "tensor", "kernel": "dual_attn_fwd_pair_roles_kernel (C=320 layers) / dual_attn_fwd_pair_kernel (C>=640): fused Q-proj + dual-branch attention on cta_group::2 CTA pairs; single-CTA persistent kernel for S <= 128",
+    roof = {"bound": "tensor", "kernel": "dual_attn_fwd_pair_roles_kernel (head_dim 40 / 80 layers) / dual_attn_fwd_pair_kernel (head_dim 160): fused Q-proj + dual-branch attention on cta_group::2 CTA pairs; single-CTA persistent kernel for S <= 128",
             "achieved": round(ach, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": round(ach / peaks["bf16_tflops"], 4), "peak_source": peaks["source"] + " cuBLAS bf16 burst",
             # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant (S4096, C320) instance from the ncu
-            # --set full capture of tools/profile_layer_stack.py (profiles/r01m_ncu_attn.csv): 44.6 MB + 3.7 MB;
+            # --set full capture of tools/profile_layer_stack.py (profiles/r01n_ncu_attn.csv): 44.7 MB + 4.6 MB;
             # algorithmic bytes of that launch: X 41.9 MB in (+ 0.2 MB Wq, 2.4 MB K/V tiles), O 41.9 MB out (stays in L2)
-            "traffic": 48.3e6, "traffic_unit": "bytes per launch, S4096_C320 layer (ncu r01m)",
+            "traffic": 49.3e6, "traffic_unit": "bytes per launch, S4096_C320 layer (ncu r01n)",
             "how": f"CUDA events around a CUDA graph of 20 launches per attn2 layer shape at {rows_b} rows (uncond+cond), "
                    f"inputs rotated through > L2 of buffers; aggregated over the 16 layers of one UNet evaluation; "
                    f"algorithmic FLOPs = 2 rows C^2 + 4 rows C (77 + Li) per launch",
