@@ -85,6 +85,7 @@ int g_opt_gemm_pair = 0;         // cta_group::2 CTA-pair GEMM (pv_gemm2.cu) for
 // 4: persistent CTA pairs (cta_group::2), B operands split across the pair (pv_attn4.cu); falls back to 3 when a sample
 //    has a single 128-row tile
 int g_opt_attn_variant = 6;
+int g_opt_bwd_mma = 1;            // bf16 attention backward on mma.sync tensor cores (0: fp32-accurate SIMT kernel)
 int g_opt_attn3_stages = 0;
 int g_opt_attn3_prefetch = 0;   // L2 prefetch distance (units) of the X tiles in the persistent attention kernel
 int g_opt_attn3_wstat = 1;      // C = 320: keep the CTA's Wq slice resident in shared memory (A/B switch)
@@ -213,6 +214,7 @@ int pv_set_option(const char* name, int value) {
   if (!strcmp(name, "gemm_persistent")) { g_opt_gemm_persistent = value; return PV_OK; }
   if (!strcmp(name, "pdl")) { g_opt_pdl = value; return PV_OK; }
   if (!strcmp(name, "attn_variant")) { g_opt_attn_variant = value; return PV_OK; }
+  if (!strcmp(name, "bwd_mma")) { g_opt_bwd_mma = value; return PV_OK; }
   if (!strcmp(name, "attn3_dbg")) { g_opt_attn3_dbg = value; return PV_OK; }
   if (!strcmp(name, "attn3_stages")) { g_opt_attn3_stages = value; return PV_OK; }
   if (!strcmp(name, "attn3_wstat")) { g_opt_attn3_wstat = value; return PV_OK; }

@@ -99,7 +99,7 @@ int transpose_2d(bool bf16, const void* in, void* out, long long R, long long Cc
 // ------------------------------------------------------------------------------------------------
 // dW[N,K] = alpha * sum_m G[m,n] X[m,k]   -- SIMT fp32, split over M, deterministic two-pass reduction
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_MCHUNK = 1024;
+constexpr int WG_MCHUNK = 128;       // rows per block: a block walks them in 16-row steps, so short chunks = many blocks
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -416,7 +416,7 @@ int group_mean_bwd(bool bf16, const void* dy, void* dx, long long groups, int P,
 // block = (query chunk, head, sample), 256 threads; dK / dV of the chunk accumulate in registers.
 // ------------------------------------------------------------------------------------------------
 constexpr int AB_TQ = 32;         // queries per tile
-constexpr int AB_CHUNK = 256;     // queries per block
+constexpr int AB_CHUNK = 128;     // queries per block (== the row tile of the tensor-core kernel in pv_bwd_mma.cu)
 constexpr int AB_LP = PV_KEYS_PAD + 1;
 
 template <int D, typename T>
@@ -569,12 +569,19 @@ static int launch_attn_bwd(const void* dO, const void* Q, const float* kv_text, 
   return PV_OK;
 }
 
+int dual_attn_bwd_mma(const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats, void* dQ,
+                      float* part, int nchunk, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                      cudaStream_t stream);
+extern int g_opt_bwd_mma;
+
 int dual_attn_bwd(bool bf16, const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats,
                   void* dQ, float* part, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                   cudaStream_t stream) {
   PV_REQUIRE(B > 0 && S > 0 && H > 0 && C % H == 0 && B <= 65535 && H <= 65535, "bad shape");
   PV_REQUIRE(Lt >= 1 && Li >= 1 && Lt + Li <= PV_KEYS_PAD, "need 1 <= Lt, 1 <= Li, Lt+Li <= %d", PV_KEYS_PAD);
   const int d = C / H;
+  if (bf16 && g_opt_bwd_mma != 0)       // tensor-core kernel (pv_bwd_mma.cu); the SIMT kernel below is the fp32 parity path
+    return dual_attn_bwd_mma(dO, Q, kv_text, kv_img, stats, dQ, part, attn_bwd_chunks(S), B, S, C, H, Lt, Li, w_text, w_img, stream);
 #define PV_AB(DD)                                                                                                        \
   return bf16 ? launch_attn_bwd<DD, __nv_bfloat16>(dO, Q, kv_text, kv_img, stats, dQ, part, B, S, C, H, Lt, Li, w_text, w_img, stream) \
               : launch_attn_bwd<DD, float>(dO, Q, kv_text, kv_img, stats, dQ, part, B, S, C, H, Lt, Li, w_text, w_img, stream)
