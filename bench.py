@@ -28,6 +28,10 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE JSON line: NCCL's own messages (e.g. the "NCCL version ..." banner that NCCL_DEBUG=VERSION
+# prints on the first communicator) go to stderr.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
