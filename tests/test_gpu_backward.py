@@ -208,3 +208,33 @@ def test_backward_is_deterministic(cuda_device):
         outs.append((x.grad.clone(), proc.to_k_ip[0].weight.grad.clone(), attn.to_q.lora_A["default"].weight.grad.clone()))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_tensor_core_backward_agrees_with_simt_backward(cuda_device):
+    """bf16 training path: the mma.sync attention backward (pv_bwd_mma.cu, default) and the fp32-accumulating SIMT kernel
+    (pv_set_option('bwd_mma', 0)) on identical inputs -- two independent implementations of reference :317-420's
+    derivative must agree to bf16 rounding."""
+    from photoverse_b200 import _lib
+    case = cases.ProcCase("mma_vs_simt", B=2, S=300, C=640, Li=5, lora_r=8, seed=79)
+    grads = {}
+    for flag in (1, 0):
+        _lib.set_option("bwd_mma", flag)
+        try:
+            attn, proc = build_product_layer(case, cuda_device)
+            for n, p in attn.named_parameters():
+                p.requires_grad_("lora_" in n or "to_k_ip" in n or "to_v_ip" in n)
+            x, text, img = (t.to(cuda_device, torch.bfloat16) for t in cases.proc_inputs(case, torch.float32))
+            x.requires_grad_(True)
+            text.requires_grad_(True)
+            force_fusion_seed(1.0, 1.0)
+            with torch.enable_grad():
+                y = attn(x, encoder_hidden_states=(text, img))
+                (y.float().square().sum() + proc.to_v_ip_norm.float().sum()).backward()
+            grads[flag] = {"x": x.grad.clone(), "text": text.grad.clone(), "kip": proc.to_k_ip[0].weight.grad.clone(),
+                           "vip": proc.to_v_ip[0].weight.grad.clone(), "qA": attn.to_q.lora_A["default"].weight.grad.clone(),
+                           "kB": attn.to_k.lora_B["default"].weight.grad.clone()}
+        finally:
+            _lib.set_option("bwd_mma", 1)
+    for k in grads[1]:
+        e = _rel(grads[1][k], grads[0][k])
+        assert e <= 2e-2, f"{k}: tensor-core vs SIMT backward relative difference {e:.3e}"
