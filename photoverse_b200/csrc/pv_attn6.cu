@@ -1,5 +1,5 @@
-// photoverse_b200 -- fused Q-projection + dual-branch cross-attention, variant 6: the C = 320 (head_dim 40) layers on
-// persistent CTA pairs with DECOUPLED roles.
+// photoverse_b200 -- fused Q-projection + dual-branch cross-attention, variant 6: persistent CTA pairs with DECOUPLED
+// roles, for head_dim 40 (C = 320: Wq slice resident) and head_dim 80 (X and Wq streamed together).
 //
 // The device timelines of variants 4 / 5 (tools/attn_trace.py) showed that at C = 320 the kernel is
 // bound by the CUDA-core side, not by the tensor pipe or the TMA ingest: a softmax group spent ~2200 cycles on the
