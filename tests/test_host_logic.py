@@ -123,6 +123,30 @@ def test_lora_injection_matches_peft_layout():
     assert n_lora == 595_968                                            # SURVEY 8 a5 (r = 8, 16 layers)
 
 
+def test_lora_dropout_routing_follows_the_train_toggle():
+    """peft applies `lora_dropout` only in training mode; the reference switches the attn2 modules to train() with
+    `set_cross_attention_layers_to_train` (models/unet.py:50-53, train.py:462).  The processor must take the un-merged
+    path exactly then."""
+    unet = UNetSD15(block_out_channels=(320, 640), layers_per_block=1)
+    pv.set_visual_cross_attention_adapter(unet)
+    inject_lora(unet, r=8, lora_dropout=0.1)
+    unet.eval()
+    attn = unet.mid_block.attentions[0].transformer_blocks[0].attn2
+    proc = attn.processor
+    assert linear_parts(attn.to_q)[4] == 0.0 and not proc.lora_dropout_active(attn)        # eval: nn.Dropout is the identity
+    pv.set_cross_attention_layers_to_train(unet)
+    assert attn.to_q.training and linear_parts(attn.to_q)[4] == pytest.approx(0.1)
+    assert proc.lora_dropout_active(attn)
+    attn1 = unet.mid_block.attentions[0].transformer_blocks[0].attn1
+    assert not attn1.training                                                              # only attn2 is switched
+    plain = UNetSD15(block_out_channels=(320, 640), layers_per_block=1)
+    pv.set_visual_cross_attention_adapter(plain)
+    inject_lora(plain, r=8)                                                                # p = 0: nn.Identity
+    pv.set_cross_attention_layers_to_train(plain)
+    a2 = plain.mid_block.attentions[0].transformer_blocks[0].attn2
+    assert not a2.processor.lora_dropout_active(a2)
+
+
 def UNetSD15_lora_params():
     unet = UNetSD15()
     inject_lora(unet, r=8)
