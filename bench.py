@@ -187,6 +187,7 @@ def roofline_leg(device, rows_b, Li, scale):
         os_ = [torch.empty_like(xs[0]) for _ in range(nbuf)]
         ys = [torch.empty_like(xs[0]) for _ in range(nbuf)]
         lib = _lib.lib()
+        sync = torch.zeros(int(lib.pv_dual_attn_sync_words(rows_b, S)), device=device, dtype=torch.int32)
 
         def attn_only(i):
             _lib.check(lib.pv_dual_attn_core_fwd(1, ops._ptr(xs[i]), ops._ptr(wq), ops._ptr(kv.Kp), ops._ptr(kv.Vp),
@@ -195,7 +196,7 @@ def roofline_leg(device, rows_b, Li, scale):
         def full(i):
             _lib.check(lib.pv_dual_attn_fwd(1, ops._ptr(xs[i]), ops._ptr(wq), ops._ptr(kv.Kp), ops._ptr(kv.Vp),
                                             ops._ptr(wo), ops._ptr(bo), ops._ptr(ys[i]), None, ops._ptr(os_[i]), None,
-                                            rows_b, S, C, H, LT, Li, 1.0, 1.0, ops._stream()))
+                                            ops._ptr(sync), rows_b, S, C, H, LT, Li, 1.0, 1.0, ops._stream()))
 
         out = {}
         for name, fn in (("attn", attn_only), ("proc", full)):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PV_ABI_VERSION 1
+#define PV_ABI_VERSION 2
 
 enum { PV_OK = 0, PV_ERR_INVALID = 1, PV_ERR_CUDA = 2, PV_ERR_UNSUPPORTED = 3 };
 typedef enum { PV_F32 = 0, PV_BF16 = 1 } pv_dtype;
@@ -45,10 +45,19 @@ int pv_version(void);
 const char* pv_last_error(void);
 /* Number of kernels this library has launched since it was loaded (bench.py: "gpu_launches"). */
 unsigned long long pv_launch_count(void);
-/* Runtime switches for A/B testing kernel variants (name -> int). Unknown names return PV_ERR_INVALID. */
+/* TEST-ONLY process-wide switches (not thread-safe; production code never calls this).  Every value selects among
+ * kernels that compute the same result -- none changes results:
+ *   "fuse_out" 1|0        out projection as the second phase of the attention launch | as a separate GEMM launch
+ *   "gemm_persistent" 1|0 persistent CTA-pair GEMM for out-projection-shaped pv_linear_fwd calls | single-CTA kernel
+ *   "gemm_two_cta" 1|0, "force_bn" 0|64|128|160|256, "epi_swizzle" 1|0   tile choices of the single-CTA GEMM
+ *   "pdl" 1|0             programmatic dependent launch of the persistent kernels
+ *   "bwd_mma" 1|0         bf16 attention backward on tensor cores | the fp32-accurate SIMT kernel
+ *   "trace_block" n       which leader CTA writes the debug timeline (PV_TRACE builds)
+ * Unknown names return PV_ERR_INVALID.                                                                         */
 int pv_set_option(const char* name, int value);
-/* Debug only: device buffer of 4 + 3*capacity uint64 (zeroed by the caller) that CTA 0 of the persistent attention
- * kernel fills with (event, index, SM clock) triples; NULL switches tracing off.                                */
+/* Debug builds only (PV_TRACE=1 python -m photoverse_b200.build --force): device buffer of 4 + 3*capacity uint64
+ * (zeroed by the caller) that one CTA of the persistent attention kernels fills with (event, index, SM clock)
+ * triples; NULL switches it off.  Release builds return PV_ERR_INVALID for a non-NULL buffer.                    */
 int pv_debug_trace(void* buf, int capacity_events);
 
 /* ---- weights ---------------------------------------------------------------------------------------
@@ -63,7 +72,10 @@ int pv_pack_weight(pv_dtype out_dt, const float* W, const float* lora_A, const f
  *                                    W:[batch,N,K] (ldw, strideW; strideW == 0 -> one shared weight)
  *                                    bias fp32 [batch,N] (strideBias) or NULL;  D:[batch,M,N] (ldd, strideD)
  * dt is the type of A and W; out_dt the type of D.  PV_BF16: K % 8 == 0 and 16-byte aligned rows.
- * Replaces nn.Linear (attention_processor.py:297,304,305,392,393,423; adapters.py:14-28).               */
+ * Replaces nn.Linear (attention_processor.py:297,304,305,392,393,423; adapters.py:14-28).
+ * Stream-ordering precondition: W and bias must not be the OUTPUT of the kernel enqueued immediately before this
+ * call on `stream` (they are weights: the persistent kernels fetch them before their programmatic-dependent-launch
+ * wait; A and D are only touched after it).  Weights written two or more kernels earlier are fine.            */
 int pv_linear_fwd(pv_dtype dt, pv_dtype out_dt, const void* A, const void* W, const float* bias, void* D,
                   int64_t M, int64_t N, int64_t K, int64_t batch, int64_t lda, int64_t ldw, int64_t ldd,
                   int64_t strideA, int64_t strideW, int64_t strideBias, int64_t strideD, void* stream);
@@ -87,12 +99,19 @@ int pv_kv_pack_fwd(pv_dtype dt, const void* text, const void* img, const void* W
  * ws_q : PV_F32 only, [B,S,C] fp32 scratch for Q (may be NULL for PV_BF16: Q never leaves the SM)
  * ws_o : [B,S,C] (dt) attention output before the out projection (saved for backward)
  * stats: optional [B,H,S,4] fp32 = (max_text, sum_text, max_img, sum_img) of the scaled logits, for backward
- * PV_BF16 path: ONE fused tcgen05 kernel does Q-projection -> QK^T over the concatenated keys -> per-segment
- * softmax with the branch weights folded in -> ONE PV contraction; a second tcgen05 GEMM applies Wo + bias.
+ * ws_sync: PV_BF16, optional: pv_dual_attn_sync_words(B, S) uint32 words, ZERO on entry and left zero on return
+ *          (row-block counters; one buffer may serve any number of calls that are ordered on one stream).
+ * PV_BF16 path with ws_sync and S > 128: ONE persistent tcgen05 launch per processor call -- per CTA pair:
+ * Q-projection -> QK^T over the concatenated keys -> per-segment softmax with the branch weights folded in -> ONE PV
+ * contraction -> O to global memory; then, in the same launch, the pair's share of the out-projection tiles
+ * (Wo + bias), each tile starting as soon as the row block's head groups have announced their O rows on ws_sync.
+ * Without ws_sync (or S <= 128, a single row tile per sample) the out projection is a second tcgen05 GEMM launch.
+ * Same precondition on Wq / Wo / bo as pv_linear_fwd (weights, not outputs of the immediately preceding kernel).
  * Supported head dims: 40, 80, 160 (C = 320, 640, 1280 with H = 8); 1 <= Lt <= 80; 1 <= Li <= 16.                */
+int64_t pv_dual_attn_sync_words(int B, int S);
 int pv_dual_attn_fwd(pv_dtype dt, const void* X, const void* Wq, const void* Kp, const void* Vp, const void* Wo,
-                     const float* bo, void* Y, float* ws_q, void* ws_o, float* stats, int B, int S, int C, int H,
-                     int Lt, int Li, float w_text, float w_img, void* stream);
+                     const float* bo, void* Y, float* ws_q, void* ws_o, float* stats, unsigned int* ws_sync, int B, int S,
+                     int C, int H, int Lt, int Li, float w_text, float w_img, void* stream);
 
 /* The fused kernel alone (no out projection): PV_BF16: XorQ = X [B,S,C] bf16 and Wq is used (Q-projection fused);
  * PV_F32: XorQ = Q [B,S,C] fp32 (already projected) and Wq is ignored.  O:[B,S,C] (dt).  Used by the roofline

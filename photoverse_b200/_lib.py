@@ -30,7 +30,8 @@ _SIGNATURES = {
     "pv_linear_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 11 + [c_void_p]),
     "pv_kv_tile_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "pv_kv_pack_fwd": (c_int, [c_int] + [c_void_p] * 9 + [c_int] * 6 + [c_void_p]),
-    "pv_dual_attn_fwd": (c_int, [c_int] + [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p]),
+    "pv_dual_attn_sync_words": (c_int64, [c_int, c_int]),
+    "pv_dual_attn_fwd": (c_int, [c_int] + [c_void_p] * 11 + [c_int] * 6 + [c_float, c_float, c_void_p]),
     "pv_dual_attn_core_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int] * 6 + [c_float, c_float, c_void_p]),
     "pv_ln_lrelu_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     "pv_group_mean_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),

@@ -17,24 +17,20 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* D, bool out
 int gemm_f32(const float* A, const float* W, const float* bias, float* D, long long M, long long N, long long K,
              long long batch, long long lda, long long ldw, long long ldd, long long strideA, long long strideW,
              long long strideBias, long long strideD, cudaStream_t stream);
-int dual_attn_core_bf16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
-                        int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
-int dual_attn_core_bf16_ts(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
-                           int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
 int dual_attn_core_bf16_persistent(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
                                    int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                                    cudaStream_t stream);
 bool dual_attn_pair_roles_supported(int S, int C, int H);
+bool dual_attn_pair_roles_fused_supported(int S, int C, int H);
 int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
                                    int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
-                                   cudaStream_t stream);
-int dual_attn_core_bf16_pair16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
-                               int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
+                                   cudaStream_t stream, const void* Wo, const float* bo, void* Y, unsigned int* sync);
 int dual_attn_core_bf16_pair(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
-                             int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
+                             int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream,
+                             const void* Wo, const float* bo, void* Y, unsigned int* sync);
 int dual_attn_core_f32(const float* Q, const float* Kp, const float* Vp, float* O, float* stats, int B, int S, int C,
                        int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream);
-int64_t attn_kv_tile_bytes(int d);
+static int64_t attn_kv_tile_bytes(int d) { return static_cast<int64_t>(PV_KEYS_PAD) * ((d + 15) / 16 * 16) * 2; }
 int pack_weight(bool out_bf16, const float* W, const float* A, const float* Bm, float scaling, void* out, int out_f,
                 int in_f, int r, cudaStream_t stream);
 int kv_pack(bool bf16, const float* kv_text, const float* kv_img, void* Kp, void* Vp, float* v_ip_norm, int B, int Lt,
@@ -74,37 +70,48 @@ int dropout_bwd_acc(bool bf16, void* dst, const void* src, const uint8_t* mask, 
 
 // ---- globals ---------------------------------------------------------------------------------------
 std::atomic<unsigned long long> g_launches{0};
-int g_opt_epi_swizzle = 1;
-int g_opt_force_bn = 0;
-int g_opt_gemm_two_cta = 1;
+// Test / A-B switches (pv_set_option; process-wide, NOT thread-safe, never needed in production): every value selects
+// among correct kernels -- none changes results.
+int g_opt_epi_swizzle = 1;       // pv_gemm.cu: swizzled epilogue staging tile
+int g_opt_force_bn = 0;          // pv_gemm.cu: force the N tile (64/128/160/256) instead of the wave-count pick
+int g_opt_gemm_two_cta = 1;      // pv_gemm.cu: two resident CTAs per SM for short K
 int g_opt_pdl = 1;               // programmatic dependent launch for the persistent kernels
-int g_opt_gemm_persistent = 1;   // persistent CTA-pair GEMM (pv_gemm3.cu) for the out projection
-int g_opt_gemm_pair = 0;         // cta_group::2 CTA-pair GEMM (pv_gemm2.cu) for tall projections
-// 1: operands staged in smem (pv_attn.cu)   2: operands in TMEM, 2 CTAs/SM (pv_attn2.cu)
-// 3: persistent, projection / attention / softmax pipelined against each other (pv_attn3.cu)
-// 4: persistent CTA pairs (cta_group::2), B operands split across the pair (pv_attn4.cu); falls back to 3 when a sample
-//    has a single 128-row tile
-int g_opt_attn_variant = 6;
-int g_opt_bwd_mma = 1;            // bf16 attention backward on mma.sync tensor cores (0: fp32-accurate SIMT kernel)
-int g_opt_attn3_stages = 0;
-int g_opt_attn3_prefetch = 0;   // L2 prefetch distance (units) of the X tiles in the persistent attention kernel
-int g_opt_attn3_wstat = 1;      // C = 320: keep the CTA's Wq slice resident in shared memory (A/B switch)
-unsigned long long* g_attn3_trace = nullptr;   // debug timeline buffer (pv_debug_trace)
+int g_opt_gemm_persistent = 1;   // persistent CTA-pair GEMM (pv_gemm3.cu) for the out projection shapes
+int g_opt_fuse_out = 1;          // out projection as the second phase of the attention launch (0: separate GEMM launch)
+int g_opt_bwd_mma = 1;           // bf16 attention backward on tensor cores (0: fp32-accurate SIMT kernel)
+unsigned long long* g_attn3_trace = nullptr;   // debug timeline buffer (pv_debug_trace; kernels record only in -DPV_TRACE builds)
 int g_attn3_trace_cap = 0;
-int g_opt_attn3_dbg = 0;       // timing experiments on the persistent kernel (results are wrong when != 0)
+int g_opt_trace_block = 0;       // which leader CTA writes the debug timeline
 static thread_local std::string t_error;
 
 void set_error(const std::string& msg) { t_error = msg; }
 const char* last_error_cstr() { return t_error.c_str(); }
 
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+cudaError_t set_max_smem_once_impl(const void* kern, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> done;       // (kernel, device) -> bytes already granted
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t key = reinterpret_cast<uint64_t>(kern) * 131u + static_cast<uint64_t>(dev);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[key] = bytes;
+  return e;
 }
 
 // ---- TMA descriptor encoding (driver entry point fetched through the runtime: no link against libcuda) ----
@@ -178,21 +185,28 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0
 
 static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
+// Fused Q projection + dual-branch attention (+ out projection when Wo is given and the shape family supports the
+// single-launch form).  Shape families: S > 128: CTA-pair kernels (pv_attn6.cu for head_dim 40 at C = 320 and head_dim 80,
+// pv_attn4.cu otherwise); S <= 128 (a single 128-row tile per sample): the single-CTA persistent kernel of pv_attn3.cu.
+// Returns through *fused whether Y has been produced.
 static int attn_core_bf16(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
-                          int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t st) {
-  if (g_opt_attn_variant == 1) return dual_attn_core_bf16(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
-  if (g_opt_attn_variant == 6 && S > 128) {    // CTA pairs with decoupled roles (head_dim 40 at C = 320, head_dim 80), else variant 4
-    if (dual_attn_pair_roles_supported(S, C, H))
-      return dual_attn_core_bf16_pair_roles(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
-    return dual_attn_core_bf16_pair(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+                          int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t st,
+                          const void* Wo = nullptr, const float* bo = nullptr, void* Y = nullptr, unsigned int* sync = nullptr,
+                          bool* fused = nullptr) {
+  if (fused) *fused = false;
+  if (S > 128) {
+    const bool want = Wo != nullptr && sync != nullptr && g_opt_fuse_out != 0;
+    if (dual_attn_pair_roles_supported(S, C, H)) {
+      const bool f = want && dual_attn_pair_roles_fused_supported(S, C, H);
+      if (fused) *fused = f;
+      return dual_attn_core_bf16_pair_roles(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st,
+                                            f ? Wo : nullptr, bo, f ? Y : nullptr, f ? sync : nullptr);
+    }
+    if (fused) *fused = want;
+    return dual_attn_core_bf16_pair(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st, want ? Wo : nullptr, bo,
+                                    want ? Y : nullptr, want ? sync : nullptr);
   }
-  if (g_opt_attn_variant == 5 && S > 128)      // CTA pairs, key-split softmax groups (16 softmax warps)
-    return dual_attn_core_bf16_pair16(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
-  if (g_opt_attn_variant == 4 && S > 128)      // CTA pairs need two row tiles per sample
-    return dual_attn_core_bf16_pair(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
-  if (g_opt_attn_variant >= 3)
-    return dual_attn_core_bf16_persistent(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
-  return dual_attn_core_bf16_ts(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
+  return dual_attn_core_bf16_persistent(X, Wq, Kp, Vp, O, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
 }
 
 }  // namespace pv
@@ -210,22 +224,24 @@ int pv_set_option(const char* name, int value) {
   if (!strcmp(name, "epi_swizzle")) { g_opt_epi_swizzle = value; return PV_OK; }
   if (!strcmp(name, "force_bn")) { g_opt_force_bn = value; return PV_OK; }
   if (!strcmp(name, "gemm_two_cta")) { g_opt_gemm_two_cta = value; return PV_OK; }
-  if (!strcmp(name, "gemm_pair")) { g_opt_gemm_pair = value; return PV_OK; }
   if (!strcmp(name, "gemm_persistent")) { g_opt_gemm_persistent = value; return PV_OK; }
+  if (!strcmp(name, "fuse_out")) { g_opt_fuse_out = value; return PV_OK; }
   if (!strcmp(name, "pdl")) { g_opt_pdl = value; return PV_OK; }
-  if (!strcmp(name, "attn_variant")) { g_opt_attn_variant = value; return PV_OK; }
   if (!strcmp(name, "bwd_mma")) { g_opt_bwd_mma = value; return PV_OK; }
-  if (!strcmp(name, "attn3_dbg")) { g_opt_attn3_dbg = value; return PV_OK; }
-  if (!strcmp(name, "attn3_stages")) { g_opt_attn3_stages = value; return PV_OK; }
-  if (!strcmp(name, "attn3_wstat")) { g_opt_attn3_wstat = value; return PV_OK; }
-  if (!strcmp(name, "attn3_prefetch")) { g_opt_attn3_prefetch = value; return PV_OK; }
+  if (!strcmp(name, "trace_block")) { g_opt_trace_block = value; return PV_OK; }
   PV_FAIL(PV_ERR_INVALID, "unknown option '%s'", name);
 }
 
 int pv_debug_trace(void* buf, int capacity_events) {
+#ifdef PV_TRACE
   g_attn3_trace = static_cast<unsigned long long*>(buf);
   g_attn3_trace_cap = buf ? capacity_events : 0;
   return PV_OK;
+#else
+  (void)capacity_events;
+  if (buf == nullptr) return PV_OK;
+  PV_FAIL(PV_ERR_INVALID, "this build records no device timeline (rebuild with PV_TRACE=1 python -m photoverse_b200.build --force)");
+#endif
 }
 
 int pv_pack_weight(pv_dtype out_dt, const float* W, const float* lora_A, const float* lora_B, float scaling,
@@ -280,15 +296,21 @@ int pv_kv_pack_fwd(pv_dtype dt, const void* text, const void* img, const void* W
   return kv_pack(dt == PV_BF16, kv_text_ws, kv_img_ws, Kp, Vp, v_ip_norm, B, Lt, Li, C, H, st);
 }
 
+int64_t pv_dual_attn_sync_words(int B, int S) {
+  if (B <= 0 || S <= 0) return -1;
+  return 2ll * B * ((S + 255) / 256);
+}
+
 int pv_dual_attn_fwd(pv_dtype dt, const void* X, const void* Wq, const void* Kp, const void* Vp, const void* Wo,
-                     const float* bo, void* Y, float* ws_q, void* ws_o, float* stats, int B, int S, int C, int H,
-                     int Lt, int Li, float w_text, float w_img, void* stream) {
+                     const float* bo, void* Y, float* ws_q, void* ws_o, float* stats, unsigned int* ws_sync, int B, int S,
+                     int C, int H, int Lt, int Li, float w_text, float w_img, void* stream) {
   PV_REQUIRE(X && Wq && Kp && Vp && Wo && Y && ws_o, "null pointer");
   cudaStream_t st = as_stream(stream);
   int rc;
   if (dt == PV_BF16) {
-    rc = attn_core_bf16(X, Wq, Kp, Vp, ws_o, stats, B, S, C, H, Lt, Li, w_text, w_img, st);
-    if (rc) return rc;
+    bool fused = false;
+    rc = attn_core_bf16(X, Wq, Kp, Vp, ws_o, stats, B, S, C, H, Lt, Li, w_text, w_img, st, Wo, bo, Y, ws_sync, &fused);
+    if (rc || fused) return rc;
     return gemm_bf16(ws_o, Wo, bo, Y, false, (long long)B * S, C, C, 1, C, C, C, 0, 0, 0, 0, st);
   }
   PV_REQUIRE(ws_q != nullptr, "PV_F32 needs the ws_q scratch");

@@ -82,11 +82,8 @@ struct Attn3Params {
   int V;                   // units per head group = B * MT
   long long units;         // B * G * MT
   float w_text, w_img, scale_log2e;
-  int dbg_stages;
-  int prefetch;            // X tiles prefetched into L2 this many units ahead (0 = off)
   unsigned long long* trace;   // optional [1 + 3*n] event buffer (CTA 0 only): count, then (event, index, clock) triples
   int trace_cap;
-  int dbg;                 // timing experiments only (pv_set_option attn3_dbg): 1 no softmax math, 2 + no S load / O store, 3 + no Q conversion
 };
 
 template <int D, bool LT77, bool WSTAT>
@@ -172,38 +169,22 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
         }
         __syncwarp();
       }
-      // X tiles are read once, from HBM (~2100 cycles round trip): prefetch them into L2 `pf` units ahead so that the
-      // ring's loads are L2 hits and a short ring is enough
-      const int pf = p.prefetch;
-      auto prefetch_unit = [&](int u) {
-        if (u < u1 && elect_one()) {
-          const int b = u / p.MT;
-          const int mt = u - b * p.MT;
-          for (int kb = 0; kb < kblocks; ++kb) tma_prefetch_3d(&tmX, kb * A3_BK, mt * A3_BM, b);
-        }
-        __syncwarp();
-      };
-      for (int k = 0; k < pf; ++k) prefetch_unit(u0 + k);
       for (int u = u0; u < u1; ++u) {
         const int b = u / p.MT;
         const int mt = u - b * p.MT;
-        if (pf > 0) prefetch_unit(u + pf);
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % nst;
           const uint32_t ph = (it / nst) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           if (elect_one()) {
             uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-            // timing experiments: dbg 7 streams X only, dbg 8 Wq only (stale operands in the ring; wrong results)
-            const bool ld_x = !(p.dbg == 8 && it >= static_cast<uint32_t>(nst));
-            const bool ld_w = !WSTAT && !(p.dbg == 7 && it >= static_cast<uint32_t>(nst));
-            mbar_expect_tx(&full[s], (ld_x ? A3_A_BYTES : 0) + (ld_w ? A3_W_BYTES : 0));
-            if (ld_x) tma_load_3d(a_dst, &tmX, &full[s], kb * A3_BK, mt * A3_BM, b);
-            if (ld_w) tma_load_3d(a_dst + A3_A_BYTES, &tmWq, &full[s], kb * A3_BK, g * A3_BN, 0);
+            mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+            tma_load_3d(a_dst, &tmX, &full[s], kb * A3_BK, mt * A3_BM, b);
+            if constexpr (!WSTAT) tma_load_3d(a_dst + A3_A_BYTES, &tmWq, &full[s], kb * A3_BK, g * A3_BN, 0);
           }
           __syncwarp();
         }
-        if (b != prev_b && p.dbg < 4) {
+        if (b != prev_b) {
           // K / V^T tiles of this (sample, head group): needed only once the projection above has completed
           if (kv_gen > 0) mbar_wait(kv_free, (kv_gen - 1) & 1);
           if (elect_one()) {
@@ -241,19 +222,14 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
         tc_fence_after();
         a3_trace(tr, 12, kb);
         if (elect_one()) {
-          if (p.dbg >= 5) {                       // pure TMA streaming rate: consume the stage without MMAs
-            mbar_arrive(&empty[s]);
-            if (kb == kblocks - 1) mbar_arrive(&q_full[slot]);
-          } else {
           const uint8_t* a_src = smem + s * Cfg::STAGE_BYTES;
           const uint64_t da = umma_desc_sw128(a_src);
           const uint64_t dw = umma_desc_sw128(WSTAT ? smem + Cfg::OFF_W + kb * A3_W_BYTES : a_src + A3_A_BYTES);
 #pragma unroll
           for (int k = 0; k < A3_BK / 16; ++k)
-            if (p.dbg != 6 || k == 0) umma_bf16_ss(tmem + slot * A3_BN, da + 2 * k, dw + 2 * k, idesc_q, (kb | k) != 0);
+            umma_bf16_ss(tmem + slot * A3_BN, da + 2 * k, dw + 2 * k, idesc_q, (kb | k) != 0);
           umma_commit(&empty[s]);
           if (kb == kblocks - 1) umma_commit(&q_full[slot]);
-          }
         }
         __syncwarp();
         a3_trace(tr, 13, kb);
@@ -271,7 +247,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
     constexpr uint32_t idesc_s = umma_idesc_bf16(A3_BM, A3_KEYS);
     constexpr uint32_t idesc_o = umma_idesc_bf16(A3_BM, (D == 160) ? 80 : D_PAD);
     A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1);
-    const int nheads = (p.dbg >= 4) ? 0 : (u1 - u0) * HPC;
+    const int nheads = (u1 - u0) * HPC;
     int issued_qk = 0;
     uint32_t kv_gen = 0;
     int kv_b = -1;                  // sample whose K/V tiles (of this CTA's head group) are resident
@@ -406,7 +382,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (p.dbg < 2 && elect_one()) {
+        if (elect_one()) {
           tma_store_3d(&tmO, ost, po.c0 + h * 80, po.r0, po.b);
           bulk_commit();
         }
@@ -427,8 +403,7 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
       mbar_wait(&q_full[slot], (i >> 1) & 1);
       tc_fence_after();
       a3_trace(tr, 30 + 10 * wg, i);
-      if (p.dbg >= 3) {
-      } else if constexpr (D == 40) {
+      if constexpr (D == 40) {
         // group wg converts heads wg and wg + 2 : fp32 [40 j, 40 j + 40) -> bf16 [40 j + 16, 40 j + 40)
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
@@ -473,7 +448,6 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
         a3_trace(tr, 32 + 10 * wg, i);
       }
 
-      if (p.dbg >= 4) { mbar_arrive(&slot_free[slot]); continue; }
       const bool row_ok = (m0 + row) < p.S;
       bool had_head = false;
 
@@ -487,18 +461,13 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
         tc_fence_after();
         a3_trace(tr, 33 + 10 * wg, nn);
         uint32_t sr[A3_KEYS];                    // S row (fp32 bits), later the exponentials
-        if (p.dbg >= 2) {
-#pragma unroll
-          for (int k = 0; k < A3_KEYS; ++k) sr[k] = 0u;
-        } else {
-          tmem_ld32_raw(sbuf, sr);
-          tmem_ld32_raw(sbuf + 32, sr + 32);
-          tmem_ld32_raw(sbuf + 64, sr + 64);
-          tmem_ld_wait();
-        }
+        tmem_ld32_raw(sbuf, sr);
+        tmem_ld32_raw(sbuf + 32, sr + 32);
+        tmem_ld32_raw(sbuf + 64, sr + 64);
+        tmem_ld_wait();
         float fi = 1.f, oscale = 1.f;
         bool text_on = true;
-        if (p.dbg < 1) {
+        {
         // Key-slot validity.  LT77 (the CLIP context length, every PhotoVerse caller): the text mask is a compile-time
         // constant, so padding slots 77..79 cost nothing; otherwise it is a per-slot runtime select.  The 16 image
         // slots are always masked at run time (Li = 1..16).
@@ -636,10 +605,6 @@ dual_attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const _
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
-extern int g_opt_attn3_dbg;
-extern int g_opt_attn3_stages;
-extern int g_opt_attn3_wstat;
-extern int g_opt_attn3_prefetch;
 extern unsigned long long* g_attn3_trace;
 extern int g_attn3_trace_cap;
 
@@ -648,11 +613,7 @@ static int launch_attn3(const CUtensorMap& tmX, const CUtensorMap& tmWq, const C
                         cudaStream_t stream) {
   using Cfg = Attn3Cfg<D, WSTAT>;
   auto kern = dual_attn_fwd_persistent_kernel<D, LT77, WSTAT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES));
   const long long sms = sm_count();
   const int grid = static_cast<int>(p.units < sms ? p.units : sms);
   PV_CUDA(launch_pdl(kern, dim3(grid), dim3(A3_THREADS), Cfg::SMEM_BYTES, stream, tmX, tmWq, tmO, p));
@@ -687,15 +648,12 @@ int dual_attn_core_bf16_persistent(const void* X, const void* Wq, const void* Kp
   p.units = static_cast<long long>(B) * p.G * p.MT;
   PV_REQUIRE(p.units < (1ll << 30), "too many work units");
   p.w_text = w_text; p.w_img = w_img;
-  p.dbg = g_opt_attn3_dbg;
-  p.dbg_stages = g_opt_attn3_stages;
-  p.prefetch = g_opt_attn3_prefetch;
   p.trace = g_attn3_trace;
   p.trace_cap = g_attn3_trace_cap;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(d));
   switch (d) {
     case 40:
-      if (C == A3_KB_WSTAT * A3_BK && g_opt_attn3_wstat)
+      if (C == A3_KB_WSTAT * A3_BK)
         return Lt == 77 ? launch_attn3<40, true, true>(tmX, tmWq, tmO, p, stream) : launch_attn3<40, false, true>(tmX, tmWq, tmO, p, stream);
       return Lt == 77 ? launch_attn3<40, true, false>(tmX, tmWq, tmO, p, stream) : launch_attn3<40, false, false>(tmX, tmWq, tmO, p, stream);
     case 80: return Lt == 77 ? launch_attn3<80, true, false>(tmX, tmWq, tmO, p, stream) : launch_attn3<80, false, false>(tmX, tmWq, tmO, p, stream);

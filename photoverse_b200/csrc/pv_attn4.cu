@@ -14,6 +14,7 @@
 // mbarrier.arrive) on the leader's q_ready / p_ready / slot_free barriers.
 #include "pv_common.cuh"
 #include "pv_softmax.cuh"
+#include "pv_outproj.cuh"
 #include "pv_host.h"
 #include "../../include/photoverse_b200.h"
 
@@ -49,7 +50,11 @@ struct Attn4Cfg {
   static constexpr int OW = (D == 160) ? 80 : D;
   static constexpr int OST_WARP_BYTES = 32 * OW * 2;
   static constexpr int OFF_OST = OFF_KV + KV_BYTES;
-  static constexpr int OFF_BAR = OFF_OST + 8 * OST_WARP_BYTES;
+  // fused out projection (second phase of the same launch, pv_outproj.cuh): Wo streamed with the O tiles, 7-stage ring
+  using OP = OutProjCfg<0, 7>;
+  static constexpr int OFF_BAR_1 = OFF_OST + 8 * OST_WARP_BYTES;
+  static constexpr int OFF_BAR = ((OFF_BAR_1 > OP::BYTES ? OFF_BAR_1 : OP::BYTES) + 15) / 16 * 16;
+  static constexpr int OP_BAR_OFF = 320;                           // phase-2 barriers inside the 512-byte barrier block
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(STAGES <= A4_MAX_STAGES, "barrier array");
@@ -69,12 +74,17 @@ struct Attn4Params {
   float w_text, w_img, scale_log2e;
   unsigned long long* trace;   // debug timeline (leader CTA 0 only)
   int trace_cap;
+  // fused out projection (FUSE kernels only)
+  const float* bias;           // [C] or nullptr
+  unsigned int* sync;          // [2 * V] row-block counters, zero between launches (pv_outproj.cuh)
 };
 
-template <int D, bool LT77, bool WSTAT>
+template <int D, bool LT77, bool WSTAT, bool FUSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(A4_THREADS, 1)
 dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
-                          const __grid_constant__ CUtensorMap tmO, const Attn4Params p) {
+                          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmOa,
+                          const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmY,
+                          const Attn4Params p) {
   using Cfg = Attn4Cfg<D, WSTAT>;
   constexpr int HPC = Cfg::HPC;
   constexpr int D_PAD = Cfg::D_PAD;
@@ -115,6 +125,12 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWq);
     tma_prefetch_desc(&tmO);
+    if constexpr (FUSE) {
+      tma_prefetch_desc(&tmOa);
+      tma_prefetch_desc(&tmWo);
+      tma_prefetch_desc(&tmY);
+      op_mbar_init(reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR + Cfg::OP_BAR_OFF));
+    }
     for (int s = 0; s < A4_MAX_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -337,6 +353,8 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     }
     a3_trace_done_raw(p.trace, tr, 1);
   }
+  // the second phase runs every warp on the launch allocation again (blocks until the softmax warps have released theirs)
+  if constexpr (FUSE) { __syncwarp(); asm volatile("setmaxnreg.inc.sync.aligned.u32 168;"); }
   } else {
     // ===================== softmax groups (warps 4..7 and 8..11) of BOTH CTAs: one thread per query row =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
@@ -352,6 +370,7 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     if (q != 0) tr.base = nullptr;
     PendingO pend;
     pend.valid = false;
+    int sig_unit = -1;                 // FUSE: unit whose O stores of this warp are committed but not yet announced
 
     // O accumulator -> registers -> * row scale -> bf16 -> this warp's staging tile -> TMA store (clips rows >= S)
     uint8_t* ost = smem + Cfg::OFF_OST + ((warp - 4) * Cfg::OST_WARP_BYTES);
@@ -374,7 +393,18 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       tc_fence_after();
 #pragma unroll
       for (int h = 0; h < (D == 160 ? 2 : 1); ++h) {
-        if (elect_one()) bulk_wait_read<0>();          // the previous TMA store of this warp has read the tile
+        if (FUSE && h == 0 && sig_unit >= 0) {
+          // the stores of this warp's previous unit were committed a whole softmax ago: once they have COMPLETED (not
+          // merely read the staging tile) that unit's rows of O are in global memory -- announce it to the
+          // out-projection tiles
+          if (elect_one()) {
+            bulk_wait_all<0>();
+            op_signal_unit(p.sync, sig_unit);
+          }
+          sig_unit = -1;
+        } else {
+          if (elect_one()) bulk_wait_read<0>();          // the previous TMA store of this warp has read the tile
+        }
         __syncwarp();
         if constexpr (D == 40) {
           uint32_t a[32], c8[8];
@@ -401,6 +431,7 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         }
         __syncwarp();
       }
+      if (FUSE && po.last_of_unit) sig_unit = po.slot_unit;
     };
 
     // Q of unit iu: fp32 accumulator -> packed bf16, written inside the columns this group has just read
@@ -620,6 +651,8 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         pend.oscale = oscale;
         pend.parity = par;
         pend.slot = slot;
+        pend.last_of_unit = (j + 2 >= HPC);          // this group's last head of the unit
+        pend.slot_unit = u;
       }
       if (!had_head) {                                         // d = 160: the other group owns this unit's head
         arrive_leader(&slot_free[slot]);
@@ -630,11 +663,34 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       }
     }
     if (pend.valid) drain(pend);
-    if (elect_one()) bulk_wait_read<0>();
+    if (elect_one()) {
+      if (FUSE) {
+        bulk_wait_all<0>();
+        if (sig_unit >= 0) op_signal_unit(p.sync, sig_unit);
+      } else {
+        bulk_wait_read<0>();
+      }
+    }
     __syncwarp();
     a3_trace_done_raw(p.trace, tr, 2 + wg);
+    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 168;");
   }
 
+  if constexpr (FUSE) {
+    // ===================== second phase: the out-projection tiles of this pair's (head group, unit range) =====================
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    OutProjArgs oa;
+    oa.bias = p.bias;
+    oa.sync = p.sync;
+    oa.G = p.G; oa.MTP = p.MTP; oa.C = p.C; oa.V = p.V;
+    oa.u0 = u0; oa.u1 = u1; oa.g = g;
+    oa.ready_target = static_cast<unsigned int>((HPC >= 2 ? 16 : 8) * p.G);   // draining warps per unit: 4 per head group x 2 CTAs
+    outproj_phase<typename Cfg::OP>(smem, reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR + Cfg::OP_BAR_OFF), tmem, &tmOa, &tmWo,
+                                    &tmY, oa);
+  }
 
   tc_fence_before();
   __syncthreads();
@@ -643,42 +699,51 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   if (warp == 2) tmem_dealloc_2sm<512>(tmem);
 }
 
-extern int g_opt_attn3_wstat;
 extern unsigned long long* g_attn3_trace;
 extern int g_attn3_trace_cap;
 
-template <int D, bool LT77, bool WSTAT>
-static int launch_attn4(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const Attn4Params& p,
-                        long long unit_pairs, cudaStream_t stream) {
+template <int D, bool LT77, bool WSTAT, bool FUSE>
+static int launch_attn4(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const CUtensorMap& tmOa,
+                        const CUtensorMap& tmWo, const CUtensorMap& tmY, const Attn4Params& p, long long unit_pairs,
+                        cudaStream_t stream) {
   using Cfg = Attn4Cfg<D, WSTAT>;
-  auto kern = dual_attn_fwd_pair_kernel<D, LT77, WSTAT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  auto kern = dual_attn_fwd_pair_kernel<D, LT77, WSTAT, FUSE>;
+  PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES));
   const long long max_pairs = sm_count() / 2;
   const int npairs = static_cast<int>(unit_pairs < max_pairs ? unit_pairs : max_pairs);
-  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(A4_THREADS), Cfg::SMEM_BYTES, stream, tmX, tmWq, tmO, p));
+  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(A4_THREADS), Cfg::SMEM_BYTES, stream, tmX, tmWq, tmO, tmOa, tmWo, tmY, p));
   PV_LAUNCHED();
   return PV_OK;
 }
 
-// Same contract as dual_attn_core_bf16_persistent (pv_attn3.cu); requires at least two row tiles per sample.
+// Fused Q projection + dual-branch attention on CTA pairs; requires at least two row tiles per sample (S > 128).
+// Wo == nullptr: attention only.  Otherwise the whole processor call in ONE launch: Y = O Wo^T + bo as a second phase
+// (pv_outproj.cuh), O also left in global memory, `sync` = 2 * B * ceil(S / 256) zeroed counters (left zeroed).
 int dual_attn_core_bf16_pair(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats, int B,
-                             int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream) {
+                             int S, int C, int H, int Lt, int Li, float w_text, float w_img, cudaStream_t stream,
+                             const void* Wo, const float* bo, void* Y, unsigned int* sync) {
   PV_REQUIRE(B > 0 && S > 0 && H > 0 && C % H == 0, "bad shape B=%d S=%d C=%d H=%d", B, S, C, H);
   const int d = C / H;
   PV_REQUIRE(d == 40 || d == 80 || d == 160, "head_dim %d unsupported (40/80/160)", d);
   PV_REQUIRE(C % A4_BN == 0 && C % A4_BK == 0, "C=%d must be a multiple of 320", C);
   PV_REQUIRE(Lt >= 1 && Lt <= A4_IMG_OFF && Li >= 1 && Li <= A4_KEYS - A4_IMG_OFF,
              "need 1 <= Lt <= %d and 1 <= Li <= %d (Lt=%d Li=%d)", A4_IMG_OFF, A4_KEYS - A4_IMG_OFF, Lt, Li);
+  const bool fuse = Wo != nullptr;
+  PV_REQUIRE(!fuse || (Y != nullptr && sync != nullptr), "fused out projection needs Y and the sync workspace");
   PV_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wq) | reinterpret_cast<uintptr_t>(Kp) |
-              reinterpret_cast<uintptr_t>(Vp) | reinterpret_cast<uintptr_t>(O)) % 16 == 0, "pointers must be 16-byte aligned");
-  CUtensorMap tmX, tmWq, tmO;
+              reinterpret_cast<uintptr_t>(Vp) | reinterpret_cast<uintptr_t>(O) | reinterpret_cast<uintptr_t>(Wo) |
+              reinterpret_cast<uintptr_t>(Y)) % 16 == 0, "pointers must be 16-byte aligned");
+  CUtensorMap tmX, tmWq, tmO, tmOa, tmWo, tmY;
   if (make_tmap_3d(&tmX, X, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, A4_BK, A4_BM, 1, Swz::B128)) return PV_ERR_CUDA;
   if (make_tmap_3d(&tmWq, Wq, 2, C, C, 1, C * 2ull, static_cast<uint64_t>(C) * C * 2, A4_BK, A4_BN / 2, 1, Swz::B128)) return PV_ERR_CUDA;
   if (make_tmap_3d(&tmO, O, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, d == 160 ? 80 : d, 32, 1, Swz::None)) return PV_ERR_CUDA;
+  if (fuse) {
+    if (make_tmap_3d(&tmOa, O, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, OP_BK, 128, 1, Swz::B128)) return PV_ERR_CUDA;
+    if (make_tmap_3d(&tmWo, Wo, 2, C, C, 1, C * 2ull, static_cast<uint64_t>(C) * C * 2, OP_BK, OP_BN / 2, 1, Swz::B128)) return PV_ERR_CUDA;
+    if (make_tmap_3d(&tmY, Y, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, 80, 32, 1, Swz::None)) return PV_ERR_CUDA;
+  } else {
+    tmOa = tmO; tmWo = tmO; tmY = tmO;
+  }
   Attn4Params p;
   p.Kp = static_cast<const uint8_t*>(Kp);
   p.Vp = static_cast<const uint8_t*>(Vp);
@@ -694,20 +759,21 @@ int dual_attn_core_bf16_pair(const void* X, const void* Wq, const void* Kp, cons
   p.trace = g_attn3_trace;
   p.trace_cap = g_attn3_trace_cap;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(d));
+  p.bias = bo;
+  p.sync = sync;
+#define PV_A4_LAUNCH(DD, LT, WS, FU) launch_attn4<DD, LT, WS, FU>(tmX, tmWq, tmO, tmOa, tmWo, tmY, p, unit_pairs, stream)
+#define PV_A4_LT(DD, WS, FU) (Lt == 77 ? PV_A4_LAUNCH(DD, true, WS, FU) : PV_A4_LAUNCH(DD, false, WS, FU))
   switch (d) {
     case 40:
-      if (C == A4_KB_WSTAT * A4_BK && g_opt_attn3_wstat)
-        return Lt == 77 ? launch_attn4<40, true, true>(tmX, tmWq, tmO, p, unit_pairs, stream)
-                        : launch_attn4<40, false, true>(tmX, tmWq, tmO, p, unit_pairs, stream);
-      return Lt == 77 ? launch_attn4<40, true, false>(tmX, tmWq, tmO, p, unit_pairs, stream)
-                      : launch_attn4<40, false, false>(tmX, tmWq, tmO, p, unit_pairs, stream);
+      if (C == A4_KB_WSTAT * A4_BK) return fuse ? PV_A4_LT(40, true, true) : PV_A4_LT(40, true, false);
+      return fuse ? PV_A4_LT(40, false, true) : PV_A4_LT(40, false, false);
     case 80:
-      return Lt == 77 ? launch_attn4<80, true, false>(tmX, tmWq, tmO, p, unit_pairs, stream)
-                      : launch_attn4<80, false, false>(tmX, tmWq, tmO, p, unit_pairs, stream);
+      return fuse ? PV_A4_LT(80, false, true) : PV_A4_LT(80, false, false);
     default:
-      return Lt == 77 ? launch_attn4<160, true, false>(tmX, tmWq, tmO, p, unit_pairs, stream)
-                      : launch_attn4<160, false, false>(tmX, tmWq, tmO, p, unit_pairs, stream);
+      return fuse ? PV_A4_LT(160, false, true) : PV_A4_LT(160, false, false);
   }
+#undef PV_A4_LT
+#undef PV_A4_LAUNCH
 }
 
 }  // namespace pv

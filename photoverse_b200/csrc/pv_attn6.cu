@@ -19,6 +19,7 @@
 // softmax arithmetic are those of pv_attn4.cu.
 #include "pv_common.cuh"
 #include "pv_softmax.cuh"
+#include "pv_outproj.cuh"
 #include "pv_host.h"
 #include "../../include/photoverse_b200.h"
 
@@ -58,7 +59,12 @@ struct Attn6Cfg {
   static constexpr int OFF_OST = OFF_KV + KV_BYTES;                 // [epilogue warp][group] slabs
   static constexpr int OFF_P = OFF_OST + 4 * 2 * OST_BYTES;
   static constexpr int OFF_OSC = OFF_P + 2 * A6_P_BYTES;            // O row scales [group][parity][128] fp32
-  static constexpr int OFF_BAR = OFF_OSC + 2 * 2 * A6_BM * 4;
+  // fused out projection (second phase of the same launch): C = 320 keeps its Wo half resident next to an 8-stage ring
+  // of O tiles, C = 640 next to a 5-stage ring
+  using OP = OutProjCfg<WSTAT ? 5 : 10, WSTAT ? 8 : 5>;
+  static constexpr int OFF_BAR_1 = OFF_OSC + 2 * 2 * A6_BM * 4;
+  static constexpr int OFF_BAR = ((OFF_BAR_1 > OP::BYTES ? OFF_BAR_1 : OP::BYTES) + 15) / 16 * 16;
+  static constexpr int OP_BAR_OFF = 320;                            // phase-2 barriers inside the 512-byte barrier block
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   // TMEM: packed bf16 Q of head j / O accumulator of softmax group w inside a 160-column slot
@@ -76,13 +82,18 @@ struct Attn6Params {
   float w_text, w_img, scale_log2e;
   unsigned long long* trace;
   int trace_cap;
-  int trace_block;         // which (leader) CTA writes the debug timeline (pv_set_option attn3_dbg; default 0)
+  int trace_block;         // which (leader) CTA writes the debug timeline
+  // fused out projection (FUSE kernels only)
+  const float* bias;       // [C] or nullptr
+  unsigned int* sync;      // [2 * V] row-block counters, zero between launches (pv_outproj.cuh)
 };
 
-template <int D, bool LT77>
+template <int D, bool LT77, bool FUSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(A6_THREADS, 1)
 dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWq,
-                                const __grid_constant__ CUtensorMap tmO, const Attn6Params p) {
+                                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmOa,
+                                const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmY,
+                                const Attn6Params p) {
   using Cfg = Attn6Cfg<D>;
   constexpr int A6_HPC = Cfg::HPC;
   constexpr int A6_DPAD = Cfg::DPAD;
@@ -134,6 +145,12 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWq);
     tma_prefetch_desc(&tmO);
+    if constexpr (FUSE) {
+      tma_prefetch_desc(&tmOa);
+      tma_prefetch_desc(&tmWo);
+      tma_prefetch_desc(&tmY);
+      op_mbar_init(reinterpret_cast<uint64_t*>(smem + A6_OFF_BAR + Cfg::OP_BAR_OFF));
+    }
     for (int s = 0; s < A6_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -351,6 +368,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         }
       }
     }
+    // the second phase runs every warp on the launch allocation again (blocks until the softmax warps have released theirs)
+    if constexpr (FUSE) { __syncwarp(); asm volatile("setmaxnreg.inc.sync.aligned.u32 128;"); }
   } else if (warp < 12) {
     // ===================== softmax groups (warps 4..7 and 8..11) of BOTH CTAs: one thread per query row =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
@@ -546,6 +565,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       }
     }
     a3_trace_done_raw(p.trace, tr, 2 + wg);
+    if constexpr (FUSE) { __syncwarp(); asm volatile("setmaxnreg.dec.sync.aligned.u32 128;"); }
   } else {
     // ===================== epilogue warps 12..15 of BOTH CTAs: Q conversion + O drain for lane quarter q =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -554,6 +574,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     uint8_t* ost = smem + A6_OFF_OST + q * (2 * A6_OST_BYTES);
     const uint32_t osc_a = smem_u32(smem + A6_OFF_OSC) + (q * 32 + lane) * 4;
     int converted = 0, drained = 0;
+    int signalled = 0;                               // FUSE: units [0, signalled) announced on the row-block counters
     int kv_end_d = 0;                                // sample tracking for the drain stream
     int b_d = u0 / p.MTP - 1;
     int m0_d = 0;
@@ -646,6 +667,19 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       if (elect_one()) {
         tma_store_3d(&tmO, slab, g * A6_BN + j * A6_D, m0_d + q * 32, b_d);
         bulk_commit();
+        if constexpr (FUSE) {
+          // store groups [0, nn - 2] cover units [0, (nn - 1) / HPC): once they have completed their rows of O are in
+          // global memory -- announce them to the out-projection tiles (two stores of slack: the wait is almost free)
+          const int done_units = (nn >= 1) ? (nn - 1) / A6_HPC : 0;
+          if (done_units > signalled) {
+            bulk_wait_all<2>();
+            for (int k = signalled; k < done_units; ++k) op_signal_unit(p.sync, u0 + k);
+          }
+        }
+      }
+      if constexpr (FUSE) {
+        const int done_units = (nn >= 1) ? (nn - 1) / A6_HPC : 0;
+        if (done_units > signalled) signalled = done_units;
       }
       __syncwarp();
     };
@@ -669,8 +703,34 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         ++drained;
       }
     }
-    if (elect_one()) bulk_wait_read<0>();
+    if (elect_one()) {
+      if constexpr (FUSE) {
+        bulk_wait_all<0>();
+        for (int k = signalled; k < nunits; ++k) op_signal_unit(p.sync, u0 + k);
+      } else {
+        bulk_wait_read<0>();
+      }
+    }
     __syncwarp();
+    if constexpr (FUSE) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+  }
+
+  if constexpr (FUSE) {
+    // ===================== second phase: the out-projection tiles of this pair's (head group, unit range) =====================
+    // Every MMA of the attention phase has completed (the epilogue warps drained the last accumulator), every TMA store
+    // has read its staging slab: shared memory and tensor memory are free in both CTAs after this barrier.
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    OutProjArgs oa;
+    oa.bias = p.bias;
+    oa.sync = p.sync;
+    oa.G = p.G; oa.MTP = p.MTP; oa.C = p.C; oa.V = p.V;
+    oa.u0 = u0; oa.u1 = u1; oa.g = g;
+    oa.ready_target = static_cast<unsigned int>(8 * p.G);        // 4 epilogue warps x 2 CTAs announce every unit
+    outproj_phase<typename Cfg::OP>(smem, reinterpret_cast<uint64_t*>(smem + A6_OFF_BAR + Cfg::OP_BAR_OFF), tmem, &tmOa, &tmWo,
+                                    &tmY, oa);
   }
 
   tc_fence_before();
@@ -682,20 +742,18 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
 
 extern unsigned long long* g_attn3_trace;
 extern int g_attn3_trace_cap;
-extern int g_opt_attn3_dbg;
+extern int g_opt_trace_block;
 
-template <int D, bool LT77>
-static int launch_attn6(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const Attn6Params& p,
-                        long long unit_pairs, cudaStream_t stream) {
-  auto kern = dual_attn_fwd_pair_roles_kernel<D, LT77>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn6Cfg<D>::SMEM_BYTES));
-    attr_done = true;
-  }
+template <int D, bool LT77, bool FUSE>
+static int launch_attn6(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const CUtensorMap& tmOa,
+                        const CUtensorMap& tmWo, const CUtensorMap& tmY, const Attn6Params& p, long long unit_pairs,
+                        cudaStream_t stream) {
+  auto kern = dual_attn_fwd_pair_roles_kernel<D, LT77, FUSE>;
+  PV_CUDA(set_max_smem_once(kern, Attn6Cfg<D>::SMEM_BYTES));
   const long long max_pairs = sm_count() / 2;
   const int npairs = static_cast<int>(unit_pairs < max_pairs ? unit_pairs : max_pairs);
-  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(A6_THREADS), Attn6Cfg<D>::SMEM_BYTES, stream, tmX, tmWq, tmO, p));
+  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(A6_THREADS), Attn6Cfg<D>::SMEM_BYTES, stream, tmX, tmWq, tmO, tmOa, tmWo,
+                     tmY, p));
   PV_LAUNCHED();
   return PV_OK;
 }
@@ -707,21 +765,39 @@ bool dual_attn_pair_roles_supported(int S, int C, int H) {
   const int d = C / H;
   return (d == 40 && C == Attn6Cfg<40>::KB_RES * A6_BK) || d == 80;
 }
+// ... and the out projection as a second phase of the same launch (pv_outproj.cuh): C = 320 / 640 (resident Wo halves)
+bool dual_attn_pair_roles_fused_supported(int S, int C, int H) {
+  return dual_attn_pair_roles_supported(S, C, H) && (C == 320 || C == 640);
+}
 
+// Wo == nullptr: attention only, O = result.  Otherwise the whole processor call in ONE launch:
+// Y = O Wo^T + bo, with O also left in global memory (saved for the backward pass) and `sync` = 2 * B * ceil(S / 256)
+// zero-initialised counters that the kernel leaves zeroed.
 int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp, const void* Vp, void* O, float* stats,
                                    int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
-                                   cudaStream_t stream) {
+                                   cudaStream_t stream, const void* Wo, const float* bo, void* Y, unsigned int* sync) {
   PV_REQUIRE(B > 0 && dual_attn_pair_roles_supported(S, C, H), "needs head_dim 40 with C=320 or head_dim 80, S>128 (B=%d S=%d C=%d H=%d)",
              B, S, C, H);
+  const bool fuse = Wo != nullptr;
+  PV_REQUIRE(!fuse || (dual_attn_pair_roles_fused_supported(S, C, H) && Y != nullptr && sync != nullptr),
+             "fused out projection needs C = 320 or 640, Y and the sync workspace");
   const int d = C / H;
   PV_REQUIRE(Lt >= 1 && Lt <= A6_IMG_OFF && Li >= 1 && Li <= A6_KEYS - A6_IMG_OFF,
              "need 1 <= Lt <= %d and 1 <= Li <= %d (Lt=%d Li=%d)", A6_IMG_OFF, A6_KEYS - A6_IMG_OFF, Lt, Li);
   PV_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wq) | reinterpret_cast<uintptr_t>(Kp) |
-              reinterpret_cast<uintptr_t>(Vp) | reinterpret_cast<uintptr_t>(O)) % 16 == 0, "pointers must be 16-byte aligned");
-  CUtensorMap tmX, tmWq, tmO;
+              reinterpret_cast<uintptr_t>(Vp) | reinterpret_cast<uintptr_t>(O) | reinterpret_cast<uintptr_t>(Wo) |
+              reinterpret_cast<uintptr_t>(Y)) % 16 == 0, "pointers must be 16-byte aligned");
+  CUtensorMap tmX, tmWq, tmO, tmOa, tmWo, tmY;
   if (make_tmap_3d(&tmX, X, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, A6_BK, A6_BM, 1, Swz::B128)) return PV_ERR_CUDA;
   if (make_tmap_3d(&tmWq, Wq, 2, C, C, 1, C * 2ull, static_cast<uint64_t>(C) * C * 2, A6_BK, A6_BN / 2, 1, Swz::B128)) return PV_ERR_CUDA;
   if (make_tmap_3d(&tmO, O, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, d, 32, 1, Swz::None)) return PV_ERR_CUDA;
+  if (fuse) {
+    if (make_tmap_3d(&tmOa, O, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, OP_BK, 128, 1, Swz::B128)) return PV_ERR_CUDA;
+    if (make_tmap_3d(&tmWo, Wo, 2, C, C, 1, C * 2ull, static_cast<uint64_t>(C) * C * 2, OP_BK, OP_BN / 2, 1, Swz::B128)) return PV_ERR_CUDA;
+    if (make_tmap_3d(&tmY, Y, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, 80, 32, 1, Swz::None)) return PV_ERR_CUDA;
+  } else {
+    tmOa = tmO; tmWo = tmO; tmY = tmO;
+  }
   Attn6Params p;
   p.Kp = static_cast<const uint8_t*>(Kp);
   p.Vp = static_cast<const uint8_t*>(Vp);
@@ -736,13 +812,18 @@ int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp
   p.w_text = w_text; p.w_img = w_img;
   p.trace = g_attn3_trace;
   p.trace_cap = g_attn3_trace_cap;
-  p.trace_block = g_opt_attn3_dbg;
+  p.trace_block = g_opt_trace_block;
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(d));
-  if (d == 40)
-    return Lt == 77 ? launch_attn6<40, true>(tmX, tmWq, tmO, p, unit_pairs, stream)
-                    : launch_attn6<40, false>(tmX, tmWq, tmO, p, unit_pairs, stream);
-  return Lt == 77 ? launch_attn6<80, true>(tmX, tmWq, tmO, p, unit_pairs, stream)
-                  : launch_attn6<80, false>(tmX, tmWq, tmO, p, unit_pairs, stream);
+  p.bias = bo;
+  p.sync = sync;
+#define PV_A6_LAUNCH(DD, LT, FU) launch_attn6<DD, LT, FU>(tmX, tmWq, tmO, tmOa, tmWo, tmY, p, unit_pairs, stream)
+  if (d == 40) {
+    if (fuse) return Lt == 77 ? PV_A6_LAUNCH(40, true, true) : PV_A6_LAUNCH(40, false, true);
+    return Lt == 77 ? PV_A6_LAUNCH(40, true, false) : PV_A6_LAUNCH(40, false, false);
+  }
+  if (fuse) return Lt == 77 ? PV_A6_LAUNCH(80, true, true) : PV_A6_LAUNCH(80, false, true);
+  return Lt == 77 ? PV_A6_LAUNCH(80, true, false) : PV_A6_LAUNCH(80, false, false);
+#undef PV_A6_LAUNCH
 }
 
 }  // namespace pv

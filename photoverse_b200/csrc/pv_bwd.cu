@@ -555,11 +555,7 @@ static int launch_attn_bwd(const void* dO, const void* Q, const float* kv_text, 
                            cudaStream_t stream) {
   auto kern = attn_bwd_kernel<D, T>;
   const size_t smem = (2 * PV_KEYS_PAD * (D + 1) + 2 * AB_TQ * (D + 1) + 2 * AB_TQ * AB_LP) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_done = true;
-  }
+  PV_CUDA(set_max_smem_once(kern, static_cast<int>(smem)));
   dim3 grid(attn_bwd_chunks(S), H, B);
   const float scale = 1.f / sqrtf(static_cast<float>(D));
   kern<<<grid, 256, smem, stream>>>(static_cast<const T*>(dO), static_cast<const T*>(Q), kv_text, kv_img, stats,

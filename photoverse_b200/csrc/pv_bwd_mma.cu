@@ -269,11 +269,7 @@ static int launch_attn_bwd_mma(const void* dO, const void* Q, const float* kv_te
                                void* dQ, float* part, int nchunk, int B, int S, int C, int H, int Lt, int Li, float w_text,
                                float w_img, cudaStream_t stream) {
   auto kern = attn_bwd_mma_kernel<D>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdMmaCfg<D>::SMEM_BYTES));
-    attr_done = true;
-  }
+  PV_CUDA(set_max_smem_once(kern, BwdMmaCfg<D>::SMEM_BYTES));
   dim3 grid(nchunk, H, B);
   const float scale = 1.f / sqrtf(static_cast<float>(D));
   kern<<<grid, 256, BwdMmaCfg<D>::SMEM_BYTES, stream>>>(static_cast<const __nv_bfloat16*>(dO), static_cast<const __nv_bfloat16*>(Q),

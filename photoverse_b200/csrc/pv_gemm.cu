@@ -190,11 +190,7 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUte
                       long long strideBias, int M, int N, int K, int batch, int w_batched, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, STAGES_>;
   auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES_, OUT_F32, EPI_SWZ>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES));
   dim3 grid((N + BN - 1) / BN, (M + GEMM_BM - 1) / GEMM_BM, batch);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmW, tmD, bias, strideBias, N, K, w_batched);
   PV_LAUNCHED();
@@ -202,13 +198,9 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUte
 }
 
 extern int g_opt_gemm_two_cta;
-extern int g_opt_gemm_pair;
 extern int g_opt_gemm_persistent;
 int gemm3_bf16(const void* A, const void* W, const float* bias, void* D, long long M, long long N, long long K, long long lda,
                long long ldw, long long ldd, cudaStream_t stream);
-int gemm2_bf16(const void* A, const void* W, const float* bias, void* D, bool out_f32, long long M, long long N, long long K,
-               long long batch, long long lda, long long ldw, long long ldd, long long strideA, long long strideW,
-               long long strideBias, long long strideD, cudaStream_t stream);
 
 template <int BN>
 static int launch_bn(bool out_f32, bool swz, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD,
@@ -262,9 +254,6 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* D, bool out
   // persistent CTA-pair kernel (pv_gemm3.cu): the out projection shapes (bf16 out, N % 160 == 0, K % 64 == 0, tall M)
   if (g_opt_gemm_persistent != 0 && g_opt_force_bn == 0 && !out_f32 && batch == 1 && M >= 512 && N % 160 == 0 && K % 64 == 0)
     return gemm3_bf16(A, W, bias, D, M, N, K, lda, ldw, ldd, stream);
-  // CTA-pair (cta_group::2) kernel for the tall projections of the path: M >= 2048 rows, N a multiple of 32
-  if (g_opt_gemm_pair != 0 && g_opt_force_bn == 0 && M >= 2048 && N >= 160 && N % 32 == 0)
-    return gemm2_bf16(A, W, bias, D, out_f32, M, N, K, batch, lda, ldw, ldd, strideA, strideW, strideBias, strideD, stream);
   const bool two_cta = g_opt_gemm_two_cta != 0 && (K + GEMM_BK - 1) / GEMM_BK <= 8;
   const int bn = pick_bn(M, N, batch, two_cta);
   const bool swz = g_opt_epi_swizzle != 0 || out_f32 || two_cta;

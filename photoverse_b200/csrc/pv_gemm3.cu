@@ -219,11 +219,7 @@ static int launch_g3(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUten
                      int K, cudaStream_t stream) {
   using Cfg = Gemm3Cfg<KB_RES>;
   auto kern = gemm3_pair_persistent_kernel<KB_RES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES));
   const long long units = static_cast<long long>(G) * V;
   const long long max_pairs = sm_count() / 2;
   const int npairs = static_cast<int>(units < max_pairs ? units : max_pairs);

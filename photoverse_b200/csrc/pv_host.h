@@ -54,7 +54,11 @@ enum class Swz { None, B64, B128 };
 int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
                  uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, Swz swz);
 
-int sm_count();
+int sm_count();                       // SM count of the CURRENT device (cached per device)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set once per (kernel, device)
+cudaError_t set_max_smem_once_impl(const void* kern, int bytes);
+template <typename K>
+cudaError_t set_max_smem_once(K kern, int bytes) { return set_max_smem_once_impl(reinterpret_cast<const void*>(kern), bytes); }
 
 extern int g_opt_pdl;
 // Launch with programmatic stream serialisation (PDL) when enabled: the kernel must call pdl_wait() before touching any

@@ -18,7 +18,8 @@ struct PendingO {
   int c0, r0, b;           // TMA store coordinates: first channel, first row of this warp's 32-row slab, sample
   int slot;
   bool valid;
-  bool last_of_unit;       // (pv_attn5 PSMEM) draining it releases the unit's Q slot
+  bool last_of_unit;       // the draining group's last head of its unit (fused out projection: announce the unit)
+  int slot_unit;           // global unit index (row-block counter) of that unit
 };
 
 
@@ -75,12 +76,14 @@ __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 
-// Debug timeline: lane 0 of a role warp of CTA 0 appends (event, index, SM clock) to the role's private region of the
-// trace buffer (no atomics: the stores are fire-and-forget).  Off (trace == nullptr) in production.
+// Debug timeline (-DPV_TRACE builds only): lane 0 of a role warp of one CTA appends (event, index, SM clock) to the
+// role's private region of the trace buffer (no atomics: the stores are fire-and-forget).  Release builds compile the
+// calls away.
 struct A3Trace {
   unsigned long long* base;
   int n, cap;
 };
+#ifdef PV_TRACE
 __device__ __forceinline__ A3Trace a3_trace_init_raw(unsigned long long* trace, int trace_cap, int role, int block = 0) {
   A3Trace t;
   const int per = trace_cap / 4;
@@ -100,5 +103,10 @@ __device__ __forceinline__ void a3_trace(A3Trace& t, int ev, int idx) {
 __device__ __forceinline__ void a3_trace_done_raw(unsigned long long* trace, const A3Trace& t, int role) {
   if (t.base != nullptr) trace[role] = static_cast<unsigned long long>(t.n);
 }
+#else
+__device__ __forceinline__ A3Trace a3_trace_init_raw(unsigned long long*, int, int, int = 0) { return A3Trace{nullptr, 0, 0}; }
+__device__ __forceinline__ void a3_trace(A3Trace&, int, int) {}
+__device__ __forceinline__ void a3_trace_done_raw(unsigned long long*, const A3Trace&, int) {}
+#endif
 
 }  // namespace pv

@@ -135,11 +135,27 @@ def kv_pack(text: torch.Tensor, img: torch.Tensor, wkv_text: torch.Tensor, wkv_i
     return kv
 
 
+_SYNC = {}
+
+
+def _sync_words(B: int, S: int, device) -> torch.Tensor:
+    """Zeroed uint32 row-block counters of the single-launch processor kernel (include/photoverse_b200.h: ws_sync).
+    One grow-only buffer per (device, stream): the kernel leaves it zeroed, calls on one stream are ordered."""
+    need = int(_lib.lib().pv_dual_attn_sync_words(B, S))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _SYNC.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros(max(need, 1 << 16), device=device, dtype=torch.int32)
+        _SYNC[key] = buf
+    return buf
+
+
 def dual_attn(x: torch.Tensor, wq: torch.Tensor, kv: PackedKV, wo: torch.Tensor, bo: torch.Tensor,
               w_text: float = 1.0, w_img: float = 1.0, want_stats: bool = False):
     """Y = (w_t softmax(QK_t^T/sqrt d) V_t + w_i softmax(QK_i^T/sqrt d) V_i) Wo^T + bo with Q = x Wq^T.
     Returns (Y, O, stats|None, Q|None); O (pre-out-projection) and Q (fp32 mode only) are kept for backward."""
     B, S, C = x.shape
+    sync = _sync_words(B, S, x.device) if x.dtype == torch.bfloat16 else None
     assert x.is_contiguous() and wq.is_contiguous() and wo.is_contiguous()
     assert x.dtype == wq.dtype == wo.dtype == kv.dtype and bo.dtype == torch.float32
     assert (kv.B, kv.C) == (B, C)
@@ -148,7 +164,7 @@ def dual_attn(x: torch.Tensor, wq: torch.Tensor, kv: PackedKV, wo: torch.Tensor,
     q = torch.empty(B, S, C, device=x.device, dtype=torch.float32) if x.dtype == torch.float32 else None
     stats = torch.empty(B, kv.H, S, 4, device=x.device, dtype=torch.float32) if want_stats else None
     check(_lib.lib().pv_dual_attn_fwd(_dt(x), _ptr(x), _ptr(wq), _ptr(kv.Kp), _ptr(kv.Vp), _ptr(wo), _ptr(bo),
-                                      _ptr(y), _ptr(q), _ptr(o), _ptr(stats), B, S, C, kv.H, kv.Lt, kv.Li,
+                                      _ptr(y), _ptr(q), _ptr(o), _ptr(stats), _ptr(sync), B, S, C, kv.H, kv.Lt, kv.Li,
                                       float(w_text), float(w_img), _stream()), "pv_dual_attn_fwd")
     return y, o, stats, q
 

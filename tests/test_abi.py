@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     l = ctypes.CDLL(_lib.LIB_PATH)
     missing = [s for s in declared_symbols() if not hasattr(l, s)]
     assert not missing, f"declared in the header but not exported: {missing}"
-    assert _lib.lib().pv_version() == 1
+    assert _lib.lib().pv_version() == 2
 
 
 def test_python_binding_covers_the_header():

@@ -12,8 +12,6 @@ from tests.helpers import build_product_layer, force_fusion_seed, golden
 
 pytestmark = pytest.mark.gpu
 
-DEFAULT_ATTN_VARIANT = 6          # g_opt_attn_variant in csrc/pv_api.cu
-
 TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
 
 
@@ -47,15 +45,14 @@ def test_linear_bf16(cuda_device, M, N, K, bn, out_f32, swz):
     assert _lib_loaded()
 
 
-@pytest.mark.parametrize("kernel", ["single-cta", "cta-pair", "persistent-pair"])
+@pytest.mark.parametrize("kernel", ["single-cta", "persistent-pair"])
 @pytest.mark.parametrize("out_f32", [False, True])
 @pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (2500, 640, 640), (2048, 1280, 1280), (8192, 768, 1024), (3000, 1024, 1024)])
 def test_linear_bf16_tall(cuda_device, M, N, K, out_f32, kernel):
-    """Tall projections (out projection / adapter layers) through each GEMM kernel: single-CTA (pv_gemm.cu), CTA pair
-    (pv_gemm2.cu) and the persistent CTA-pair kernel used for the out projection (pv_gemm3.cu; bf16 out, N % 160 == 0 --
-    other shapes fall through to the default kernel)."""
+    """Tall projections (out projection / adapter layers) through both GEMM kernels: single-CTA (pv_gemm.cu) and the
+    persistent CTA-pair kernel used for out-projection shapes (pv_gemm3.cu; bf16 out, N % 160 == 0 -- other shapes fall
+    through to the default kernel)."""
     from photoverse_b200 import _lib, ops
-    _lib.set_option("gemm_pair", int(kernel == "cta-pair"))
     _lib.set_option("gemm_persistent", int(kernel == "persistent-pair"))
     try:
         g = torch.Generator().manual_seed(M + N)
@@ -68,7 +65,6 @@ def test_linear_bf16_tall(cuda_device, M, N, K, out_f32, kernel):
         tol = 2e-5 * K ** 0.5 + (0 if out_f32 else 4e-3 * ref.abs().max().item())
         assert err <= tol, f"max err {err} > {tol}"
     finally:
-        _lib.set_option("gemm_pair", 0)
         _lib.set_option("gemm_persistent", 1)
 
 
@@ -230,44 +226,54 @@ def test_kv_cache_reuses_projection(cuda_device):
         n1 = _lib.launch_count()
         proc.enable_kv_cache(False)
     assert torch.equal(y0, y1) and torch.equal(y1, y2)
-    assert n1 - n0 == 2, f"cached call should launch attention + out-proj only, launched {n1 - n0}"
+    assert n1 - n0 == 1, f"a cached bf16 call is ONE launch (attention + out projection fused), launched {n1 - n0}"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6],
-                         ids=["smem-operands", "tmem-operands", "persistent", "cta-pair", "cta-pair16", "cta-pair-roles"])
-@pytest.mark.parametrize("S,C,Li,wt,wi", [(384, 320, 5, 1.0, 1.0), (200, 640, 16, 1.0, 1.0), (128, 1280, 1, 1.0, 1.0),
-                                          (256, 320, 3, 2.0, 0.0), (256, 640, 5, 0.0, 2.0), (4096, 320, 5, 1.0, 1.0),
-                                          (1024, 640, 4, 1.0, 1.0), (300, 1280, 5, 1.0, 1.0)])
-def test_attention_kernel_variants(cuda_device, variant, S, C, Li, wt, wi):
-    """Both fused-kernel variants (A operands staged in shared memory / kept in tensor memory) vs the oracle."""
-    from photoverse_b200 import _lib
-    case = cases.ProcCase(f"var_{S}_{C}", B=2, S=S, C=C, Li=Li, seed=60 + Li, w_text=wt, w_img=wi)
-    _lib.set_option("attn_variant", variant)
+@pytest.mark.parametrize("fuse", [1, 0], ids=["one-launch", "attention+gemm"])
+@pytest.mark.parametrize("B,S,C,Li,wt,wi", [(2, 384, 320, 5, 1.0, 1.0), (2, 200, 640, 16, 1.0, 1.0), (2, 128, 1280, 1, 1.0, 1.0),
+                                            (2, 256, 320, 3, 2.0, 0.0), (2, 256, 640, 5, 0.0, 2.0), (2, 4096, 320, 5, 1.0, 1.0),
+                                            (2, 1024, 640, 4, 1.0, 1.0), (2, 300, 1280, 5, 1.0, 1.0), (3, 576, 1280, 4, 1.0, 1.0),
+                                            (16, 4096, 320, 1, 1.0, 1.0), (16, 1024, 640, 1, 1.0, 1.0), (16, 256, 1280, 1, 1.0, 1.0),
+                                            (5, 700, 320, 2, 1.0, 1.0), (40, 256, 640, 1, 1.0, 1.0)])
+def test_attention_kernel_families(cuda_device, fuse, B, S, C, Li, wt, wi):
+    """Every shape family of the bf16 processor (CTA-pair roles kernel d = 40 / 80, CTA-pair kernel d = 160, single-CTA
+    kernel for S <= 128), as ONE launch (out projection = second phase of the attention kernel, row-block counters) and
+    as attention + GEMM launches, vs the oracle -- including the BASELINE config[1] layer shapes at 16 rows, ragged S,
+    an odd number of row tiles and more units than CTA pairs.  The counters must be back to zero afterwards."""
+    from photoverse_b200 import _lib, ops
+    case = cases.ProcCase(f"fam_{S}_{C}", B=B, S=S, C=C, Li=Li, seed=60 + Li, w_text=wt, w_img=wi)
+    _lib.set_option("fuse_out", fuse)
     try:
         attn, proc = build_product_layer(case, cuda_device)
         for p_ in attn.parameters():
             p_.requires_grad_(False)
         x, text, img = cases.proc_inputs(case, torch.float32)
         force_fusion_seed(wt, wi)
+        xb, tb, ib = (t.to(cuda_device, torch.bfloat16) for t in (x, text, img))
         with torch.enable_grad():
-            y = attn(x.to(cuda_device, torch.bfloat16), encoder_hidden_states=(text.to(cuda_device, torch.bfloat16),
-                                                                              img.to(cuda_device, torch.bfloat16)))
+            y = attn(xb, encoder_hidden_states=(tb, ib))
+            force_fusion_seed(wt, wi)
+            y2 = attn(xb, encoder_hidden_states=(tb, ib))        # second call on the same counters
         with torch.no_grad():
             w = cases.proc_weights(case).to(device=cuda_device)
             y_ref, _ = dual_branch_attention(x.to(cuda_device), text.to(cuda_device), img.to(cuda_device), w, wt, wi)
         err = (y.float() - y_ref).abs().max().item()
-        assert err <= 2e-2, f"variant {variant}: max-abs {err}"
+        assert err <= 2e-2, f"fuse={fuse}: max-abs {err}"
+        assert torch.equal(y, y2), "repeated call differs (row-block counters not reset?)"
+        for buf in ops._SYNC.values():
+            assert int(buf.abs().max().item()) == 0, "row-block counters must be zero between launches"
     finally:
-        _lib.set_option("attn_variant", DEFAULT_ATTN_VARIANT)
+        _lib.set_option("fuse_out", 1)
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4, 5, 6], ids=["tmem-operands", "persistent", "cta-pair", "cta-pair16", "cta-pair-roles"])
-@pytest.mark.parametrize("Lt,S,C,Li", [(20, 256, 320, 5), (48, 256, 640, 1), (50, 384, 320, 16), (80, 256, 1280, 3), (1, 256, 320, 1)])
-def test_attention_kernel_other_text_lengths(cuda_device, variant, Lt, S, C, Li):
+@pytest.mark.parametrize("fuse", [1, 0], ids=["one-launch", "attention+gemm"])
+@pytest.mark.parametrize("Lt,S,C,Li", [(20, 256, 320, 5), (48, 256, 640, 1), (50, 384, 320, 16), (80, 256, 1280, 3), (1, 256, 320, 1),
+                                       (33, 128, 640, 2)])
+def test_attention_kernel_other_text_lengths(cuda_device, fuse, Lt, S, C, Li):
     """Text contexts other than CLIP's 77 tokens (the run-time key mask of the kernels; 1 <= Lt <= 80)."""
     from photoverse_b200 import _lib
     case = cases.ProcCase(f"lt_{Lt}_{C}", B=2, S=S, C=C, Li=Li, Lt=Lt, seed=80 + Lt)
-    _lib.set_option("attn_variant", variant)
+    _lib.set_option("fuse_out", fuse)
     try:
         attn, proc = build_product_layer(case, cuda_device)
         x, text, img = cases.proc_inputs(case, torch.float32)
@@ -277,9 +283,9 @@ def test_attention_kernel_other_text_lengths(cuda_device, variant, Lt, S, C, Li)
             w = cases.proc_weights(case).to(device=cuda_device)
             y_ref, _ = dual_branch_attention(x.to(cuda_device), text.to(cuda_device), img.to(cuda_device), w, 1.0, 1.0)
         err = (y.float() - y_ref).abs().max().item()
-        assert err <= 2e-2, f"variant {variant} Lt={Lt}: max-abs {err}"
+        assert err <= 2e-2, f"fuse={fuse} Lt={Lt}: max-abs {err}"
     finally:
-        _lib.set_option("attn_variant", DEFAULT_ATTN_VARIANT)
+        _lib.set_option("fuse_out", 1)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])

@@ -1,4 +1,5 @@
-"""Timeline of CTA 0 of the persistent attention kernel (debug trace events) for one layer shape."""
+"""Timeline of one CTA of the persistent attention kernels (debug trace events) for one layer shape.
+Needs a trace build: PV_TRACE=1 python -m photoverse_b200.build --force.  env PV_BLOCK selects the leader CTA."""
 import os
 import sys
 
@@ -12,8 +13,7 @@ dt = torch.bfloat16
 S, C = int(os.environ.get("PV_S", "4096")), int(os.environ.get("PV_C", "320"))
 ROWS, LI = 16, 1
 g = torch.Generator().manual_seed(0)
-_lib.set_option("attn_variant", int(os.environ.get("PV_ATTN_VARIANT", "3")))
-_lib.set_option("attn3_dbg", int(os.environ.get("PV_DBG", "0")))
+_lib.set_option("trace_block", int(os.environ.get("PV_BLOCK", "0")))
 lib = _lib.lib()
 text = torch.randn(ROWS, 77, 768, generator=g).to(dev, dt)
 img = torch.randn(ROWS, LI, 768, generator=g).to(dev, dt)

@@ -1,4 +1,4 @@
-"""Out-projection GEMM timing (CUDA graph of 20 launches, rotated buffers): single-CTA vs CTA-pair kernel."""
+"""Out-projection GEMM timing (CUDA graph of 20 launches, rotated buffers): single-CTA vs persistent CTA-pair kernel."""
 import os
 import sys
 
@@ -16,8 +16,7 @@ for M, N, K in [(65536, 320, 320), (16384, 640, 640), (4096, 1280, 1280), (1024,
     b = torch.zeros(N, device=dev)
     o = [torch.empty(M, N, device=dev, dtype=dt) for _ in range(nbuf)]
     res = []
-    for pair in (0, 1, 2):
-        _lib.set_option("gemm_pair", int(pair == 1))
+    for pair in (0, 2):
         _lib.set_option("gemm_persistent", int(pair == 2))
         for i in range(3):
             ops.linear(a[i], w, b, out=o[i])
@@ -35,6 +34,5 @@ for M, N, K in [(65536, 320, 320), (16384, 640, 640), (4096, 1280, 1280), (1024,
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 20
         res.append(f"{("single", "pair", "persistent")[pair]}: {us:.1f} us {2 * M * N * K / us / 1e6:.0f} TFLOP/s")
-    _lib.set_option("gemm_pair", 0)
     _lib.set_option("gemm_persistent", 1)
     print(f"M={M} N={N} K={K}: " + "   ".join(res))

@@ -36,10 +36,12 @@ for L in (32, 64, 96):
                 ys = [torch.empty_like(xs[0]) for _ in range(nbuf)]
                 os_ = [torch.empty_like(xs[0]) for _ in range(nbuf)]
 
+                sync = torch.zeros(int(lib.pv_dual_attn_sync_words(B, S)), device=dev, dtype=torch.int32)
+
                 def run(i):
                     _lib.check(lib.pv_dual_attn_fwd(1, ops._ptr(xs[i]), ops._ptr(wq), ops._ptr(kv.Kp), ops._ptr(kv.Vp),
                                                     ops._ptr(wo), ops._ptr(bo), ops._ptr(ys[i]), None, ops._ptr(os_[i]), None,
-                                                    B, S, C, 8, 77, Li, 1.0, 1.0, ops._stream()))
+                                                    ops._ptr(sync), B, S, C, 8, 77, Li, 1.0, 1.0, ops._stream()))
                 for i in range(3):
                     run(i % nbuf)
                 torch.cuda.synchronize()

@@ -1,5 +1,5 @@
 """Profiling target: the 16 attn2 layer shapes of one SD-1.5 UNet evaluation at 16 rows (batch 8, uncond+cond),
-each as the two native launches of a cached-K/V processor call (fused attention kernel + out-projection GEMM).
+each as the ONE native launch of a cached-K/V processor call (PV_FUSE_OUT=0: attention kernel + out-projection GEMM).
 Run under ncu (see tools/gpu_profile.sh); prints CUDA-event timings when run plainly."""
 import os
 import sys
@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 ROWS = int(os.environ.get("PV_ROWS", "16"))
 LI = int(os.environ.get("PV_LI", "1"))
 REPS = int(os.environ.get("PV_REPS", "3"))
-_lib.set_option("attn_variant", int(os.environ.get("PV_ATTN_VARIANT", "6")))
+_lib.set_option("fuse_out", int(os.environ.get("PV_FUSE_OUT", "1")))
 _lib.set_option("gemm_two_cta", int(os.environ.get("PV_GEMM_TWO_CTA", "1")))
 SHAPES = [(4096, 320), (1024, 640), (256, 1280), (64, 1280)]
 g = torch.Generator().manual_seed(0)

@@ -1,4 +1,4 @@
-"""One attn2 layer shape, the fused attention kernel only (ncu target).  env: PV_S, PV_C, PV_ROWS, PV_LI, PV_ATTN_VARIANT"""
+"""One attn2 layer shape, the fused attention kernel only (ncu target).  env: PV_S, PV_C, PV_ROWS, PV_LI"""
 import os
 import sys
 
@@ -10,7 +10,6 @@ from photoverse_b200 import _lib, ops  # noqa: E402
 dev = torch.device("cuda:0")
 S, C = int(os.environ.get("PV_S", "4096")), int(os.environ.get("PV_C", "320"))
 ROWS, LI = int(os.environ.get("PV_ROWS", "16")), int(os.environ.get("PV_LI", "1"))
-_lib.set_option("attn_variant", int(os.environ.get("PV_ATTN_VARIANT", "6")))
 g = torch.Generator().manual_seed(0)
 dt = torch.bfloat16
 text = torch.randn(ROWS, 77, 768, generator=g).to(dev, dt)
