@@ -47,7 +47,8 @@ const char* pv_last_error(void);
 unsigned long long pv_launch_count(void);
 /* TEST-ONLY process-wide switches (not thread-safe; production code never calls this).  Every value selects among
  * kernels that compute the same result -- none changes results:
- *   "fuse_out" 1|0        out projection as the second phase of the attention launch | as a separate GEMM launch
+ *   "fuse_out" 2|1|0      out projection as the second phase of the attention launch for every S > 128 shape | where it
+ *                         is at least as fast as two launches (default: C <= 320) | always a separate GEMM launch
  *   "gemm_persistent" 1|0 persistent CTA-pair GEMM for out-projection-shaped pv_linear_fwd calls | single-CTA kernel
  *   "gemm_two_cta" 1|0, "force_bn" 0|64|128|160|256, "epi_swizzle" 1|0   tile choices of the single-CTA GEMM
  *   "pdl" 1|0             programmatic dependent launch of the persistent kernels
@@ -101,7 +102,8 @@ int pv_kv_pack_fwd(pv_dtype dt, const void* text, const void* img, const void* W
  * stats: optional [B,H,S,4] fp32 = (max_text, sum_text, max_img, sum_img) of the scaled logits, for backward
  * ws_sync: PV_BF16, optional: pv_dual_attn_sync_words(B, S) uint32 words, ZERO on entry and left zero on return
  *          (row-block counters; one buffer may serve any number of calls that are ordered on one stream).
- * PV_BF16 path with ws_sync and S > 128: ONE persistent tcgen05 launch per processor call -- per CTA pair:
+ * PV_BF16 path with ws_sync, S > 128 (and, by default, C <= 320: see pv_set_option "fuse_out"): ONE persistent tcgen05
+ * launch per processor call -- per CTA pair:
  * Q-projection -> QK^T over the concatenated keys -> per-segment softmax with the branch weights folded in -> ONE PV
  * contraction -> O to global memory; then, in the same launch, the pair's share of the out-projection tiles
  * (Wo + bias), each tile starting as soon as the row block's head groups have announced their O rows on ws_sync.

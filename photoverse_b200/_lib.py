@@ -7,7 +7,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphotoverse_b200.so")
+LIB_PATH = os.environ.get("PV_LIB_PATH") or os.path.join(_HERE, "libphotoverse_b200.so")   # PV_LIB_PATH: debug (trace) builds
 
 PV_F32 = 0
 PV_BF16 = 1

@@ -19,8 +19,10 @@ SOURCES = ["pv_api.cu", "pv_gemm.cu", "pv_gemm3.cu", "pv_attn3.cu", "pv_attn4.cu
 HEADERS = ["pv_common.cuh", "pv_softmax.cuh", "pv_outproj.cuh", "pv_host.h", os.path.join("..", "..", "include", "photoverse_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-if os.environ.get("PV_TRACE"):          # debug builds: the persistent attention kernels record a device timeline
-    NVCC_FLAGS.append("-DPV_TRACE")
+if os.environ.get("PV_TRACE"):          # debug build: the persistent attention kernels record a device timeline;
+    NVCC_FLAGS.append("-DPV_TRACE")     # separate objects and library (load it with PV_LIB_PATH=...)
+    OBJ_DIR = os.path.join(CSRC, "build_trace")
+    LIB_PATH = os.path.join(HERE, "libphotoverse_b200_trace.so")
 
 
 def _nvcc() -> str:

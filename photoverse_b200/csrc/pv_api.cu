@@ -77,7 +77,8 @@ int g_opt_force_bn = 0;          // pv_gemm.cu: force the N tile (64/128/160/256
 int g_opt_gemm_two_cta = 1;      // pv_gemm.cu: two resident CTAs per SM for short K
 int g_opt_pdl = 1;               // programmatic dependent launch for the persistent kernels
 int g_opt_gemm_persistent = 1;   // persistent CTA-pair GEMM (pv_gemm3.cu) for the out projection shapes
-int g_opt_fuse_out = 1;          // out projection as the second phase of the attention launch (0: separate GEMM launch)
+int g_opt_fuse_out = 1;          // out projection as the second phase of the attention launch: 1 = where it is at least as
+                                 // fast as two launches (C <= 320, measured: DESIGN.md 4.2), 2 = every S > 128 shape, 0 = never
 int g_opt_bwd_mma = 1;           // bf16 attention backward on tensor cores (0: fp32-accurate SIMT kernel)
 unsigned long long* g_attn3_trace = nullptr;   // debug timeline buffer (pv_debug_trace; kernels record only in -DPV_TRACE builds)
 int g_attn3_trace_cap = 0;
@@ -195,7 +196,10 @@ static int attn_core_bf16(const void* X, const void* Wq, const void* Kp, const v
                           bool* fused = nullptr) {
   if (fused) *fused = false;
   if (S > 128) {
-    const bool want = Wo != nullptr && sync != nullptr && g_opt_fuse_out != 0;
+    // Single launch where it pays: with G = C / 160 <= 2 column groups the pairs that share a row block run in lockstep and
+    // the second phase starts at once; with more groups the wait for the slowest of G pairs (plus the announcement
+    // round trip) costs ~1 us more than the launch boundary it replaces (tools/attn_bench.py).
+    const bool want = Wo != nullptr && sync != nullptr && (g_opt_fuse_out >= 2 || (g_opt_fuse_out == 1 && C <= 320));
     if (dual_attn_pair_roles_supported(S, C, H)) {
       const bool f = want && dual_attn_pair_roles_fused_supported(S, C, H);
       if (fused) *fused = f;

@@ -186,6 +186,7 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     uint32_t it = 0;
     int prev_b = -1;
     uint32_t kv_gen = 0;
+    const uint64_t pol_x = l2_policy_evict_first();        // X is read once
     for (int u = u0; u < u1; ++u) {
       const int b = u / p.MTP;
       const int mt = 2 * (u - b * p.MTP) + static_cast<int>(rank);
@@ -197,7 +198,7 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
           if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
-          tma_load_3d_2sm(a_dst, &tmX, bar, kb * A4_BK, mt * A4_BM, b);
+          tma_load_3d_2sm_hint(a_dst, &tmX, bar, kb * A4_BK, mt * A4_BM, b, pol_x);
           if constexpr (!WSTAT)
             tma_load_3d_2sm(a_dst + A4_A_BYTES, &tmWq, bar, kb * A4_BK, g * A4_BN + static_cast<int>(rank) * (A4_BN / 2), 0);
         }
@@ -370,7 +371,7 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     if (q != 0) tr.base = nullptr;
     PendingO pend;
     pend.valid = false;
-    int sig_unit = -1;                 // FUSE: unit whose O stores of this warp are committed but not yet announced
+    const uint64_t pol_o = l2_policy_evict_last();         // O is read back by the out projection: keep it in L2
 
     // O accumulator -> registers -> * row scale -> bf16 -> this warp's staging tile -> TMA store (clips rows >= S)
     uint8_t* ost = smem + Cfg::OFF_OST + ((warp - 4) * Cfg::OST_WARP_BYTES);
@@ -393,18 +394,7 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       tc_fence_after();
 #pragma unroll
       for (int h = 0; h < (D == 160 ? 2 : 1); ++h) {
-        if (FUSE && h == 0 && sig_unit >= 0) {
-          // the stores of this warp's previous unit were committed a whole softmax ago: once they have COMPLETED (not
-          // merely read the staging tile) that unit's rows of O are in global memory -- announce it to the
-          // out-projection tiles
-          if (elect_one()) {
-            bulk_wait_all<0>();
-            op_signal_unit(p.sync, sig_unit);
-          }
-          sig_unit = -1;
-        } else {
-          if (elect_one()) bulk_wait_read<0>();          // the previous TMA store of this warp has read the tile
-        }
+        if (elect_one()) bulk_wait_read<0>();          // the previous TMA store of this warp has read the tile
         __syncwarp();
         if constexpr (D == 40) {
           uint32_t a[32], c8[8];
@@ -426,12 +416,11 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         fence_proxy_async_smem();
         __syncwarp();
         if (elect_one()) {
-          tma_store_3d(&tmO, ost, po.c0 + h * 80, po.r0, po.b);
+          tma_store_3d_hint(&tmO, ost, po.c0 + h * 80, po.r0, po.b, pol_o);
           bulk_commit();
         }
         __syncwarp();
       }
-      if (FUSE && po.last_of_unit) sig_unit = po.slot_unit;
     };
 
     // Q of unit iu: fp32 accumulator -> packed bf16, written inside the columns this group has just read
@@ -651,8 +640,6 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         pend.oscale = oscale;
         pend.parity = par;
         pend.slot = slot;
-        pend.last_of_unit = (j + 2 >= HPC);          // this group's last head of the unit
-        pend.slot_unit = u;
       }
       if (!had_head) {                                         // d = 160: the other group owns this unit's head
         arrive_leader(&slot_free[slot]);
@@ -663,14 +650,7 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       }
     }
     if (pend.valid) drain(pend);
-    if (elect_one()) {
-      if (FUSE) {
-        bulk_wait_all<0>();
-        if (sig_unit >= 0) op_signal_unit(p.sync, sig_unit);
-      } else {
-        bulk_wait_read<0>();
-      }
-    }
+    if (elect_one()) bulk_wait_read<0>();            // the staging tiles are free (the stores may still be in flight)
     __syncwarp();
     a3_trace_done_raw(p.trace, tr, 2 + wg);
     if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 168;");
@@ -682,12 +662,25 @@ dual_attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
+    if (warp >= 4) {
+      // Every draining warp announces this pair's units once its O stores have COMPLETED (per-unit announcements inside
+      // the attention loop stall the warps on the writer-side proxy fence); the first out-projection tile's loads and
+      // MMAs run meanwhile.  A warp announces every unit, also those whose head its group did not drain: the counter
+      // target is (all softmax warps of the pair) x G.
+      if (elect_one()) {
+        bulk_wait_all<0>();
+        op_signal_units(p.sync, u0, u1 - u0);
+      }
+      __syncwarp();
+    }
     OutProjArgs oa;
     oa.bias = p.bias;
     oa.sync = p.sync;
     oa.G = p.G; oa.MTP = p.MTP; oa.C = p.C; oa.V = p.V;
     oa.u0 = u0; oa.u1 = u1; oa.g = g;
-    oa.ready_target = static_cast<unsigned int>((HPC >= 2 ? 16 : 8) * p.G);   // draining warps per unit: 4 per head group x 2 CTAs
+    oa.w_preloaded = 0;
+    oa.ready_target = static_cast<unsigned int>(16 * p.G);       // 8 softmax warps x 2 CTAs announce every unit
+    oa.trace = p.trace; oa.trace_cap = p.trace_cap; oa.trace_block = 0;
     outproj_phase<typename Cfg::OP>(smem, reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR + Cfg::OP_BAR_OFF), tmem, &tmOa, &tmWo,
                                     &tmY, oa);
   }

@@ -195,6 +195,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
   pdl_wait();
   pdl_launch_dependents();
   const long long t_pdl = clock64();
+  a3_pair_time(p.trace, p.trace_block, 0);
 
   // one elected lane per warp arrives on the LEADER CTA's copy of `bar`
   auto arrive_leader = [&](uint64_t* bar) {
@@ -210,6 +211,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       uint32_t it = 0;
       uint32_t kv_gen = 0;
       int kv_end = 0;
+      const uint64_t pol_x = l2_policy_evict_first();      // X is read once
       for (int i = 0; i < nunits; ++i) {
         const int u = u0 + i;
         const int b = u / p.MTP;
@@ -221,7 +223,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
           if (elect_one()) {
             const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
             if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
-            tma_load_3d_2sm(smem + s * Cfg::STAGE_BYTES, &tmX, bar, kb * A6_BK, mt * A6_BM, b);
+            tma_load_3d_2sm_hint(smem + s * Cfg::STAGE_BYTES, &tmX, bar, kb * A6_BK, mt * A6_BM, b, pol_x);
             if constexpr (!Cfg::WSTAT)
               tma_load_3d_2sm(smem + s * Cfg::STAGE_BYTES + A6_A_BYTES, &tmWq, bar, kb * A6_BK,
                               g * A6_BN + static_cast<int>(rank) * (A6_BN / 2), 0);
@@ -248,6 +250,22 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
           __syncwarp();
           ++kv_gen;
           kv_end = (kv_end == 0) ? first_end : kv_end + p.MTP;
+        }
+      }
+      if constexpr (FUSE) {
+        // The last projection has consumed every X stage (wait for the commit of each stage's last fill): the ring is
+        // dead from here on in BOTH CTAs (the leader's MMAs read both), and the resident Wo half of the second phase
+        // lives inside it -- request it now, under the remaining attention units.
+        static_assert(Cfg::OP::W_RES_BYTES <= A6_STAGES * Cfg::STAGE_BYTES, "resident Wo half must fit the X ring");
+        if (nunits > 0) {
+          for (int s = 0; s < A6_STAGES; ++s) {
+            const uint32_t fills = (it + A6_STAGES - 1 - s) / A6_STAGES;     // loads that went to stage s
+            if (fills > 0) mbar_wait(&empty[s], (fills - 1) & 1);
+          }
+          // the peer's ring must be dead too: its producer runs the same schedule, and the multicast commits that
+          // complete my `empty` barriers complete the peer's copies at the same time
+          if (elect_one()) op_preload_w<typename Cfg::OP>(smem, reinterpret_cast<uint64_t*>(smem + A6_OFF_BAR + Cfg::OP_BAR_OFF), &tmWo, g, rank);
+          __syncwarp();
         }
       }
     } else if (warp == 1) {
@@ -574,7 +592,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     uint8_t* ost = smem + A6_OFF_OST + q * (2 * A6_OST_BYTES);
     const uint32_t osc_a = smem_u32(smem + A6_OFF_OSC) + (q * 32 + lane) * 4;
     int converted = 0, drained = 0;
-    int signalled = 0;                               // FUSE: units [0, signalled) announced on the row-block counters
+    const uint64_t pol_o = l2_policy_evict_last();     // O is read back by the out projection: keep it in L2
     int kv_end_d = 0;                                // sample tracking for the drain stream
     int b_d = u0 / p.MTP - 1;
     int m0_d = 0;
@@ -665,21 +683,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       fence_proxy_async_smem();
       __syncwarp();
       if (elect_one()) {
-        tma_store_3d(&tmO, slab, g * A6_BN + j * A6_D, m0_d + q * 32, b_d);
+        tma_store_3d_hint(&tmO, slab, g * A6_BN + j * A6_D, m0_d + q * 32, b_d, pol_o);
         bulk_commit();
-        if constexpr (FUSE) {
-          // store groups [0, nn - 2] cover units [0, (nn - 1) / HPC): once they have completed their rows of O are in
-          // global memory -- announce them to the out-projection tiles (two stores of slack: the wait is almost free)
-          const int done_units = (nn >= 1) ? (nn - 1) / A6_HPC : 0;
-          if (done_units > signalled) {
-            bulk_wait_all<2>();
-            for (int k = signalled; k < done_units; ++k) op_signal_unit(p.sync, u0 + k);
-          }
-        }
-      }
-      if constexpr (FUSE) {
-        const int done_units = (nn >= 1) ? (nn - 1) / A6_HPC : 0;
-        if (done_units > signalled) signalled = done_units;
       }
       __syncwarp();
     };
@@ -703,14 +708,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         ++drained;
       }
     }
-    if (elect_one()) {
-      if constexpr (FUSE) {
-        bulk_wait_all<0>();
-        for (int k = signalled; k < nunits; ++k) op_signal_unit(p.sync, u0 + k);
-      } else {
-        bulk_wait_read<0>();
-      }
-    }
+    if (elect_one()) bulk_wait_read<0>();             // the staging slabs are free (the stores may still be in flight)
     __syncwarp();
     if constexpr (FUSE) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
   }
@@ -723,20 +721,41 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
+    a3_pair_time(p.trace, p.trace_block, 1);
+    if (warp >= 12) {
+      // The epilogue warps have nothing to do in the second phase: they wait for their O stores to COMPLETE and announce
+      // this pair's units on the row-block counters.  Announcing per unit inside the attention loop costs ~2000 cycles
+      // per unit on the warps that own q_ready / o_free (the writer-side proxy fence drains the stores in flight), and
+      // the pairs that share a row block run in lockstep anyway.
+      A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 7, p.trace_block);
+      if ((warp & 3) != 0) tr.base = nullptr;
+      a3_trace(tr, 84, 0);
+      if (elect_one()) {
+        bulk_wait_all<0>();
+        op_signal_units(p.sync, u0, nunits);
+      }
+      __syncwarp();
+      a3_trace(tr, 85, 0);
+      a3_trace_done_raw(p.trace, tr, 7);
+    }
     OutProjArgs oa;
     oa.bias = p.bias;
     oa.sync = p.sync;
     oa.G = p.G; oa.MTP = p.MTP; oa.C = p.C; oa.V = p.V;
     oa.u0 = u0; oa.u1 = u1; oa.g = g;
+    oa.w_preloaded = 1;
     oa.ready_target = static_cast<unsigned int>(8 * p.G);        // 4 epilogue warps x 2 CTAs announce every unit
+    oa.trace = p.trace; oa.trace_cap = p.trace_cap; oa.trace_block = p.trace_block;
     outproj_phase<typename Cfg::OP>(smem, reinterpret_cast<uint64_t*>(smem + A6_OFF_BAR + Cfg::OP_BAR_OFF), tmem, &tmOa, &tmWo,
                                     &tmY, oa);
+    a3_pair_time(p.trace, p.trace_block, 3);     // the producer (thread 0's warp) has issued its last load
   }
 
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                 // neither CTA frees TMEM / exits while pair-wide MMAs or remote signals are in flight
   tc_fence_after();
+  a3_pair_time(p.trace, p.trace_block, 4);
   if (warp == 2) tmem_dealloc_2sm<512>(tmem);
 }
 

@@ -10,6 +10,7 @@
 // the next tile's MMAs) with 3-D (channel, row, sample) coordinates so that tiles coincide with attention units.
 #pragma once
 #include "pv_common.cuh"
+#include "pv_softmax.cuh"
 
 namespace pv {
 
@@ -27,8 +28,11 @@ struct OutProjCfg {
   static constexpr int W_RES_BYTES = KB_RES * OP_WH_BYTES;
   static constexpr int STAGES = NSTAGES;
   static constexpr int STAGE_BYTES = WSTAT ? OP_A_BYTES : OP_A_BYTES + OP_WH_BYTES;
-  static constexpr int OFF_W = STAGES * STAGE_BYTES;
-  static constexpr int OFF_OST = OFF_W + W_RES_BYTES;
+  // the resident W half comes FIRST: the fused kernels load it into the (already drained) X ring of the attention phase
+  // while the last attention units are still running (op_preload_w)
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_STAGES = W_RES_BYTES;
+  static constexpr int OFF_OST = OFF_STAGES + STAGES * STAGE_BYTES;
   static constexpr int OST_WARP_BYTES = 32 * 80 * 2;
   static constexpr int OFF_BIAS = OFF_OST + 8 * OST_WARP_BYTES;
   static constexpr int BYTES = OFF_BIAS + OP_BN * 4;
@@ -43,6 +47,9 @@ struct OutProjArgs {
   int u0, u1;              // this pair's tiles: units [u0, u1) of column group g
   int g;
   unsigned int ready_target;   // arrivals that complete a row block: (draining warps per unit) x G
+  int w_preloaded;             // the resident W half has already been requested (op_preload_w)
+  unsigned long long* trace;   // debug timeline (PV_TRACE builds)
+  int trace_cap, trace_block;
 };
 
 __device__ __forceinline__ void op_mbar_init(uint64_t* pb) {
@@ -62,11 +69,31 @@ __device__ __forceinline__ void op_mbar_init(uint64_t* pb) {
   mbar_init(w_full, 1);
 }
 
+// The resident W half of column group g -> shared memory [0, W_RES_BYTES); completion on the LEADER's w_full barrier.
+// One elected lane of the producer warp of BOTH CTAs calls it, either inside outproj_phase or earlier, as soon as that
+// shared memory is free in both CTAs.
+template <typename Cfg>
+__device__ __forceinline__ void op_preload_w(uint8_t* smem, uint64_t* pb, const CUtensorMap* tmW, int g, uint32_t rank) {
+  uint64_t* w_full = pb + 2 * OP_MAX_STAGES + 4;
+  const uint32_t bar = mapa_u32(smem_u32(w_full), 0);
+  const uint64_t pol_w = l2_policy_evict_last();           // every pair of the column group reads the same slice
+  if (rank == 0) mbar_expect_tx(w_full, 2 * Cfg::W_RES_BYTES);
+  for (int kb = 0; kb < Cfg::KB_RESIDENT; ++kb)
+    tma_load_3d_2sm_hint(smem + Cfg::OFF_W + kb * OP_WH_BYTES, tmW, bar, kb * OP_BK, g * OP_BN + static_cast<int>(rank) * (OP_BN / 2), 0,
+                         pol_w);
+}
+
 // An attention unit's O rows are in global memory: publish.  Called by ONE lane of a warp after
 // cp.async.bulk.wait_group (full completion, not .read) has covered the warp's stores of that unit.
 __device__ __forceinline__ void op_signal_unit(unsigned int* sync, int u) {
   asm volatile("fence.proxy.async;" ::: "memory");          // async-proxy (TMA) writes -> ordered before the release below
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync + u) : "memory");
+}
+// ... the same for units [u0, u0 + n) with one proxy fence and one gpu-scope fence
+__device__ __forceinline__ void op_signal_units(unsigned int* sync, int u0, int n) {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  for (int k = 0; k < n; ++k) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(sync + u0 + k) : "memory");
 }
 template <int N>
 __device__ __forceinline__ void bulk_wait_all() {             // groups complete AND their writes performed
@@ -96,33 +123,92 @@ __device__ __forceinline__ void outproj_phase(uint8_t* smem, uint64_t* pb, uint3
 
   if (warp == 0) {
     // ===================== producer (both CTAs): resident W half, then the A (= O) tiles as they become ready ==========
-    if constexpr (WSTAT) {
-      if (a.u0 < a.u1 && elect_one()) {
-        const uint32_t bar = mapa_u32(smem_u32(w_full), 0);
-        if (rank == 0) mbar_expect_tx(w_full, 2 * Cfg::W_RES_BYTES);
-        for (int kb = 0; kb < Cfg::KB_RESIDENT; ++kb)
-          tma_load_3d_2sm(smem + Cfg::OFF_W + kb * OP_WH_BYTES, tmW, bar, kb * OP_BK, n0 + static_cast<int>(rank) * (OP_BN / 2), 0);
-      }
-      __syncwarp();
-    }
+    A3Trace tr = a3_trace_init_raw(a.trace, a.trace_cap, 4, a.trace_block);
+    a3_trace(tr, 50, 0);
     uint32_t it = 0;
+    const uint64_t pol_a = l2_policy_evict_first();        // the A tiles are read once here
+    const bool has_sync = a.sync != nullptr;     // nullptr: plain GEMM, every tile is ready (pv_gemm3.cu)
     const unsigned int target = a.ready_target;
     unsigned int* ready = a.sync;
     unsigned int* seen = a.sync + a.V;
+    // Almost every tile's rows were announced long before this pair got here: probe 32 tiles at a time, one per lane
+    // (one L2 round trip for all of them); only a tile that is not complete yet is waited for individually.
+    auto probe32 = [&](int t0, uint32_t known) -> uint32_t {     // known: tiles of this group of 32 already seen complete
+      const int u = a.u0 + t0 + lane;
+      bool ok = false;
+      if (u < a.u1 && !((known >> lane) & 1u)) {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready + u) : "memory");
+        ok = v >= target;
+      }
+      return known | __ballot_sync(0xffffffffu, ok);
+    };
+    // The proxy fence (generic-proxy acquire -> async-proxy TMA reads) also waits for this thread's TMA loads in flight
+    // (~1 us): it is executed only right after an observation, never once per tile.
+    uint32_t ready_mask = 0;
+    if (has_sync && a.u0 < a.u1) {
+      ready_mask = probe32(0, 0u);
+      __syncwarp();
+      a3_pair_time(a.trace, a.trace_block, 5);     // first probe answered
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    if constexpr (WSTAT) {
+      if (!a.w_preloaded && a.u0 < a.u1 && elect_one()) op_preload_w<Cfg>(smem, pb, tmW, a.g, rank);
+      __syncwarp();
+    }
     for (int u = a.u0; u < a.u1; ++u) {
       const int b = u / a.MTP;
       const int mt = 2 * (u - b * a.MTP) + static_cast<int>(rank);
-      if (lane == 0) {
-        unsigned int v;
-        uint32_t tries = 0;
-        for (;;) {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready + u) : "memory");
-          if (v >= target) break;
-          __nanosleep(100);
-          if (++tries > 20000000u) __trap();      // ~2 s: a protocol bug must surface as an error, not hang the GPU
+      const int t = u - a.u0;
+      if (has_sync) {
+        bool observed = false;
+        if ((t & 31) == 0 && t > 0) { ready_mask = probe32(t, 0u); observed = true; }
+        if (!((ready_mask >> (t & 31)) & 1u)) {
+          // not announced at the last look: look at the whole group of 32 again, then wait for this very tile
+          ready_mask = probe32(t & ~31, ready_mask);
+          observed = true;
+          if (!((ready_mask >> (t & 31)) & 1u)) {
+            if (lane == 0) {
+              unsigned int v;
+              uint32_t tries = 0;
+              for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready + u) : "memory");
+                if (v >= target) break;
+                __nanosleep(32);
+                if (++tries > 20000000u) __trap();    // > 1 s: a protocol bug must surface as an error, not hang the GPU
+              }
+            }
+            ready_mask |= 1u << (t & 31);
+          }
         }
-        // 2 G producers (both CTAs of the G pairs that own this row block's column groups) look at ready[u]; the last
-        // one to have seen it complete puts both words back to zero for the next launch
+        a3_trace(tr, 51, t);
+        if (t == 0) a3_pair_time(a.trace, a.trace_block, 2);      // first tile ready
+        if (u == a.u1 - 1) a3_pair_time(a.trace, a.trace_block, 6);   // last tile ready
+        if (observed) {
+          __syncwarp();
+          asm volatile("fence.proxy.async;" ::: "memory");    // acquires above -> ordered before the TMA (async-proxy) reads
+        }
+      }
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % nst;
+        const uint32_t ph = (it / nst) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
+          uint8_t* a_dst = smem + Cfg::OFF_STAGES + s * Cfg::STAGE_BYTES;
+          const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+          tma_load_3d_2sm_hint(a_dst, tmA, bar, kb * OP_BK, mt * 128, b, pol_a);
+          if constexpr (!WSTAT)
+            tma_load_3d_2sm(a_dst + OP_A_BYTES, tmW, bar, kb * OP_BK, n0 + static_cast<int>(rank) * (OP_BN / 2), 0);
+        }
+        __syncwarp();
+      }
+      a3_trace(tr, 52, t);
+    }
+    // 2 G producers (both CTAs of the G pairs that own a row block's column groups) have looked at ready[u]; the last one
+    // to say so puts both words back to zero for the next launch.  Off the critical path: every load has been issued.
+    if (has_sync) {
+      for (int u = a.u0 + lane; u < a.u1; u += 32) {
         unsigned int old;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(seen + u) : "memory");
         if (old == static_cast<unsigned int>(2 * a.G - 1)) {
@@ -130,27 +216,13 @@ __device__ __forceinline__ void outproj_phase(uint8_t* smem, uint64_t* pb, uint3
           asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(seen + u), "r"(0u) : "memory");
         }
       }
-      __syncwarp();
-      asm volatile("fence.proxy.async;" ::: "memory");      // acquire above -> ordered before the TMA (async-proxy) reads
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        const int s = it % nst;
-        const uint32_t ph = (it / nst) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        if (elect_one()) {
-          uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-          const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
-          if (rank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
-          tma_load_3d_2sm(a_dst, tmA, bar, kb * OP_BK, mt * 128, b);
-          if constexpr (!WSTAT)
-            tma_load_3d_2sm(a_dst + OP_A_BYTES, tmW, bar, kb * OP_BK, n0 + static_cast<int>(rank) * (OP_BN / 2), 0);
-        }
-        __syncwarp();
-      }
     }
+    a3_trace_done_raw(a.trace, tr, 4);
   } else if (warp == 1) {
     if (rank == 0) {
       // ===================== MMA issuer (leader): M = 256, N = 160 for both CTAs =====================
       constexpr uint32_t idesc = umma_idesc_bf16(256, OP_BN);
+      A3Trace tr = a3_trace_init_raw(a.trace, a.trace_cap, 5, a.trace_block);
       uint32_t it = 0;
       int i = 0;
       if constexpr (WSTAT) {
@@ -165,8 +237,9 @@ __device__ __forceinline__ void outproj_phase(uint8_t* smem, uint64_t* pb, uint3
           const uint32_t ph = (it / nst) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (kb == 0) a3_trace(tr, 60, i);
           if (elect_one()) {
-            const uint8_t* a_src = smem + s * Cfg::STAGE_BYTES;
+            const uint8_t* a_src = smem + Cfg::OFF_STAGES + s * Cfg::STAGE_BYTES;
             const uint64_t da = umma_desc_sw128(a_src);
             const uint64_t dw = umma_desc_sw128(WSTAT ? smem + Cfg::OFF_W + kb * OP_WH_BYTES : a_src + OP_A_BYTES);
 #pragma unroll
@@ -176,7 +249,9 @@ __device__ __forceinline__ void outproj_phase(uint8_t* smem, uint64_t* pb, uint3
           }
           __syncwarp();
         }
+        a3_trace(tr, 61, i);
       }
+      a3_trace_done_raw(a.trace, tr, 5);
     }
   } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue (both CTAs): group w handles columns [80 w, 80 w + 80) =====================
@@ -184,10 +259,13 @@ __device__ __forceinline__ void outproj_phase(uint8_t* smem, uint64_t* pb, uint3
     const int q = warp & 3;
     const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* ost = smem + Cfg::OFF_OST + (warp - 4) * Cfg::OST_WARP_BYTES;
-    const float* bw = sbias + 80 * w;
+    const uint32_t bias_a = smem_u32(sbias + 80 * w);
+    const uint32_t ost_a = smem_u32(ost);
     // this group's 80 bias values (the attention phase owned the shared memory until the barrier before this call)
     for (int c = (warp & 3) * 32 + lane; c < 80; c += 128) sbias[80 * w + c] = a.bias ? a.bias[n0 + 80 * w + c] : 0.f;
     named_bar_sync(9 + w, 128);
+    A3Trace tr = a3_trace_init_raw(a.trace, a.trace_cap, 6, a.trace_block);
+    if (warp != 4) tr.base = nullptr;
     int i = 0;
     for (int u = a.u0; u < a.u1; ++u, ++i) {
       const int slot = i & 1;
@@ -195,32 +273,48 @@ __device__ __forceinline__ void outproj_phase(uint8_t* smem, uint64_t* pb, uint3
       const int m0 = (2 * (u - b * a.MTP) + static_cast<int>(rank)) * 128;
       mbar_wait(&acc_full[slot], (i >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32], r2[16];
+      a3_trace(tr, 70, i);
+      uint32_t v[80];
       const uint32_t src = tlane + slot * OP_BN + 80 * w;
-      tmem_ld_x32(src, r0);
-      tmem_ld_x32(src + 32, r1);
-      tmem_ld_x16(src + 64, r2);
+      tmem_ld32_raw(src, v);
+      tmem_ld32_raw(src + 32, v + 32);
+      tmem_ld16_raw(src + 64, v + 64);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
+      a3_trace(tr, 73, i);
       if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(&slot_free[slot]), 0));   // accumulator is in registers
       if (elect_one()) bulk_wait_read<0>();              // previous TMA store of this warp has read the staging tile
       __syncwarp();
-      auto put = [&](const uint32_t* v, int col0, int ncols) {
+      a3_trace(tr, 74, i);
+      // + bias -> bf16 pairs, in place (word 4c + k = columns 8c + 2k, 8c + 2k + 1).  The tensor core's operand reads and
+      // the TMA writes leave little shared-memory bandwidth: the bias comes in 16-byte (broadcast) loads ...
 #pragma unroll
-        for (int c = 0; c < ncols / 8; ++c) {
-          uint32_t w4[4];
+      for (int c = 0; c < 10; ++c) {
+        float4 b0, b1;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(bias_a + c * 32));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(bias_a + c * 32 + 16));
+        v[4 * c + 0] = pack_bf16x2(__uint_as_float(v[8 * c + 0]) + b0.x, __uint_as_float(v[8 * c + 1]) + b0.y);
+        v[4 * c + 1] = pack_bf16x2(__uint_as_float(v[8 * c + 2]) + b0.z, __uint_as_float(v[8 * c + 3]) + b0.w);
+        v[4 * c + 2] = pack_bf16x2(__uint_as_float(v[8 * c + 4]) + b1.x, __uint_as_float(v[8 * c + 5]) + b1.y);
+        v[4 * c + 3] = pack_bf16x2(__uint_as_float(v[8 * c + 6]) + b1.z, __uint_as_float(v[8 * c + 7]) + b1.w);
+      }
+      // ... and the 16-byte staging stores of a quarter warp must not collide: rows are 160 bytes apart (8 l mod 32
+      // banks), so lanes 4..7 of every quarter write the NEXT 16-byte chunk of their row in the same instruction
+      {
+        const bool hi = (lane & 4) != 0;
+        const uint32_t row_a = ost_a + lane * 160;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int cc = col0 + c * 8 + 2 * k;
-            w4[k] = pack_bf16x2(__uint_as_float(v[c * 8 + 2 * k]) + bw[cc], __uint_as_float(v[c * 8 + 2 * k + 1]) + bw[cc + 1]);
-          }
-          st_shared_v4(ost + lane * 160 + (col0 + c * 8) * 2, w4[0], w4[1], w4[2], w4[3]);
+        for (int c = 0; c < 10; ++c) {
+          const int c2 = (c + 1) % 10;
+          const uint32_t w0 = hi ? v[4 * c2 + 0] : v[4 * c + 0];
+          const uint32_t w1 = hi ? v[4 * c2 + 1] : v[4 * c + 1];
+          const uint32_t w2 = hi ? v[4 * c2 + 2] : v[4 * c + 2];
+          const uint32_t w3 = hi ? v[4 * c2 + 3] : v[4 * c + 3];
+          st_shared_v4_a(row_a + (hi ? c2 : c) * 16, w0, w1, w2, w3);
         }
-      };
-      put(r0, 0, 32);
-      put(r1, 32, 32);
-      put(r2, 64, 16);
+      }
+      a3_trace(tr, 75, i);
       fence_proxy_async_smem();
       __syncwarp();
       if (elect_one()) {
@@ -228,9 +322,12 @@ __device__ __forceinline__ void outproj_phase(uint8_t* smem, uint64_t* pb, uint3
         bulk_commit();
       }
       __syncwarp();
+      a3_trace(tr, 71, i);
     }
     if (elect_one()) bulk_wait_read<0>();
     __syncwarp();
+    a3_trace(tr, 72, 0);
+    a3_trace_done_raw(a.trace, tr, 6);
   }
 }
 

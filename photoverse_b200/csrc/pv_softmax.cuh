@@ -18,8 +18,6 @@ struct PendingO {
   int c0, r0, b;           // TMA store coordinates: first channel, first row of this warp's 32-row slab, sample
   int slot;
   bool valid;
-  bool last_of_unit;       // the draining group's last head of its unit (fused out projection: announce the unit)
-  int slot_unit;           // global unit index (row-block counter) of that unit
 };
 
 
@@ -86,8 +84,8 @@ struct A3Trace {
 #ifdef PV_TRACE
 __device__ __forceinline__ A3Trace a3_trace_init_raw(unsigned long long* trace, int trace_cap, int role, int block = 0) {
   A3Trace t;
-  const int per = trace_cap / 4;
-  t.base = (trace != nullptr && static_cast<int>(blockIdx.x) == block && (threadIdx.x & 31) == 0) ? trace + 4 + static_cast<size_t>(role) * per * 3 : nullptr;
+  const int per = trace_cap / 8;                  // 8 role regions after an 8-word header of event counts
+  t.base = (trace != nullptr && static_cast<int>(blockIdx.x) == block && (threadIdx.x & 31) == 0) ? trace + 8 + static_cast<size_t>(role) * per * 3 : nullptr;
   t.n = 0;
   t.cap = per;
   return t;
@@ -103,7 +101,17 @@ __device__ __forceinline__ void a3_trace(A3Trace& t, int ev, int idx) {
 __device__ __forceinline__ void a3_trace_done_raw(unsigned long long* trace, const A3Trace& t, int role) {
   if (t.base != nullptr) trace[role] = static_cast<unsigned long long>(t.n);
 }
+// trace_block == -1: instead of one CTA's event list, every leader CTA records the global timer at a few points of its
+// life (slot k of pair `pair`): the load balance of a launch at a glance (tools/pair_times.py).
+__device__ __forceinline__ void a3_pair_time(unsigned long long* trace, int trace_block, int k) {
+  if (trace != nullptr && trace_block == -1 && threadIdx.x == 0 && (blockIdx.x & 1) == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[8 + (blockIdx.x >> 1) * 8 + k] = t;
+  }
+}
 #else
+__device__ __forceinline__ void a3_pair_time(unsigned long long*, int, int) {}
 __device__ __forceinline__ A3Trace a3_trace_init_raw(unsigned long long*, int, int, int = 0) { return A3Trace{nullptr, 0, 0}; }
 __device__ __forceinline__ void a3_trace(A3Trace&, int, int) {}
 __device__ __forceinline__ void a3_trace_done_raw(unsigned long long*, const A3Trace&, int) {}

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from photoverse_b200 import _lib  # noqa: E402
 
-variants = [int(v) for v in sys.argv[1:]] or [1, 0]
+variants = [int(v) for v in sys.argv[1:]] or [2, 1, 0]
 rows = int(os.environ.get("PV_ROWS", "16"))
 li = int(os.environ.get("PV_LI", "1"))
 dev = torch.device("cuda:0")
