@@ -173,3 +173,66 @@ def load_reference_inject_fn():
     ns = {"torch": torch}
     exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
     return ns["_inject_concept_embeddings"]
+
+
+def load_reference_checkpoint_fns():
+    """The verbatim ``save_progress`` and ``load_photoverse_model`` of ``models/modeling_utils.py`` (:13-50).  The module
+    imports diffusers / peft / models.clip at the top (absent here), so only the two functions' sources are compiled,
+    where they lie, against stand-ins for the two peft names they use:
+      * ``LoraConfig``: a dataclass whose ``to_dict()`` is ``dataclasses.asdict`` like peft 0.10.0's PeftConfigMixin --
+        including a ``peft_type`` enum member defined under peft's module path and ``target_modules`` as a set;
+      * ``inject_adapter_in_model``: wraps the target Linears in LoraLinearStandIn.
+    Returns (save_progress, load_photoverse_model, LoraConfig)."""
+    import ast
+    import dataclasses
+    import enum
+    path = os.path.join(REFERENCE_ROOT, "models", "modeling_utils.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("save_progress", "load_photoverse_model")]
+    assert len(fns) == 2
+
+    # peft.utils.peft_types.PeftType, value == name (peft 0.10.0), pickled by reference under that module path
+    mod = sys.modules.get("peft.utils.peft_types")
+    if mod is None or not hasattr(mod, "PeftType"):
+        peft = sys.modules.setdefault("peft", types.ModuleType("peft"))
+        utils = sys.modules.setdefault("peft.utils", types.ModuleType("peft.utils"))
+        mod = types.ModuleType("peft.utils.peft_types")
+        mod.PeftType = enum.Enum("PeftType", {"LORA": "LORA", "IA3": "IA3"}, type=str, module="peft.utils.peft_types",
+                                 qualname="PeftType")
+        sys.modules["peft.utils.peft_types"] = mod
+        peft.utils, utils.peft_types = utils, mod
+    PeftType = mod.PeftType
+
+    @dataclasses.dataclass
+    class LoraConfig:
+        r: int = 8
+        lora_alpha: float = 8
+        lora_dropout: float = 0.0
+        target_modules: object = None
+        init_lora_weights: bool = True
+        peft_type: object = None
+        task_type: object = None
+        inference_mode: bool = False
+        bias: str = "none"
+
+        def __post_init__(self):
+            self.peft_type = PeftType.LORA
+            if isinstance(self.target_modules, list):
+                self.target_modules = set(self.target_modules)
+
+        def to_dict(self):
+            return dataclasses.asdict(self)
+
+    def inject_adapter_in_model(cfg, model):
+        targets = tuple(cfg.target_modules)
+        for name, module in list(model.named_modules()):
+            for child_name, child in list(module.named_children()):
+                qual = f"{name}.{child_name}" if name else child_name
+                if isinstance(child, nn.Linear) and qual.endswith(targets):
+                    setattr(module, child_name, LoraLinearStandIn(child, cfg.r, cfg.lora_alpha, cfg.lora_dropout))
+        return model
+
+    ns = {"torch": torch, "os": os, "LoraConfig": LoraConfig, "inject_adapter_in_model": inject_adapter_in_model}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), ns)
+    return ns["save_progress"], ns["load_photoverse_model"], LoraConfig

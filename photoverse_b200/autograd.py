@@ -114,6 +114,15 @@ class _DualAttnFn(torch.autograd.Function):
                 grads[2 * j] = ops.linear_bwd_weight(u, inp, alpha=s).to(A.dtype)         # dA [r, in]
         dkip = None if dkip is None else dkip.to(ctx.pdt[0])
         dvip = None if dvip is None else dvip.to(ctx.pdt[1])
+        # A branch the fusion rule dropped (attention_processor.py:413-418) is not part of the reference's graph: its
+        # parameters get NO gradient there (``.grad`` stays None and AdamW skips them -- no weight decay, no stale-momentum
+        # update), not a zero one.  to_v_ip still receives the ``to_v_ip_norm`` regulariser term (:397, train.py:512-513).
+        if meta["w_img"] == 0.0:
+            dkip = None
+            if dvn is None or not meta["vnorm_grad"]:
+                dvip = None
+        if meta["w_text"] == 0.0:
+            grads[2:6] = [None] * 4                   # LoRA factors of to_k / to_v (text branch)
         return (dx, dtext, dimg, dkip, dvip, *grads, None)
 
 
@@ -248,6 +257,15 @@ class _DualAttnDropoutFn(torch.autograd.Function):
         dtext = None if dtext is None else dtext.view(B, Lt, Dc)
         dkip = None if dkip is None else dkip.to(ctx.pdt[0])
         dvip = None if dvip is None else dvip.to(ctx.pdt[1])
+        # A branch the fusion rule dropped (attention_processor.py:413-418) is not part of the reference's graph: its
+        # parameters get NO gradient there (``.grad`` stays None and AdamW skips them -- no weight decay, no stale-momentum
+        # update), not a zero one.  to_v_ip still receives the ``to_v_ip_norm`` regulariser term (:397, train.py:512-513).
+        if meta["w_img"] == 0.0:
+            dkip = None
+            if dvn is None or not meta["vnorm_grad"]:
+                dvip = None
+        if meta["w_text"] == 0.0:
+            grads[2:6] = [None] * 4                   # LoRA factors of to_k / to_v (text branch)
         return (dx, dtext, dimg, dkip, dvip, *grads, None)
 
 

@@ -53,34 +53,48 @@ class FlatGradBuffer:
         for s in self.sizes:
             self.offsets.append(self.offsets[-1] + s)
         dev = device if device is not None else (self.params[0].device if self.params else "cpu")
-        self.flat = torch.zeros(self.offsets[-1], device=dev, dtype=torch.float32)
+        # gradients, then one "touched" flag per parameter (1.0 where this rank produced a gradient): the flags ride
+        # along in the same allreduce, so that a parameter NO rank touched keeps ``.grad = None`` like in the reference's
+        # single-process run (the optimizer then skips it: no weight decay / momentum-only update)
+        n = self.offsets[-1]
+        self._store = torch.zeros(n + len(self.params), device=dev, dtype=torch.float32)
+        self.flat = self._store[:n]
+        self.touched = self._store[n:]
         self.views = [self.flat[o:o + s].view(p.shape) for o, s, p in zip(self.offsets, self.sizes, self.params)]
 
     def numel(self) -> int:
         return self.flat.numel()
 
     def pack(self) -> None:
-        """param.grad -> flat buffer; parameters without a gradient contribute zeros."""
+        """param.grad -> flat buffer; parameters without a gradient contribute zeros (and a 0 flag)."""
+        flags = [0.0 if p.grad is None else 1.0 for p in self.params]
         for v, p in zip(self.views, self.params):
             if p.grad is None:
                 v.zero_()
             else:
                 v.copy_(p.grad)
+        self._flags_host = flags
+        self.touched.copy_(torch.tensor(flags, dtype=torch.float32), non_blocking=True)
 
     def allreduce_mean(self, group=None, async_op: bool = False):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
         world = dist.get_world_size(group)
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        work = dist.all_reduce(self._store, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        self._flags_host = None                    # the flags now live in the reduced buffer
         if async_op:
             return work
         self.flat.div_(world)
         return None
 
     def unpack(self) -> None:
-        """flat buffer -> param.grad (allocating a gradient for parameters that had none)."""
-        for v, p in zip(self.views, self.params):
-            if p.grad is None:
+        """flat buffer -> param.grad.  A parameter that no rank produced a gradient for keeps ``.grad = None``; one that
+        only other ranks touched gets the (mean) gradient allocated here."""
+        flags = self._flags_host if getattr(self, "_flags_host", None) is not None else self.touched.tolist()
+        for v, p, f in zip(self.views, self.params, flags):
+            if f <= 0.0:
+                p.grad = None
+            elif p.grad is None:
                 p.grad = v.to(p.dtype).clone()
             else:
                 p.grad.copy_(v)
@@ -102,3 +116,113 @@ class FlatGradBuffer:
                 if n.startswith(pre):
                     v.mul_(coef)
         return norms
+
+
+class OverlappedGradReducer:
+    """Gradient allreduce overlapped with the backward pass ("overlap the allreduce of processor / LoRA grads
+    with the remaining UNet backward; adapter grads finish last").
+
+    The flat buffer is cut into contiguous buckets, launched in the order the backward pass completes them --
+    unet.up_blocks first, then mid / down blocks, the two adapters last (train.py:538: their gradients need the K/V-image
+    gradients of all 16 layers).  A post-accumulate hook copies each gradient into its slice as soon as autograd has
+    produced it; when the last EXPECTED gradient of the next bucket in line has arrived, its allreduce is launched
+    asynchronously (NCCL runs it on its own stream, under the backward kernels still queued on the compute stream).
+    Every rank issues the collectives in the same (bucket) order, whatever its own arrival times.
+
+    Parameters the stochastic fusion rule leaves without a gradient this step (attention_processor.py:413-418; each rank
+    draws its own) never fire their hook: the caller passes ``expected`` to :meth:`begin` -- known after the forward
+    pass -- so that they do not hold their bucket back; their slices are zero and their "touched" flag is 0.
+    ``finish()`` -- after ``backward()`` -- launches what is still pending plus the flags, waits and divides by the world
+    size.  With one process nothing is hooked and ``finish()`` is ``pack()``."""
+
+    ORDER = ("unet.up_blocks", "unet.mid_block", "unet.down_blocks", "unet.", "text_adapter.", "image_adapter.")
+
+    def __init__(self, buf: FlatGradBuffer, group=None):
+        self.buf, self.group = buf, group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.buckets: List[List[int]] = []      # parameter indices, each bucket contiguous in the flat buffer
+        self.launch_order: List[int] = []
+        self.handles = []
+        self.active = False
+        if self.world == 1:
+            return
+
+        def key(name):
+            for k, pre in enumerate(self.ORDER):
+                if name.startswith(pre):
+                    return k
+            return len(self.ORDER)
+        run_key, run, keys = None, [], []
+        for i, n in enumerate(buf.names):
+            k = key(n)
+            if run and k != run_key:
+                self.buckets.append(run)
+                keys.append(run_key)
+                run = []
+            run_key = k
+            run.append(i)
+        if run:
+            self.buckets.append(run)
+            keys.append(run_key)
+        self.launch_order = sorted(range(len(self.buckets)), key=lambda b: (keys[b], b))
+        self.bucket_of = {i: b for b, idxs in enumerate(self.buckets) for i in idxs}
+        for i, p in enumerate(buf.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i):
+        def hook(p):
+            if not self.active or self.seen[i]:
+                return
+            self.buf.views[i].copy_(p.grad)
+            self.seen[i] = True
+            if self.expected[i]:
+                self.missing[self.bucket_of[i]] -= 1
+                self._launch_ready()
+        return hook
+
+    def _launch_ready(self, force: bool = False):
+        while self.next < len(self.launch_order):
+            b = self.launch_order[self.next]
+            if self.missing[b] > 0 and not force:
+                return
+            idxs = self.buckets[b]
+            if force:                               # late gradients that were not expected, never-arrived ones -> zeros
+                for i in idxs:
+                    p = self.buf.params[i]
+                    if not self.seen[i] and p.grad is not None:
+                        self.buf.views[i].copy_(p.grad)
+                        self.seen[i] = True
+            lo, hi = self.buf.offsets[idxs[0]], self.buf.offsets[idxs[-1] + 1]
+            self.handles.append(dist.all_reduce(self.buf.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self.next += 1
+
+    def begin(self, expected: Sequence[bool] = None):
+        """Call after the forward pass, before ``backward()``.  ``expected[i]``: parameter i will receive a gradient."""
+        if self.world == 1:
+            return
+        n = len(self.buf.params)
+        self.expected = list(expected) if expected is not None else [True] * n
+        self.seen = [False] * n
+        self.missing = [sum(1 for i in idxs if self.expected[i]) for idxs in self.buckets]
+        self.next = 0
+        self.handles = []
+        self.early = 0
+        self.buf.flat.zero_()
+        self.active = True
+
+    def finish(self) -> int:
+        """Call after ``backward()``: returns how many buckets had been launched before backward() returned."""
+        buf = self.buf
+        if self.world == 1:
+            buf.pack()
+            return 0
+        self.active = False
+        early = self.next
+        self._launch_ready(force=True)
+        buf.touched.copy_(torch.tensor([1.0 if s else 0.0 for s in self.seen], dtype=torch.float32), non_blocking=True)
+        self.handles.append(dist.all_reduce(buf.touched, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for h in self.handles:
+            h.wait()
+        buf._flags_host = None
+        buf.flat.div_(self.world)
+        return early

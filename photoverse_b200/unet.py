@@ -5,6 +5,8 @@
 any UNet exposing diffusers' ``attn_processors`` / ``set_attn_processor`` / ``config`` protocol -- a real
 ``UNet2DConditionModel`` or the SD-1.5-shaped host model in ``photoverse_b200.host.unet_sd15``.
 """
+import re
+
 import torch
 
 from .attention_processor import PhotoVerseAttnProcessor2_0
@@ -19,45 +21,49 @@ def _default_self_attn_processor():
         return AttnProcessor2_0()
 
 
+_BLOCK_RE = re.compile(r"^(down_blocks|up_blocks)\.(\d+)\.|^(mid_block)\.")
+
+
+def _layer_width(processor_key: str, widths) -> int:
+    """Channel width C of the transformer block a processor key belongs to: down block i -> widths[i], up block i ->
+    widths[-1 - i], mid block -> widths[-1] (what reference unet.py:12-19 derives from ``block_out_channels``)."""
+    m = _BLOCK_RE.match(processor_key)
+    if m is None:
+        raise ValueError(f"unexpected attention processor name {processor_key!r}")
+    if m.group(3):
+        return widths[-1]
+    idx = int(m.group(2))
+    return widths[idx] if m.group(1) == "down_blocks" else widths[len(widths) - 1 - idx]
+
+
+def _is_self_attention(processor_key: str) -> bool:
+    return processor_key.endswith("attn1.processor")
+
+
 def set_visual_cross_attention_adapter(unet, num_tokens=(5,)):
-    attn_procs = {}
-    for name in unet.attn_processors.keys():
-        cross_attention_dim = None if name.endswith("attn1.processor") else unet.config.cross_attention_dim
-        if name.startswith("mid_block"):
-            hidden_size = unet.config.block_out_channels[-1]
-        elif name.startswith("up_blocks"):
-            block_id = int(name[len("up_blocks.")])
-            hidden_size = list(reversed(unet.config.block_out_channels))[block_id]
-        elif name.startswith("down_blocks"):
-            block_id = int(name[len("down_blocks.")])
-            hidden_size = unet.config.block_out_channels[block_id]
-        else:
-            raise ValueError(f"unexpected attention processor name {name!r}")
-        if cross_attention_dim is None:
-            attn_procs[name] = _default_self_attn_processor()
-        else:
-            attn_procs[name] = PhotoVerseAttnProcessor2_0(
-                cross_attention_dim=cross_attention_dim, hidden_size=hidden_size, num_tokens=num_tokens)
-    unet.set_attn_processor(attn_procs)
+    """Install the B200 dual-branch processor on every cross-attention (``attn2``) module and a stock SDPA processor on
+    every self-attention (``attn1``) module -- the contract of reference unet.py:8-35 (same name / arguments / result)."""
+    widths = tuple(unet.config.block_out_channels)
+    context_dim = unet.config.cross_attention_dim
+    unet.set_attn_processor({
+        key: (_default_self_attn_processor() if _is_self_attention(key) else
+              PhotoVerseAttnProcessor2_0(hidden_size=_layer_width(key, widths), cross_attention_dim=context_dim,
+                                         num_tokens=num_tokens))
+        for key in unet.attn_processors})
     return unet
 
 
 def get_visual_cross_attention_values_norm(unet):
-    """Stack the ``to_v_ip_norm`` side outputs of the attn2 processors -> [B, n_layers * H * Li] (unet.py:38-47)."""
-    attn_values = []
-    for name, attn_processor in unet.attn_processors.items():
-        if name.endswith("attn1.processor"):
-            continue
-        attn_values.append(attn_processor.to_v_ip_norm)
-    cross_attn_values_norm = torch.stack(attn_values, dim=1)
-    bsz = cross_attn_values_norm.shape[0]
-    return cross_attn_values_norm.view(bsz, -1)
+    """The regulariser input of train.py:512-513: every attn2 processor's ``to_v_ip_norm`` side output [B, H, Li, 1],
+    layers in ``attn_processors`` order -> [B, n_layers * H * Li] (reference unet.py:38-47)."""
+    norms = [proc.to_v_ip_norm for key, proc in unet.attn_processors.items() if not _is_self_attention(key)]
+    return torch.stack(norms, dim=1).flatten(1)
 
 
 def set_cross_attention_layers_to_train(unet):
-    for name, module in unet.named_modules():
-        if "attn2" in name:
-            module.train()
+    """``.train()`` on every module under an ``attn2`` (activates peft's LoRA dropout; reference unet.py:50-53)."""
+    for module in (m for n, m in unet.named_modules() if "attn2" in n):
+        module.train()
 
 
 def set_kv_cache(unet, enabled: bool, static: bool = False):

@@ -205,29 +205,96 @@ def test_checkpoint_wire_format_round_trip(tmp_path):
     assert save_progress(ia, ta, unet, str(tmp_path)).endswith("photoverse.pt")
 
 
+def test_checkpoint_written_by_the_reference_loads(tmp_path):
+    """A file written by the VERBATIM reference ``save_progress`` (modeling_utils.py:29-50: its key filter, its
+    ``lora_config.to_dict()`` with a peft PeftType enum member and a ``set``) loads into the B200 classes under
+    torch.load's weights-only rules; and a file written here is read by the verbatim reference loader."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("/root/reference not mounted")
+    from types import SimpleNamespace
+    from photoverse_b200.checkpoint import cross_attention_state_dict, load_photoverse_model, save_progress
+    ref_save, ref_load, RefLoraConfig = ref_loader.load_reference_checkpoint_fns()
+    targets = ["attn2.to_k", "attn2.to_v", "attn2.to_q"]
+
+    def fresh(seed, lora):
+        torch.manual_seed(seed)
+        u = UNetSD15(block_out_channels=(320, 640), layers_per_block=1)
+        pv.set_visual_cross_attention_adapter(u)
+        if lora:
+            inject_lora(u, r=4, lora_alpha=2.0)
+            with torch.no_grad():
+                for n, p in u.named_parameters():
+                    if "lora_B" in n:
+                        p.normal_()
+        return u, pv.PhotoVerseAdapter(num_tokens=2), pv.PhotoVerseAdapter(num_tokens=2)
+
+    # reference writes -> we read
+    unet, ia, ta = fresh(0, lora=True)
+    accel = SimpleNamespace(unwrap_model=lambda m: m)
+    cfg = RefLoraConfig(r=4, lora_alpha=2.0, lora_dropout=0.1, target_modules=targets)
+    opt = torch.optim.AdamW(ia.parameters(), lr=1e-4)
+    ref_save(ia, ta, unet, accel, str(tmp_path), step=3, lora_config=cfg, optimizer=opt)
+    path = str(tmp_path / "photoverse_000003.pt")
+    with pytest.raises(Exception):                     # the raw file is NOT loadable with torch's default rules ...
+        torch.load(path, map_location="cpu")
+    unet2, ia2, ta2 = fresh(1, lora=False)             # ... and carries the enum + set; no LoRA wrappers yet
+    _, _, unet2, cfg2 = load_photoverse_model(path, ia2, ta2, unet2)
+    assert cfg2["r"] == 4 and cfg2["lora_alpha"] == 2.0 and cfg2["lora_dropout"] == 0.1 and cfg2["peft_type"] == "LORA"
+    assert cfg2["target_modules"] == sorted(targets)
+    a, b = cross_attention_state_dict(unet), cross_attention_state_dict(unet2)
+    assert list(a) == list(b) and len(a) > 0 and all(torch.equal(a[k], b[k]) for k in a)
+    assert all(torch.equal(p, q) for p, q in zip(ta.state_dict().values(), ta2.state_dict().values()))
+    from photoverse_b200.lora import linear_parts
+    mod = unet2.mid_block.attentions[0].transformer_blocks[0].attn2.to_q
+    assert linear_parts(mod.train())[3] == 0.5 and linear_parts(mod)[4] == pytest.approx(0.1)   # scaling alpha / r, dropout p
+
+    # we write -> the reference reads (its LoraConfig(**cfg) + inject + strict=False load)
+    ours = save_progress(ia, ta, unet, str(tmp_path), step=4, lora_config=cfg)
+    assert isinstance(torch.load(ours, map_location="cpu")["lora_config"]["target_modules"], list)   # plain types
+    unet3, ia3, ta3 = fresh(2, lora=False)
+    _, _, unet3, cfg3 = ref_load(ours, ia3, ta3, unet3)
+    assert cfg3.r == 4 and set(cfg3.target_modules) == set(targets)
+    c = cross_attention_state_dict(unet3)
+    assert list(a) == list(c) and all(torch.equal(a[k], c[k]) for k in a)
+
+
 def test_dpmpp_2m_schedule_is_exact_for_a_perfect_denoiser():
     """DPM-Solver++(2M) (reference sampler, infer.py:39-40): with the exact epsilon of a fixed x0 every step must land on
-    alpha_t x0 + sigma_t n exactly (the solver integrates the data-prediction ODE exactly for constant x0), for both the
-    first-order start, the 2M steps and the lower-order final step; coefficients are finite and the grid is descending."""
+    alpha_t x0 + sigma_t n exactly (the solver integrates the data-prediction ODE exactly for constant x0), for the
+    first-order start, the 2M steps and the final step.  diffusers' default ``final_sigmas_type="zero"`` closes the grid
+    with sigma = 0: the last step is first-order for EVERY N and returns the data prediction itself; the coefficients of
+    that step are pinned to the closed form of diffusers' first-order update at (alpha, sigma) = (1, 0)."""
     import numpy as np
     from photoverse_b200.host.dpm_solver import make_dpmpp_2m_schedule
     betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000) ** 2
     ac = np.cumprod(1 - betas)
-    for n in (10, 25, 50):
-        s = make_dpmpp_2m_schedule(n)
-        assert len(s.timesteps) == n and s.timesteps[0] == 999 and all(a > b for a, b in zip(s.timesteps, s.timesteps[1:]))
-        assert all(np.isfinite(v) for v in s.cx + s.c0 + s.c0p + s.kx + s.ke)
-        assert s.c0p[0] == 0.0 and all(c != 0.0 for c in s.c0p[1:-1]) and (s.c0p[-1] == 0.0) == (n < 15)
-        x0, noise = 0.7, -1.3
-        nodes = s.timesteps + [0]
-        x = ac[nodes[0]] ** 0.5 * x0 + (1 - ac[nodes[0]]) ** 0.5 * noise
-        x0_prev = None
-        for i in range(n):
-            t = nodes[i]
-            eps = (x - ac[t] ** 0.5 * x0) / (1 - ac[t]) ** 0.5              # the perfect epsilon-prediction
-            d = s.kx[i] * x + s.ke[i] * eps
-            assert abs(d - x0) < 1e-9
-            x = s.cx[i] * x + s.c0[i] * d + (s.c0p[i] * x0_prev if s.c0p[i] != 0.0 else 0.0)
-            x0_prev = d
-            tn = nodes[i + 1]
-            assert abs(x - (ac[tn] ** 0.5 * x0 + (1 - ac[tn]) ** 0.5 * noise)) < 1e-9
+    for final in ("zero", "sigma_min"):
+        for n in (10, 25, 50):
+            s = make_dpmpp_2m_schedule(n, final_sigmas_type=final)
+            assert len(s.timesteps) == n and s.timesteps[0] == 999 and all(a > b for a, b in zip(s.timesteps, s.timesteps[1:]))
+            assert all(np.isfinite(v) for v in s.cx + s.c0 + s.c0p + s.kx + s.ke)
+            assert s.c0p[0] == 0.0 and all(c != 0.0 for c in s.c0p[1:-1])
+            if final == "zero":
+                assert (s.cx[-1], s.c0[-1], s.c0p[-1]) == (0.0, 1.0, 0.0)       # x_N = x0 prediction, first order
+            else:
+                assert (s.c0p[-1] == 0.0) == (n < 15)
+            x0, noise = 0.7, -1.3
+            nodes = s.timesteps + [0]
+            x = ac[nodes[0]] ** 0.5 * x0 + (1 - ac[nodes[0]]) ** 0.5 * noise
+            x0_prev = None
+            for i in range(n):
+                t = nodes[i]
+                eps = (x - ac[t] ** 0.5 * x0) / (1 - ac[t]) ** 0.5              # the perfect epsilon-prediction
+                d = s.kx[i] * x + s.ke[i] * eps
+                assert abs(d - x0) < 1e-9
+                x = s.cx[i] * x + s.c0[i] * d + (s.c0p[i] * x0_prev if s.c0p[i] != 0.0 else 0.0)
+                x0_prev = d
+                if final == "zero" and i == n - 1:
+                    assert abs(x - x0) < 1e-9                                   # sigma = 0: no residual noise
+                else:
+                    tn = nodes[i + 1]
+                    assert abs(x - (ac[tn] ** 0.5 * x0 + (1 - ac[tn]) ** 0.5 * noise)) < 1e-9
+    # first-order update of diffusers at the terminal node: x_t = (sigma_t / sigma_s) x - alpha_t (exp(-h) - 1) x0 with
+    # sigma_t = 0, alpha_t = 1, h = lambda_t - lambda_s = +inf  ->  0 * x + 1 * x0
+    assert (0.0 / (1 - ac[20]) ** 0.5, -1.0 * (np.exp(-np.inf) - 1.0)) == (0.0, 1.0)
