@@ -15,7 +15,12 @@ Reported on one JSON line (rank 0):
   e2e        same metric through the public API with HOST (pinned) inputs: H2D of every input + D2H of the latents
              inside the timed region
   roofline   the fused Q-projection + dual-branch attention kernel (the dominant native kernel), timed alone with
-             CUDA events over the 16 attn2 layer shapes of one UNet evaluation, against the measured bf16 peak
+             CUDA events over the 16 attn2 layer shapes of one UNet evaluation, against the measured bf16 peak; next to
+             it the whole processor call (one launch / two launches) and the SAME-BOX GPU-EAGER comparator: the
+             reference's own op sequence (attention_processor.py:297-433: cuBLASLt linears + two SDPA calls) in bf16
+  train      BASELINE config[3] as a sub-record at every N (ms/step, samples/s, exposed allreduce time) for LoRA rank
+             8 and 128, so that the driver's 1 -> 8 GPU runs carry the NCCL-limited training curve too
+  cfg3       (N >= 2) BASELINE config[2]: guidance 7.5, global batch 64 strong-scaled over the N GPUs
   cpu_baseline  the oracle port of the reference path, host UNet in fp32 on the host cores, bounded sample
   --impl reference : the CPU arm as the whole job (same metric / config keys), rank 0 only.
 """
@@ -54,6 +59,9 @@ def parse():
     ap.add_argument("--token-index", default="0", help="adapter head used at inference (reference default 0) or 'full'")
     ap.add_argument("--mode", default="batched", choices=["batched", "two_call", "cond_only"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-leg", action="store_true", help="skip the config[3] training sub-records")
+    ap.add_argument("--no-cfg3-leg", action="store_true", help="skip the config[2] CFG 7.5 strong-scaling sub-record")
+    ap.add_argument("--train-steps", type=int, default=20, help="timed steps of each training sub-record")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="keep the host UNet in NCHW (default: channels_last)")
     ap.add_argument("--workload", default="generate", choices=["generate", "train"],
@@ -144,14 +152,6 @@ def build_models(device, dtype, T=5, channels_last=True):
     return unet, image_adapter, text_adapter
 
 
-def pinned_inputs(batch, latent, seed, dtype):
-    from photoverse_b200.host.pipeline import GenInputs, synthetic_inputs
-    h = synthetic_inputs(batch, latent, seed=seed, dtype=dtype)
-    pin = lambda t: t.contiguous().pin_memory()
-    return GenInputs([pin(t) for t in h.clip_hidden], [pin(t) for t in h.clip_hidden_uncond], pin(h.text),
-                     pin(h.text_uncond), pin(h.noise))
-
-
 # ------------------------------------------------------------------------------------------------------------
 # roofline leg: the fused attention kernel alone, per attn2 layer shape, CUDA-event timed
 # ------------------------------------------------------------------------------------------------------------
@@ -163,6 +163,70 @@ def processor_flops_cached(rows_b, S, C, Li):
     return 4 * rows_b * S * C * C + 4 * rows_b * S * C * (LT + Li)      # + out projection; K/V cached across steps
 
 
+def eager_reference_processor(x, text, img, wq, wk, wv, wkip, wvip, wo, bo, H):
+    """The reference's no-grad call, op for op, in PyTorch eager (the kernels to beat on this box):
+    attention_processor.py:297 to_q, :304-305 to_k / to_v, :310-313 split heads, :317-319 SDPA(text), :321-322 merge,
+    :392-396 to_k_ip / to_v_ip, :397 norm side output, :400-407 SDPA(image), :412 add, :423 to_out, :433 rescale.
+    K/V are projected on every call, as the reference does."""
+    import torch.nn.functional as F
+    B, _, C = x.shape
+    d = C // H
+    heads = lambda t: t.view(B, -1, H, d).transpose(1, 2)
+    q = heads(F.linear(x, wq))
+    k, v = heads(F.linear(text, wk)), heads(F.linear(text, wv))
+    o = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
+    o = o.transpose(1, 2).reshape(B, -1, C).to(q.dtype)
+    ik, iv = heads(F.linear(img, wkip)), heads(F.linear(img, wvip))
+    vnorm = torch.norm(iv, dim=-1, keepdim=True)
+    io = F.scaled_dot_product_attention(q, ik, iv, attn_mask=None, dropout_p=0.0, is_causal=False)
+    io = io.transpose(1, 2).reshape(B, -1, C).to(q.dtype)
+    o = o + io
+    y = F.linear(o, wo, bo)
+    return y / 1.0, vnorm
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant (S4096, C320) attention instance, read
+    from the committed `ncu --set full` summary of this round (profiles/r02_ncu_attn.csv), else the round-1 one."""
+    import csv
+    for name in ("r02_ncu_attn.csv", "r01n_ncu_attn.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        try:
+            rows = list(csv.reader(open(path)))
+            head, units = rows[0], rows[1]
+            ir, iw, ik = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum"), head.index("Kernel Name")
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if "<40" in r[ik]:          # head_dim 40 instance = the S4096 C320 layer
+                    return (float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]],
+                            f"profiles/{name}: dram__bytes_read.sum + dram__bytes_write.sum, one launch of {r[ik][:60]}")
+        except Exception:
+            continue
+    return None, "no committed ncu --set full summary"
+
+
+def _graph_time_us(fn, nbuf, reps=20):
+    """Device time per call: `reps` launches captured in a CUDA graph (as the generation engine runs them), so that the
+    Python / ctypes launch rate does not bound kernels shorter than it; CUDA events around one replay."""
+    for i in range(3):
+        fn(i % nbuf)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for i in range(reps):
+            fn(i % nbuf)
+    gr.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
 def roofline_leg(device, rows_b, Li, scale):
     """Returns roofline dict for the fused attention kernel + per-family detail + whole-processor numbers."""
     from photoverse_b200 import _lib, ops
@@ -171,6 +235,7 @@ def roofline_leg(device, rows_b, Li, scale):
     g = torch.Generator().manual_seed(1)
     fam = {}
     l2_bytes = 192 << 20
+    lib = _lib.lib()
     for (S, C) in sorted(set(LAYER_SHAPES), reverse=True):
         H = 8
         text = torch.randn(rows_b, LT, 768, generator=g).to(device, dt)
@@ -186,7 +251,6 @@ def roofline_leg(device, rows_b, Li, scale):
         xs = [torch.randn(rows_b, S, C, device=device, dtype=dt) for _ in range(nbuf)]
         os_ = [torch.empty_like(xs[0]) for _ in range(nbuf)]
         ys = [torch.empty_like(xs[0]) for _ in range(nbuf)]
-        lib = _lib.lib()
         sync = torch.zeros(int(lib.pv_dual_attn_sync_words(rows_b, S)), device=device, dtype=torch.int32)
 
         def attn_only(i):
@@ -198,56 +262,63 @@ def roofline_leg(device, rows_b, Li, scale):
                                             ops._ptr(wo), ops._ptr(bo), ops._ptr(ys[i]), None, ops._ptr(os_[i]), None,
                                             ops._ptr(sync), rows_b, S, C, H, LT, Li, 1.0, 1.0, ops._stream()))
 
-        out = {}
-        for name, fn in (("attn", attn_only), ("proc", full)):
-            for i in range(3):
-                fn(i % nbuf)
-            reps = 20
-            torch.cuda.synchronize()
-            # device time: the launches are captured in a CUDA graph (as the generation engine runs them) so that the
-            # Python / ctypes launch rate (~15 us per call) does not bound kernels that are shorter than that
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
-                for i in range(reps):
-                    fn(i % nbuf)
-            gr.replay()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            gr.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            out[name + "_us"] = e0.elapsed_time(e1) * 1e3 / reps
+        bo_b = bo.to(dt)
+        eager_out = [None]
+
+        def eager(i):        # the reference's op sequence; K/V recomputed per call like the reference (D7)
+            eager_out[0] = eager_reference_processor(xs[i], text, img, wq, wkv_t[:C], wkv_t[C:], wkv_i[:C], wkv_i[C:], wo, bo_b, H)
+
+        out = {"attn_us": _graph_time_us(attn_only, nbuf)}
+        n0 = _lib.launch_count()
+        full(0)
+        out["launches_per_call"] = int(_lib.launch_count() - n0)
+        out["proc_us"] = _graph_time_us(full, nbuf)                     # the library's default policy
+        for opt, key in ((2, "proc_one_launch_us"), (0, "proc_two_launch_us")):
+            if S > 128:
+                _lib.set_option("fuse_out", opt)
+                out[key] = _graph_time_us(full, nbuf)
+        _lib.set_option("fuse_out", 1)
+        with torch.no_grad():
+            out["gpu_eager_us"] = _graph_time_us(eager, nbuf)
+            full(0)
+            eager(0)
+            out["eager_vs_ours_max_abs"] = float((eager_out[0][0].float() - ys[0].float()).abs().max())
+        out["speedup_vs_gpu_eager"] = out["gpu_eager_us"] / out["proc_us"]
         fam[f"S{S}_C{C}"] = out
         del xs, os_, ys
     # aggregate over the 16 layers of one UNet evaluation
-    t_attn = sum(fam[f"S{S}_C{C}"]["attn_us"] for S, C in LAYER_SHAPES) * 1e-6
-    t_proc = sum(fam[f"S{S}_C{C}"]["proc_us"] for S, C in LAYER_SHAPES) * 1e-6
+    tsum = lambda key: sum(fam[f"S{S}_C{C}"][key] for S, C in LAYER_SHAPES) * 1e-6
+    t_attn, t_proc, t_eager = tsum("attn_us"), tsum("proc_us"), tsum("gpu_eager_us")
     f_attn = sum(attn_kernel_flops(rows_b, S, C, Li) for S, C in LAYER_SHAPES)
     f_proc = sum(processor_flops_cached(rows_b, S, C, Li) for S, C in LAYER_SHAPES)
     ach = f_attn / t_attn / 1e12
-    roof = {"bound": "tensor", "kernel": "dual_attn_fwd_pair_roles_kernel (head_dim 40 / 80 layers) / dual_attn_fwd_pair_kernel (head_dim 160): fused Q-proj + dual-branch attention on cta_group::2 CTA pairs; single-CTA persistent kernel for S <= 128",
+    traffic, traffic_src = ncu_traffic()
+    roof = {"bound": "tensor", "kernel": "dual_attn_fwd_pair_roles_kernel (head_dim 40 / 80 layers) / dual_attn_fwd_pair_kernel (head_dim 160): fused Q-proj + dual-branch attention on cta_group::2 CTA pairs (attention phase only: pv_dual_attn_core_fwd); single-CTA persistent kernel for S <= 128",
             "achieved": round(ach, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": round(ach / peaks["bf16_tflops"], 4), "peak_source": peaks["source"] + " cuBLAS bf16 burst",
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant (S4096, C320) instance from the ncu
-            # --set full capture of tools/profile_layer_stack.py (profiles/r01n_ncu_attn.csv): 44.7 MB + 4.6 MB;
-            # algorithmic bytes of that launch: X 41.9 MB in (+ 0.2 MB Wq, 2.4 MB K/V tiles), O 41.9 MB out (stays in L2)
-            "traffic": 49.3e6, "traffic_unit": "bytes per launch, S4096_C320 layer (ncu r01n)",
+            "traffic": traffic, "traffic_unit": "bytes per launch, S4096_C320 layer", "traffic_source": traffic_src,
             "how": f"CUDA events around a CUDA graph of 20 launches per attn2 layer shape at {rows_b} rows (uncond+cond), "
                    f"inputs rotated through > L2 of buffers; aggregated over the 16 layers of one UNet evaluation; "
-                   f"algorithmic FLOPs = 2 rows C^2 + 4 rows C (77 + Li) per launch",
-            "per_shape_us": {k: {kk: round(vv, 2) for kk, vv in v.items()} for k, v in fam.items()},
+                   f"algorithmic FLOPs = 2 rows C^2 + 4 rows C (77 + Li) per launch (processor: 4 rows C^2 + ...); "
+                   f"proc_us = whole processor call with the library's default launch policy (one launch for C <= 320, "
+                   f"attention + out-projection launches otherwise), proc_one/two_launch_us = both forms forced; "
+                   f"gpu_eager_us = the reference's own op sequence in PyTorch eager bf16 on this GPU (cuBLASLt + 2 SDPA, "
+                   f"K/V projected per call), graph-replayed like ours",
+            "per_shape_us": {k: {kk: (round(vv, 2) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in fam.items()},
             "processor_tflops": round(f_proc / t_proc / 1e12, 2),
             "processor_frac": round(f_proc / t_proc / 1e12 / peaks["bf16_tflops"], 4),
-            "processor_ms_per_unet_eval": round(t_proc * 1e3, 3)}
+            "processor_ms_per_unet_eval": round(t_proc * 1e3, 3),
+            "gpu_eager_ms_per_unet_eval": round(t_eager * 1e3, 3),
+            "speedup_vs_gpu_eager": round(t_eager / t_proc, 2)}
     return roof
 
 
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, denoise_steps, latent, token_index, T=5):
-    """Each step = bounded sample: 1 image, adapters once + ONE denoise step (uncond + cond UNet evaluation, fp32)."""
+def cpu_reference_run(steps, warmup, denoise_steps, latent, token_index, batch, T=5):
+    """Each step = bounded sample of the SAME workload: the whole batch, adapters once + ONE of the `denoise_steps`
+    denoise steps (uncond + cond UNet evaluation as two calls, like infer.py:103-114), fp32 on all host cores."""
     from oracle.host_reference import clone_adapter_as_oracle, clone_with_oracle_processors
     from photoverse_b200.host.ddim import make_ddim_schedule
     from photoverse_b200.host.pipeline import synthetic_inputs
@@ -262,7 +333,7 @@ def cpu_reference_run(steps, warmup, denoise_steps, latent, token_index, T=5):
     torch.manual_seed(1)
     image_adapter = clone_adapter_as_oracle(pv.PhotoVerseAdapter(num_tokens=T)).eval()
     text_adapter = clone_adapter_as_oracle(pv.PhotoVerseAdapter(num_tokens=T)).eval()
-    inp = synthetic_inputs(1, latent, seed=0, dtype=torch.float32)
+    inp = synthetic_inputs(batch, latent, seed=0, dtype=torch.float32)
     sched = make_ddim_schedule(denoise_steps)
     t_ad, t_step = [], []
     with torch.no_grad():
@@ -283,34 +354,37 @@ def cpu_reference_run(steps, warmup, denoise_steps, latent, token_index, T=5):
                 t_ad.append(t1 - t0)
                 t_step.append(t2 - t1)
     ad, st = statistics.mean(t_ad), statistics.mean(t_step)
-    per_image_s = ad + denoise_steps * st
-    return {"images_per_s": 1.0 / per_image_s, "cores": cores, "adapter_s": ad, "denoise_step_s": st,
-            "sample": f"1 image: adapters once + 1 of {denoise_steps} DDIM steps (uncond+cond UNet evaluation), fp32, "
-                      f"extrapolated as adapters + {denoise_steps} x step; mean of {steps} after {warmup} warm-up"}
+    per_batch_s = ad + denoise_steps * st
+    return {"images_per_s": batch / per_batch_s, "cores": cores, "adapter_s": ad, "denoise_step_s": st, "batch": batch,
+            "sample": f"batch {batch} (the benchmarked batch): adapters once + 1 of {denoise_steps} DDIM steps (uncond + cond "
+                      f"UNet evaluations), fp32, {cores} threads; generation time taken as adapters + {denoise_steps} x step; "
+                      f"mean of {steps} after {warmup} warm-up"}
 
 
-def run_train(args, rank, world, local_rank):
-    """BASELINE config[3]: one training step = adapters + UNet forward in grad mode (16 processors, stochastic fusion),
-    backward into the trainable set {adapters, to_k_ip/to_v_ip, LoRA A/B}, ONE flat-buffer NCCL allreduce, per-group
-    clipping, AdamW.  bf16 backbone, fp32 masters for the trainable set.  Weak scaling: batch per GPU fixed."""
+def train_leg(args, rank, world, device, lora_rank, steps, warmup, lora_dropout=0.0):
+    """BASELINE config[3]: one training step = text / image adapters (5 heads) -> CLIP text tower with the concept
+    embeddings injected (train.py:495-499) -> UNet forward in grad mode (16 processors, stochastic fusion) -> backward
+    into the trainable set {adapters, to_k_ip / to_v_ip, LoRA A/B}, bucketed NCCL allreduce launched under the backward
+    pass, per-group clipping, AdamW.  bf16 backbone, fp32 masters for the trainable set.  Weak scaling: batch per GPU
+    fixed.  Returns the sub-record (rank 0) -- timing = CUDA events, max over ranks."""
     import torch.distributed as dist
     import photoverse_b200 as pv
     from photoverse_b200 import _lib
+    from photoverse_b200.host.text_encoder import ConceptTextEncoder
     from photoverse_b200.host.train_step import Trainer, synthetic_train_batch
     from photoverse_b200.host.unet_sd15 import UNetSD15
     from photoverse_b200.lora import inject_lora
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)
     unet = UNetSD15()
     pv.set_visual_cross_attention_adapter(unet, num_tokens=(5,))
     ia, ta = pv.PhotoVerseAdapter(num_tokens=5), pv.PhotoVerseAdapter(num_tokens=5)
+    te = ConceptTextEncoder()
     unet.requires_grad_(False)
-    inject_lora(unet, r=args.lora_rank, lora_dropout=args.lora_dropout)
+    te.requires_grad_(False)
+    inject_lora(unet, r=lora_rank, lora_dropout=lora_dropout)
     unet.to(device=device, dtype=torch.bfloat16).to(memory_format=torch.channels_last)
+    te.to(device=device, dtype=torch.bfloat16).eval()
     for m in (ia, ta):
         m.to(device)
     for n, p in unet.named_parameters():
@@ -318,9 +392,9 @@ def run_train(args, rank, world, local_rank):
             p.data = p.data.float()                       # fp32 masters for the trainable set
             p.requires_grad_(True)
     unet.eval()
-    if args.lora_dropout > 0:
+    if lora_dropout > 0:
         pv.unet.set_cross_attention_layers_to_train(unet)     # train.py:462 (activates the LoRA dropout)
-    tr = Trainer(unet, ia, ta)
+    tr = Trainer(unet, ia, ta, text_encoder=te)
     b = synthetic_train_batch(args.train_batch, args.latent, seed=100 + rank, device=device, dtype=torch.bfloat16)
 
     def barrier():
@@ -329,37 +403,112 @@ def run_train(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     torch.manual_seed(1000 + rank)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         tr.step(b)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(device.index or 0)
     sampler.start()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    overlapped = 0
     e0.record()
-    for _ in range(args.steps):
+    for k in range(steps):
+        tr.reducer_events = ar[k]          # Trainer.step brackets reducer.finish() (the exposed part of the allreduce)
         loss, _ = tr.step(b)
+        overlapped += tr.buckets_overlapped
     e1.record()
     barrier()
     clocks = sampler.stop()
+    exposed = sum(a.elapsed_time(b_) for a, b_ in ar) / steps
+    t = torch.tensor([e0.elapsed_time(e1), exposed], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, exposed = t.tolist()
+    rec = {"metric": "training samples/s, adapter + LoRA + to_k_ip/to_v_ip step through dual-branch attention (config[3])",
+           "value": round(args.train_batch * world * steps / (ms * 1e-3), 3), "unit": "samples/s", "n_gpus": world,
+           "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 3), "scaling": "weak", "dtype": "bf16",
+           "lora_rank": lora_rank, "lora_dropout": lora_dropout, "batch_per_gpu": args.train_batch, "latent": args.latent,
+           "grad_elements": tr.buf.numel(), "allreduce": "bucketed slices of one flat fp32 buffer (+ touched flags), launched from "
+           "autograd hooks under the backward pass; NCCL sum, / world",
+           "allreduce_exposed_ms": round(exposed, 3), "buckets": len(tr.reducer.buckets),
+           "buckets_launched_under_backward_per_step": round(overlapped / steps, 2),
+           "text_encoder": "12-layer CLIP text tower with concept-token injection (train.py:495-499)",
+           "gpu_launches": int(_lib.launch_count() - n0), "clocks": clocks, "final_loss": round(float(loss), 5)}
+    del tr, unet, ia, ta, te, b
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_train(args, rank, world, local_rank):
+    """`--workload train`: config[3] as the whole job (one JSON line)."""
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    rec = train_leg(args, rank, world, device, args.lora_rank, args.steps, args.warmup, args.lora_dropout)
+    if rank == 0:
+        rec.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic",
+                    "config": {"workload": f"config[3]: training step, batch {args.train_batch}/GPU, latent {args.latent}^2, Li=5, "
+                                           f"LoRA r={args.lora_rank} (dropout {args.lora_dropout}) on attn2.to_q/k/v, fwd+bwd through 16 "
+                                           f"processors + 2 adapters + CLIP text tower, overlapped NCCL allreduce of "
+                                           f"{rec['grad_elements']} fp32 gradients, per-group clip, AdamW",
+                               "batch_per_gpu": args.train_batch, "grad_elements": rec["grad_elements"]}})
+        print(json.dumps(rec), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def shard_inputs(global_batch, world, rank, latent, dtype):
+    """Pinned host inputs of this rank's shard; every sample is drawn from its GLOBAL index (sample_seeds), so the
+    generated latents do not depend on the number of ranks."""
+    from photoverse_b200.host.parallel import sample_seeds
+    from photoverse_b200.host.pipeline import GenInputs, synthetic_inputs
+    parts = [synthetic_inputs(1, latent, seed=sd, dtype=dtype) for sd in sample_seeds(100, global_batch, world, rank)]
+    cat = lambda ts: torch.cat(ts).contiguous().pin_memory()
+    T = len(parts[0].clip_hidden)
+    return GenInputs([cat([p.clip_hidden[k] for p in parts]) for k in range(T)],
+                     [cat([p.clip_hidden_uncond[k] for p in parts]) for k in range(T)],
+                     cat([p.text for p in parts]), cat([p.text_uncond for p in parts]), cat([p.noise for p in parts]))
+
+
+def cfg3_leg(args, rank, world, device, models, token_index):
+    """BASELINE config[2]: classifier-free guidance 7.5, GLOBAL batch 64 (128 UNet rows per step) sharded over the N
+    GPUs -- strong scaling, no collective in the loop.  One warm-up + one timed generation."""
+    import torch.distributed as dist
+    from photoverse_b200.host.pipeline import GenerationEngine
+    from photoverse_b200.host.parallel import shard_range
+    gb = 64
+    b0, b1 = shard_range(gb, world, rank)
+    unet, image_adapter, text_adapter = models
+    eng = GenerationEngine(unet, image_adapter, text_adapter, b1 - b0, args.latent, args.denoise_steps, 7.5, token_index,
+                           "batched", torch.bfloat16, device)
+    host = shard_inputs(gb, world, rank, args.latent, torch.bfloat16)
+    eng.load_inputs(host)
+    eng.generate()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lat = eng.generate()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
-    if rank == 0:
-        line = {"metric": "training samples/s, adapter + LoRA + to_k_ip/to_v_ip step through dual-branch attention (config[3])",
-                "value": round(args.train_batch * world * args.steps / (ms * 1e-3), 3), "unit": "samples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"config[3]: training step, batch {args.train_batch}/GPU, latent {args.latent}^2, Li=5, LoRA r="
-                                       f"{args.lora_rank} (dropout {args.lora_dropout}) on attn2.to_q/k/v, fwd+bwd through 16 processors + 2 adapters, flat-buffer "
-                                       f"NCCL allreduce of {tr.buf.numel()} fp32 gradients, per-group clip, AdamW",
-                           "batch_per_gpu": args.train_batch, "grad_elements": tr.buf.numel()},
-                "gpu_launches": int(_lib.launch_count() - n0), "clocks": clocks, "final_loss": round(float(loss), 5)}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    finite = bool(torch.isfinite(lat.float()).all().item())
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    return {"workload": "config[2]: CFG guidance 7.5, global batch 64 (doubled to 128 UNet rows), 50-step DDIM, sharded "
+                        f"{gb // world} per GPU", "value": round(gb / (ms * 1e-3), 4), "unit": "images/s", "scaling": "strong",
+            "global_batch": gb, "n_gpus": world, "ms_per_generation": round(ms, 2), "timed_generations": 1, "finite_output": finite}
 
 
 def main():
@@ -381,7 +530,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_run(args.steps, args.warmup, args.denoise_steps, args.latent, token_index)
+        r = cpu_reference_run(args.steps, args.warmup, args.denoise_steps, args.latent, token_index, args.batch)
+        config["cpu_sample_batch"] = r["batch"]
         line = {"impl": "reference", "metric": METRIC, "value": round(r["images_per_s"], 6), "unit": "images/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round((r["adapter_s"] + r["denoise_step_s"]) * 1e3, 3), "higher_is_better": True,
@@ -411,15 +561,15 @@ def main():
     # ---- CPU baseline (rank 0, N == 1 only) before the GPU section ----
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(2, 1, args.denoise_steps, args.latent, token_index)
+        r = cpu_reference_run(1, 1, args.denoise_steps, args.latent, token_index, args.batch)
         cpu_base = {"value": round(r["images_per_s"], 6), "unit": "images/s", "cores": r["cores"], "kind": "port",
-                    "sample": r["sample"], "denoise_step_s": round(r["denoise_step_s"], 3)}
+                    "sample": r["sample"], "denoise_step_s": round(r["denoise_step_s"], 3), "batch": r["batch"]}
 
     dtype = torch.bfloat16
     unet, image_adapter, text_adapter = build_models(device, dtype, channels_last=not args.nchw)
     eng = GenerationEngine(unet, image_adapter, text_adapter, args.batch, args.latent, args.denoise_steps, 1.0,
                            token_index, args.mode, dtype, device, use_cuda_graph=not args.no_graph)
-    host = pinned_inputs(args.batch, args.latent, seed=100 + rank, dtype=dtype)
+    host = shard_inputs(args.batch * world, world, rank, args.latent, dtype)       # per-sample seeds by GLOBAL index
     h2d = host.nbytes()
     out_host = torch.empty(args.batch, 4, args.latent, args.latent, dtype=dtype).pin_memory()
     d2h = out_host.numel() * out_host.element_size()
@@ -441,6 +591,7 @@ def main():
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = (_lib.launch_count() - n0) + (eng.replays - r0) * eng.launches_per_eval
+    native_per_eval = eng.launches_per_eval
     finite = bool(torch.isfinite(lat.float()).all().item())
 
     # ---- end-to-end leg: host buffers in, host latents out, copies inside the timed region ----
@@ -472,6 +623,16 @@ def main():
         roof["processor_share_of_step"] = round(per_gen_proc_ms / (ms / args.steps), 4)
     if world > 1:
         dist.barrier()
+    # ---- sub-records: config[2] strong scaling (N >= 2) and config[3] training (every N) ----
+    cfg3 = None
+    if world > 1 and not args.no_cfg3_leg:
+        cfg3 = cfg3_leg(args, rank, world, device, (unet, image_adapter, text_adapter), token_index)
+    eng.close()
+    del eng, unet, image_adapter, text_adapter
+    torch.cuda.empty_cache()
+    train = None
+    if not args.no_train_leg:
+        train = {f"lora_r{r}": train_leg(args, rank, world, device, r, args.train_steps, 3) for r in (8, 128)}
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
@@ -480,7 +641,7 @@ def main():
                 "e2e": {"value": round(e2e_value, 4), "unit": "images/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
                 "gpu_launches": int(launches), "clocks": clocks, "finite_output": finite,
-                "native_kernels_per_unet_eval": eng.launches_per_eval}
+                "native_kernels_per_unet_eval": native_per_eval, "train": train, "cfg3": cfg3}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

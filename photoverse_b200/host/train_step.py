@@ -107,7 +107,13 @@ class Trainer:
             loss, parts = self.loss(b)
         self.reducer.begin(self.expected_gradients())
         loss.backward()                                                               # :538
+        ev = getattr(self, "reducer_events", None)        # bench: the exposed (not overlapped) part of the allreduce
+        if ev is not None:
+            ev[0].record()
         self.buckets_overlapped = self.reducer.finish()                               # mean over ranks in the flat buffer
+        if ev is not None:
+            ev[1].record()
+            self.reducer_events = None
         self.buf.clip_groups_(self.GROUPS, max_grad_norm)                             # :541-544
         self.buf.unpack()
         self.opt.step()                                                               # :547

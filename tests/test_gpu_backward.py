@@ -85,6 +85,75 @@ def test_processor_backward_matches_oracle_autograd(cuda_device, case, dtype):
         assert e <= REL[dtype], f"{k}: relative error {e:.3e} > {REL[dtype]}"
 
 
+def _oracle_grads_on(device, dtype, case, x, text, img, gy, gv, wt, wi):
+    """The same checker evaluated on ``device`` in ``dtype`` (fp32 on the GPU for the full-size shapes, where the CPU
+    fp64 run would take minutes)."""
+    w = cases.proc_weights(case, dtype).to(device=device)
+    leaves = {k: t.to(device, dtype).clone().requires_grad_(True) for k, t in (("x", x), ("text", text), ("img", img))}
+    w.to_k_ip.requires_grad_(True)
+    w.to_v_ip.requires_grad_(True)
+    for lw in w.lora.values():
+        lw.A.requires_grad_(True)
+        lw.B.requires_grad_(True)
+    y, vn = dual_branch_attention(leaves["x"], leaves["text"], leaves["img"], w, wt, wi, None)
+    ((y * gy.to(device, dtype)).sum() + (vn.squeeze(-1) * gv.to(device, dtype)).sum()).backward()
+    out = {k: v.grad for k, v in leaves.items()}
+    out["to_k_ip"], out["to_v_ip"] = w.to_k_ip.grad, w.to_v_ip.grad
+    for name, lw in w.lora.items():
+        out[name + ".A"], out[name + ".B"] = lw.A.grad, lw.B.grad
+    return y.detach(), vn.detach(), out
+
+
+@pytest.mark.parametrize("case", [
+    cases.ProcCase("bwd_full_c320", B=16, S=4096, C=320, Li=5, lora_r=8, seed=91),          # BASELINE config[3] layer shapes:
+    cases.ProcCase("bwd_full_c640", B=16, S=1024, C=640, Li=5, lora_r=8, seed=92),          # batch 16 per GPU, latent 64^2
+    cases.ProcCase("bwd_full_c1280", B=16, S=256, C=1280, Li=5, lora_r=8, seed=93),
+    cases.ProcCase("bwd_full_mid", B=16, S=64, C=1280, Li=5, lora_r=8, seed=94),
+    cases.ProcCase("bwd_r128_c320", B=4, S=4096, C=320, Li=5, lora_r=128, seed=95),         # the shipped recipe's LoRA rank
+    cases.ProcCase("bwd_r128_c1280_textonly", B=4, S=256, C=1280, Li=5, lora_r=128, w_text=2.0, w_img=0.0, seed=96),
+    cases.ProcCase("bwd_r128_c640_imgonly", B=4, S=1024, C=640, Li=5, lora_r=128, w_text=0.0, w_img=2.0, seed=97),
+], ids=lambda c: c.name)
+def test_processor_backward_full_size_bf16(cuda_device, case):
+    """Forward + every gradient at the REAL training shapes (config[3]: B = 16 per GPU, the four attn2 layer shapes at
+    latent 64^2; LoRA rank 8 and the shipped recipe's rank 128, prepare_dataset_and_train.sh:2) in bf16, against autograd
+    through the oracle evaluated in fp32 on the GPU."""
+    dtype = torch.bfloat16
+    attn, proc = build_product_layer(case, cuda_device)
+    for p in attn.parameters():
+        p.requires_grad_(False)
+    trainable = {"to_k_ip": proc.to_k_ip[0].weight, "to_v_ip": proc.to_v_ip[0].weight}
+    for name in ("to_q", "to_k", "to_v"):
+        m = getattr(attn, name)
+        trainable[name + ".A"] = m.lora_A["default"].weight
+        trainable[name + ".B"] = m.lora_B["default"].weight
+    for p in trainable.values():
+        p.requires_grad_(True)
+    x, text, img = cases.proc_inputs(case, torch.float32)
+    g = torch.Generator().manual_seed(case.seed)
+    gy = torch.randn(case.B, case.S, case.C, generator=g)
+    gv = torch.randn(case.B, case.H, case.Li, generator=g)
+    xd, td, im = (t.to(cuda_device, dtype).requires_grad_(True) for t in (x, text, img))
+    force_fusion_seed(case.w_text, case.w_img)
+    with torch.enable_grad():
+        y = attn(xd, encoder_hidden_states=(td, im))
+        assert proc.last_fusion == (case.w_text, case.w_img)
+        vn = proc.to_v_ip_norm
+        loss = (y.float() * gy.to(cuda_device)).sum() + (vn.float().squeeze(-1) * gv.to(cuda_device)).sum()
+    loss.backward()
+    y_ref, vn_ref, ref = _oracle_grads_on(cuda_device, torch.float32, case, x, text, img, gy, gv, case.w_text, case.w_img)
+    assert (y.detach().float() - y_ref).abs().max().item() <= 2e-2
+    assert _rel(vn.float().squeeze(-1), vn_ref.squeeze(-1)) <= 1e-2
+    got = {"x": xd.grad, "text": td.grad, "img": im.grad}
+    got.update({k: p.grad for k, p in trainable.items()})
+    for k, r in ref.items():
+        if r is None or r.abs().max() == 0:
+            assert got[k] is None or got[k].abs().max().item() <= 1e-6, k
+            continue
+        assert got[k] is not None, f"no gradient for {k}"
+        e = _rel(got[k], r)
+        assert e <= REL[dtype], f"{k}: relative error {e:.3e} > {REL[dtype]}"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("case", [
     cases.ProcCase("drop_c320", B=2, S=200, C=320, Li=5, lora_r=8, seed=76),

@@ -24,25 +24,29 @@ def _cos(a, b):
     return torch.nn.functional.cosine_similarity(a, b, dim=1).min().item()
 
 
-@pytest.mark.parametrize("dtype,mode,token_index", [(torch.bfloat16, "batched", 0), (torch.float32, "two_call", "full")],
-                         ids=["bf16-batched-idx0", "f32-two_call-full"])
-def test_final_latent_cosine_50_steps(cuda_device, dtype, mode, token_index):
+@pytest.mark.parametrize("dtype,mode,token_index,batch,guidance", [
+    (torch.bfloat16, "batched", 0, 1, 1.0), (torch.float32, "two_call", "full", 1, 1.0),
+    (torch.bfloat16, "batched", 0, 8, 1.0),          # BASELINE config[1]: batch 8, guidance 1.0
+    (torch.bfloat16, "batched", 0, 2, 7.5),          # BASELINE config[2]: classifier-free guidance 7.5 (doubled batch)
+], ids=["bf16-batched-idx0", "f32-two_call-full", "bf16-batch8-config1", "bf16-cfg7.5-config2"])
+def test_final_latent_cosine_50_steps(cuda_device, dtype, mode, token_index, batch, guidance):
     from oracle.host_reference import clone_adapter_as_oracle, clone_with_oracle_processors
     from photoverse_b200.host.pipeline import run_generation, synthetic_inputs
     unet, ia, ta = _models(cuda_device, dtype)
     ref_unet = clone_with_oracle_processors(unet)
     ref_ia, ref_ta = clone_adapter_as_oracle(ia, cuda_device, dtype), clone_adapter_as_oracle(ta, cuda_device, dtype)
-    inp = synthetic_inputs(1, 64, seed=5, device=cuda_device, dtype=dtype)
-    lat, aux = run_generation(unet, ia, ta, inp, num_steps=50, guidance_scale=1.0, token_index=token_index, mode=mode,
+    inp = synthetic_inputs(batch, 64, seed=5, device=cuda_device, dtype=dtype)
+    lat, aux = run_generation(unet, ia, ta, inp, num_steps=50, guidance_scale=guidance, token_index=token_index, mode=mode,
                               use_cuda_graph=(dtype == torch.bfloat16), return_aux=True)
     # the reference arm always makes two UNet calls per step (infer.py:103-114)
-    ref, ref_aux = run_generation(ref_unet, ref_ia, ref_ta, inp, num_steps=50, guidance_scale=1.0,
+    ref, ref_aux = run_generation(ref_unet, ref_ia, ref_ta, inp, num_steps=50, guidance_scale=guidance,
                                   token_index=token_index, mode="two_call", use_cuda_graph=False, kv_cache=False,
                                   return_aux=True)
     assert torch.isfinite(lat.float()).all()
     c_img = _cos(aux["img_tokens"], ref_aux["img_tokens"])
     c = _cos(lat, ref)
-    print(f"final-latent cosine {c:.6f}  adapter-token cosine {c_img:.6f} ({dtype}, {mode})")
+    print(f"final-latent cosine (min over the {batch} samples) {c:.6f}  adapter-token cosine {c_img:.6f} ({dtype}, {mode}, "
+          f"guidance {guidance})")
     assert c_img >= 0.999
     assert c >= 0.999, f"final-latent cosine {c}"
 
