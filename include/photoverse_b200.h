@@ -157,6 +157,16 @@ int64_t pv_linear_bwd_weight_ws_bytes(pv_dtype dt, int64_t M, int64_t N, int64_t
 int pv_linear_bwd_weight(pv_dtype dt, const void* G, const void* X, float* dW, void* ws, int64_t M, int64_t N, int64_t K,
                          int64_t ldg, int64_t ldx, float alpha, float beta, void* stream);
 
+/* Both LoRA factor gradients of one projection y = W x + scaling * B (A x) (peft 0.10.0 lora.Linear; train.py:348-354) in
+ * one pass over the activations:  dA = scaling * (G B)^T X  [r,in],  dB = scaling * G^T (X A^T)  [out,r],
+ * X:[M,in] (row stride ldx), G = dL/dy:[M,out] (ldg) in dt; lora_A:[r,in], lora_B:[out,r] fp32 masters;
+ * dAB: fp32 [r*in + out*r] = dA then dB.  1 <= r <= 16 and in, out <= 1280: pv_lora_bwd_ws_bytes returns the workspace
+ * size, or -1 when the shape is outside the kernel (rank 128: use pv_linear_fwd + pv_linear_bwd_weight).
+ * Deterministic (per-block partials summed in a fixed order).                                                        */
+int64_t pv_lora_bwd_ws_bytes(int64_t M, int in_features, int out_features, int r);
+int pv_lora_bwd(pv_dtype dt, const void* X, const void* G, const float* lora_A, const float* lora_B, float scaling, float* dAB,
+                void* ws, int64_t M, int in_features, int out_features, int r, int64_t ldx, int64_t ldg, void* stream);
+
 /* out[n] = sum_m G[m,n]  (bias gradients) */
 int64_t pv_col_sum_ws_bytes(int64_t M, int64_t N);
 int pv_col_sum(pv_dtype dt, const void* G, float* out, void* ws, int64_t M, int64_t N, int64_t ldg, void* stream);

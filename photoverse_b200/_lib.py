@@ -42,6 +42,9 @@ _SIGNATURES = {
     "pv_transpose_2d": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "pv_linear_bwd_weight_ws_bytes": (c_int64, [c_int, c_int64, c_int64, c_int64]),
     "pv_linear_bwd_weight": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 5 + [c_float, c_float, c_void_p]),
+    "pv_lora_bwd_ws_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "pv_lora_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                            c_int64, c_int64, c_void_p]),
     "pv_col_sum_ws_bytes": (c_int64, [c_int64, c_int64]),
     "pv_col_sum": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "pv_ln_lrelu_bwd_ws_bytes": (c_int64, [c_int64, c_int64, c_int]),

@@ -111,6 +111,9 @@ class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):
 
     # ------------------------------------------------------------------------------------------
     def _weights(self, attn, dtype, device):
+        """Packed weights of this layer in the compute dtype, LoRA merged (W + s B A).  Each of the four operands is
+        re-packed only when one of ITS OWN sources changed (parameter version counters): in training the optimizer
+        touches the LoRA factors and to_k_ip / to_v_ip every step, the frozen out projection never."""
         wq, qa, qb, qs, qp = linear_parts(attn.to_q)
         wk, ka, kb, ks, kp = linear_parts(attn.to_k)
         wv, va, vb, vs, vp = linear_parts(attn.to_v)
@@ -118,33 +121,53 @@ class PhotoVerseAttnProcessor2_0(PhotoVerseAttnProcessor):
             raise RuntimeError("internal: merged weights requested while LoRA dropout is active")
         wo, bo = attn.to_out[0].weight, attn.to_out[0].bias
         kip, vip = self.to_k_ip[0].weight, self.to_v_ip[0].weight
-        tensors = [wq, qa, qb, wk, ka, kb, wv, va, vb, wo, bo, kip, vip]
-        key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors) + (qs, ks, vs)
+
+        def vkey(tensors, *scal):
+            return tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors) + scal
+
+        keys = {"wq": vkey([wq, qa, qb], qs), "wkv_text": vkey([wk, ka, kb, wv, va, vb], ks, vs),
+                "wkv_img": vkey([kip, vip]), "wo": vkey([wo, bo])}
         pk = self._packed.get(dtype)
-        if pk is not None and pk.key == key:
+        if pk is not None and pk.key == keys:
             return pk
         C, Dc = wq.shape[0], wk.shape[1]
-        for t in tensors:
+        for t in (wq, qa, qb, wk, ka, kb, wv, va, vb, wo, bo, kip, vip):
             if t is not None and not t.is_cuda:
                 raise RuntimeError(f"photoverse_b200 needs its weights on the CUDA device (got {t.device})")
 
         def m(t):   # fp32 master view of a parameter (a cast happens only if the module was .to(bf16)'d)
             return None if t is None else t.detach().float().contiguous()
 
+        old = pk.key if pk is not None else {}
         with torch.no_grad():
-            pk = _PackedWeights()
-            pk.key = key
-            pk.wq = ops.pack_weight(m(wq), torch.empty(C, C, device=device, dtype=dtype), m(qa), m(qb), qs)
-            pk.wkv_text = torch.empty(2 * C, Dc, device=device, dtype=dtype)
-            ops.pack_weight(m(wk), pk.wkv_text[:C], m(ka), m(kb), ks)
-            ops.pack_weight(m(wv), pk.wkv_text[C:], m(va), m(vb), vs)
-            pk.wkv_img = torch.empty(2 * C, Dc, device=device, dtype=dtype)
-            ops.pack_weight(m(kip), pk.wkv_img[:C])
-            ops.pack_weight(m(vip), pk.wkv_img[C:])
-            pk.wo = ops.pack_weight(m(wo), torch.empty(C, C, device=device, dtype=dtype))
-            pk.bo = m(bo) if bo is not None else torch.zeros(C, device=device, dtype=torch.float32)
+            if pk is None:
+                pk = _PackedWeights()
+                pk._t = {}
+            else:                      # a NEW object per key set: autograd contexts of earlier calls keep the old one
+                npk = _PackedWeights()
+                npk.wq, npk.wkv_text, npk.wkv_img, npk.wo, npk.bo = pk.wq, pk.wkv_text, pk.wkv_img, pk.wo, pk.bo
+                npk._t = dict(pk._t)
+                pk = npk
+            if old.get("wq") != keys["wq"]:
+                pk.wq = ops.pack_weight(m(wq), torch.empty(C, C, device=device, dtype=dtype), m(qa), m(qb), qs)
+                pk._t.pop("wq_t", None)
+            if old.get("wkv_text") != keys["wkv_text"]:
+                pk.wkv_text = torch.empty(2 * C, Dc, device=device, dtype=dtype)
+                ops.pack_weight(m(wk), pk.wkv_text[:C], m(ka), m(kb), ks)
+                ops.pack_weight(m(wv), pk.wkv_text[C:], m(va), m(vb), vs)
+                pk._t.pop("wkv_text_t", None)
+            if old.get("wkv_img") != keys["wkv_img"]:
+                pk.wkv_img = torch.empty(2 * C, Dc, device=device, dtype=dtype)
+                ops.pack_weight(m(kip), pk.wkv_img[:C])
+                ops.pack_weight(m(vip), pk.wkv_img[C:])
+                pk._t.pop("wkv_img_t", None)
+            if old.get("wo") != keys["wo"]:
+                pk.wo = ops.pack_weight(m(wo), torch.empty(C, C, device=device, dtype=dtype))
+                pk.bo = m(bo) if bo is not None else torch.zeros(C, device=device, dtype=torch.float32)
+                pk._t.pop("wo_t", None)
+            pk.key = keys
         self._packed[dtype] = pk
-        if self._kv_cache is not None:
+        if self._kv_cache is not None and (old.get("wkv_text") != keys["wkv_text"] or old.get("wkv_img") != keys["wkv_img"]):
             self._kv_cache.clear()
         return pk
 

@@ -93,9 +93,12 @@ class _DualAttnFn(torch.autograd.Function):
         dx = ops.linear(dq2, tw["wq_t"]).view(B, S, C) if need[0] else None              # dX = dQ Wq
         dtext = ops.linear(dkv_text, tw["wkv_text_t"]).view(B, Lt, Dc) if need[1] else None
         dimg = ops.linear(dkv_img, tw["wkv_img_t"]).view(B, Li, Dc) if need[2] else None
-        # to_k_ip / to_v_ip : dW = dK_img^T img, dV_img^T img
-        dkip = ops.linear_bwd_weight(dkv_img[:, :C], img2) if need[3] else None
-        dvip = ops.linear_bwd_weight(dkv_img[:, C:], img2) if need[4] else None
+        # to_k_ip / to_v_ip : [dK_img | dV_img]^T img in one weight-gradient call -> rows [0, C) / [C, 2C)
+        dkip = dvip = None
+        if need[3] or need[4]:
+            dkv_w = ops.linear_bwd_weight(dkv_img, img2)                     # [2C, Dc]
+            dkip = dkv_w[:C] if need[3] else None
+            dvip = dkv_w[C:] if need[4] else None
         # LoRA factors: y = W x + s B (A x)  ->  dB = s dY^T (x A^T),  dA = s (dY B)^T x
         grads = [None] * 6
         it = iter(lora)
@@ -104,6 +107,13 @@ class _DualAttnFn(torch.autograd.Function):
             if not ctx.has[j]:
                 continue
             A, Bm = next(it), next(it)
+            if j > 0 and meta["w_text"] == 0.0:
+                continue                                                     # text branch dropped: no gradient (see below)
+            if need[5 + 2 * j] and need[5 + 2 * j + 1]:
+                fused = ops.lora_bwd(inp, g, A, Bm, s)                       # both factors, one pass over x and dY (rank <= 16)
+                if fused is not None:
+                    grads[2 * j], grads[2 * j + 1] = fused[0].to(A.dtype), fused[1].to(Bm.dtype)
+                    continue
             a_c = A.detach().to(dtype).contiguous()                          # [r, in]
             bt_c = ops.transpose(Bm.detach().to(dtype).contiguous())         # [r, out]
             if need[5 + 2 * j + 1]:
@@ -270,12 +280,12 @@ class _DualAttnDropoutFn(torch.autograd.Function):
 
 
 def _transposed(pk, dtype):
-    """Transposed copies of the packed forward weights (the weights of the input-gradient GEMMs), cached on the pack."""
-    tw = getattr(pk, "_t", None)
-    if tw is None:
-        tw = {"wq_t": ops.transpose(pk.wq), "wo_t": ops.transpose(pk.wo),
-              "wkv_text_t": ops.transpose(pk.wkv_text), "wkv_img_t": ops.transpose(pk.wkv_img)}
-        pk._t = tw
+    """Transposed copies of the packed forward weights (the weights of the input-gradient GEMMs), cached per operand on the
+    pack: the processor drops an entry when it re-packs that operand (attention_processor._weights)."""
+    tw = pk._t
+    for name in ("wq", "wo", "wkv_text", "wkv_img"):
+        if name + "_t" not in tw:
+            tw[name + "_t"] = ops.transpose(getattr(pk, name))
     return tw
 
 

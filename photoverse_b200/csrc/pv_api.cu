@@ -55,6 +55,11 @@ int ln_lrelu_bwd(bool bf16, const void* da, const float* x, const float* mean, c
                  long long rows_per_group, int cols, float slope, cudaStream_t stream);
 int group_mean_bwd(bool bf16, const void* dy, void* dx, long long groups, int P, int cols, long long ldy, cudaStream_t stream);
 int attn_bwd_chunks(int S);
+bool lora_bwd_supported(int in_f, int out_f, int r);
+long long lora_bwd_ws_bytes(long long M, int in_f, int out_f, int r);
+int lora_bwd(bool bf16, const void* X, const void* G, const float* A, const float* Bm, float scaling, float* dAB, void* ws,
+             long long M, int in_f, int out_f, int r, long long ldx, long long ldg, cudaStream_t stream);
+int attn_bwd_chunks_used(bool bf16, int S, int d);
 int dual_attn_bwd(bool bf16, const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats,
                   void* dQ, float* part, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                   cudaStream_t stream);
@@ -379,6 +384,17 @@ int pv_linear_bwd_weight(pv_dtype dt, const void* G, const void* X, float* dW, v
   return linear_bwd_weight(dt == PV_BF16, G, X, dW, ws, M, N, K, ldg, ldx, alpha, beta, as_stream(stream));
 }
 
+int64_t pv_lora_bwd_ws_bytes(int64_t M, int in_features, int out_features, int r) {
+  if (M <= 0 || !lora_bwd_supported(in_features, out_features, r)) return -1;       // -1: use the GEMM route
+  return lora_bwd_ws_bytes(M, in_features, out_features, r);
+}
+
+int pv_lora_bwd(pv_dtype dt, const void* X, const void* G, const float* lora_A, const float* lora_B, float scaling, float* dAB,
+                void* ws, int64_t M, int in_features, int out_features, int r, int64_t ldx, int64_t ldg, void* stream) {
+  PV_REQUIRE(X && G && lora_A && lora_B && dAB, "null pointer");
+  return lora_bwd(dt == PV_BF16, X, G, lora_A, lora_B, scaling, dAB, ws, M, in_features, out_features, r, ldx, ldg, as_stream(stream));
+}
+
 int64_t pv_col_sum_ws_bytes(int64_t M, int64_t N) { return colsum_ws_bytes(M, N); }
 
 int pv_col_sum(pv_dtype dt, const void* G, float* out, void* ws, int64_t M, int64_t N, int64_t ldg, void* stream) {
@@ -420,7 +436,7 @@ int pv_kv_pack_bwd(pv_dtype dt, const void* ws, const float* kv_img, const float
                    void* dkv_text, void* dkv_img, int B, int S, int Lt, int Li, int C, int H, void* stream) {
   PV_REQUIRE(ws && kv_img && v_ip_norm && dkv_text && dkv_img, "null pointer");
   return kv_pack_bwd(dt == PV_BF16, static_cast<const float*>(ws), kv_img, v_ip_norm, d_v_ip_norm, dkv_text, dkv_img,
-                     attn_bwd_chunks(S), B, Lt, Li, C, H, as_stream(stream));
+                     attn_bwd_chunks_used(dt == PV_BF16, S, H > 0 ? C / H : 0), B, Lt, Li, C, H, as_stream(stream));
 }
 
 int pv_inject_concept_fwd(pv_dtype dt, const void* inputs_embeds, const void* concept, const int* placeholder_idx,

@@ -547,7 +547,14 @@ attn_bwd_kernel(const T* __restrict__ dO, const T* __restrict__ Q, const float* 
   }
 }
 
+int attn_bwd_mma_chunks(int S, int d);
+extern int g_opt_bwd_mma;
+// Query-row chunks whose dK / dV partials kv_bwd_reduce sums: 128-row blocks of the SIMT kernel, or the (longer) blocks of
+// the tensor-core kernel.  The workspace is sized for the finer split.
 int attn_bwd_chunks(int S) { return (S + AB_CHUNK - 1) / AB_CHUNK; }
+int attn_bwd_chunks_used(bool bf16, int S, int d) {
+  return (bf16 && g_opt_bwd_mma != 0) ? attn_bwd_mma_chunks(S, d) : attn_bwd_chunks(S);
+}
 
 template <int D, typename T>
 static int launch_attn_bwd(const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats,
@@ -568,7 +575,6 @@ static int launch_attn_bwd(const void* dO, const void* Q, const float* kv_text, 
 int dual_attn_bwd_mma(const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats, void* dQ,
                       float* part, int nchunk, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                       cudaStream_t stream);
-extern int g_opt_bwd_mma;
 
 int dual_attn_bwd(bool bf16, const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats,
                   void* dQ, float* part, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
@@ -577,7 +583,7 @@ int dual_attn_bwd(bool bf16, const void* dO, const void* Q, const float* kv_text
   PV_REQUIRE(Lt >= 1 && Li >= 1 && Lt + Li <= PV_KEYS_PAD, "need 1 <= Lt, 1 <= Li, Lt+Li <= %d", PV_KEYS_PAD);
   const int d = C / H;
   if (bf16 && g_opt_bwd_mma != 0)       // tensor-core kernel (pv_bwd_mma.cu); the SIMT kernel below is the fp32 parity path
-    return dual_attn_bwd_mma(dO, Q, kv_text, kv_img, stats, dQ, part, attn_bwd_chunks(S), B, S, C, H, Lt, Li, w_text, w_img, stream);
+    return dual_attn_bwd_mma(dO, Q, kv_text, kv_img, stats, dQ, part, attn_bwd_mma_chunks(S, d), B, S, C, H, Lt, Li, w_text, w_img, stream);
 #define PV_AB(DD)                                                                                                        \
   return bf16 ? launch_attn_bwd<DD, __nv_bfloat16>(dO, Q, kv_text, kv_img, stats, dQ, part, B, S, C, H, Lt, Li, w_text, w_img, stream) \
               : launch_attn_bwd<DD, float>(dO, Q, kv_text, kv_img, stats, dQ, part, B, S, C, H, Lt, Li, w_text, w_img, stream)

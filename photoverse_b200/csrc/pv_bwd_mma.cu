@@ -4,7 +4,10 @@
 // kernel's per-row statistics it produces dQ [B,S,C] and the per-chunk partial dK / dV that kv_bwd_reduce_kernel sums.
 //   p^ = 2^(s cs - m)/l per segment ; dp_k = dO.V_k ; delta_seg = sum_{k in seg} p^_k dp_k ; ds_k = w_seg p^_k (dp_k - delta_seg)
 //   dQ = scale ds K ; dK = scale ds^T Q ; dV = (w p^)^T dO
-// One block = 128 query rows of one (sample, head); 8 warps x 16 rows.  All five contractions are warp-level
+// One block = up to T consecutive 128-query-row tiles of one (sample, head) (T = 4 for head_dim 40 / 80 at S >= 2048, else
+// 2 / 1: attn_bwd_mma_tiles): K / V are staged once per block and dK / dV accumulate in registers across the tiles, so
+// the fp32 partials (82 x head_dim x 2 per block) cost T times less traffic than one block per tile; dQ leaves through
+// shared memory as 16-byte row segments.  8 warps x 16 rows per tile.  All five contractions are warp-level
 // mma.sync.m16n8k16 (bf16 in, fp32 accumulate) -- with 96 key slots the tiles are far too small for tcgen05 / TMEM to pay:
 //   phase 1 (warp = 16 query rows): S = Q K^T and dP = dO V^T (B operands straight from the [key][dim] tiles), softmax
 //            from the saved statistics, dS, dQ = dS K (dS re-used from its accumulator registers as the A operand, K via
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(256, 1)
 attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ Q,
                     const float* __restrict__ kv_text, const float* __restrict__ kv_img, const float* __restrict__ stats,
                     __nv_bfloat16* __restrict__ dQ, float* __restrict__ part, int B, int S, int C, int H, int Lt, int Li,
-                    float w_text, float w_img, float scale, float scale_log2e) {
+                    float w_text, float w_img, float scale, float scale_log2e, int tiles_per_block) {
   using Cfg = BwdMmaCfg<D>;
   constexpr int DP = Cfg::DP, PD = Cfg::PD, NT_D = Cfg::NT_D;
   extern __shared__ __align__(16) uint8_t smem_b[];
@@ -77,9 +80,14 @@ attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = Lt + Li;
   const int C2 = 2 * C;
-  const int q0 = chunk * BM_ROWS;
+  // dK / dV tiles of this warp, accumulated over the block's row tiles
+  float ak[Cfg::TPW][4], av[Cfg::TPW][4];
+#pragma unroll
+  for (int i = 0; i < Cfg::TPW; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { ak[i][e] = 0.f; av[i][e] = 0.f; }
 
-  // ---- stage K, V (fp32 projections -> bf16, the rounding the forward kernel's tiles have), Q, dO ----
+  // ---- stage K, V (fp32 projections -> bf16, the rounding the forward kernel's tiles have) once per block ----
   for (int i = threadIdx.x; i < BM_KEYS * (DP / 2); i += 256) {
     const int k = i / (DP / 2), c = (i - k * (DP / 2)) * 2;
     float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
@@ -92,6 +100,12 @@ attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* _
     *reinterpret_cast<uint32_t*>(Ks + k * PD + c) = pack_bf16x2(k0, k1);
     *reinterpret_cast<uint32_t*>(Vs + k * PD + c) = pack_bf16x2(v0, v1);
   }
+#pragma unroll 1
+  for (int tile_i = 0; tile_i < tiles_per_block; ++tile_i) {
+  const int q0 = (chunk * tiles_per_block + tile_i) * BM_ROWS;
+  if (q0 >= S) break;
+  if (tile_i > 0) __syncthreads();           // the previous tile's dQ copy-out still reads Qs
+  // ---- this tile's Q, dO ----
   for (int i = threadIdx.x; i < BM_ROWS * (DP / 8); i += 256) {
     const int r = i / (DP / 8), c = (i - r * (DP / 8)) * 8;
     uint4 qv = make_uint4(0u, 0u, 0u, 0u), ov = qv;
@@ -106,6 +120,7 @@ attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* _
   __syncthreads();
 
   // =============================== phase 1: this warp's 16 query rows ===============================
+  uint32_t dqr[NT_D / 2][4];                 // this thread's dQ fragments: [dim tile pair][row g | g + 8, dims 8 half + 2 t]
   {
     const int r0 = warp * 16;
     const int g = lane >> 2, t = lane & 3;
@@ -206,15 +221,11 @@ attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* _
         mma_bf16(acc0, dsr[2 * j][0], dsr[2 * j][1], dsr[2 * j + 1][0], dsr[2 * j + 1][1], b0, b1);
         mma_bf16(acc1, dsr[2 * j][0], dsr[2 * j][1], dsr[2 * j + 1][0], dsr[2 * j + 1][1], b2, b3);
       }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const float* a = half ? acc1 : acc0;
-        const int dim = n2 * 16 + half * 8 + 2 * t;
-        if (dim < D) {
-          if (row_a < S) *reinterpret_cast<uint32_t*>(dQ + (static_cast<size_t>(b) * S + row_a) * C + h * D + dim) = pack_bf16x2(a[0], a[1]);
-          if (row_b < S) *reinterpret_cast<uint32_t*>(dQ + (static_cast<size_t>(b) * S + row_b) * C + h * D + dim) = pack_bf16x2(a[2], a[3]);
-        }
-      }
+      // bf16 pairs, kept in registers until phase 2 has read Q: the tile then leaves through Qs as 16-byte segments
+      dqr[n2][0] = pack_bf16x2(acc0[0], acc0[1]);
+      dqr[n2][1] = pack_bf16x2(acc0[2], acc0[3]);
+      dqr[n2][2] = pack_bf16x2(acc1[0], acc1[1]);
+      dqr[n2][3] = pack_bf16x2(acc1[2], acc1[3]);
     }
   }
   __syncthreads();
@@ -222,8 +233,6 @@ attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* _
   // =============================== phase 2: dK = (scale ds)^T Q, dV = (w p^)^T dO ===============================
   {
     const int g = lane >> 2, t = lane & 3;
-    float* dstK = part + ((static_cast<size_t>(chunk) * B + b) * H + h) * 2 * L * D;
-    float* dstV = dstK + static_cast<size_t>(L) * D;
     // A (16 keys x 16 rows) = transposed load of the [row][key] tiles: matrix rows = rows 16 k + (lane & 7) + 8 (lane >> 4),
     // columns = keys 16 mt + 8 ((lane >> 3) & 1)
     const uint32_t a_off = ((lane & 7) + (lane >> 4) * 8) * BM_PKEY + ((lane >> 3) & 1) * 8;
@@ -234,7 +243,6 @@ attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* _
       const int tile = warp + 8 * i;
       if (tile < Cfg::TILES) {
         const int mt = tile / NT_D, nt = tile - mt * NT_D;
-        float ak[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
         const uint32_t da = smem_u32(Ds + a_off + mt * 16), pa = smem_u32(Ps + a_off + mt * 16);
         const uint32_t qb = smem_u32(Qs + b_off + nt * 8), ob = smem_u32(Os + b_off + nt * 8);
 #pragma unroll
@@ -244,24 +252,70 @@ attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* _
           ldsm_x4_t(pa + (k * 16 * BM_PKEY) * 2, p0, p1, p2, p3);
           ldsm_x2_t(qb + (k * 16 * PD) * 2, bq0, bq1);
           ldsm_x2_t(ob + (k * 16 * PD) * 2, bo0, bo1);
-          mma_bf16(ak, a0, a1, a2, a3, bq0, bq1);
-          mma_bf16(av, p0, p1, p2, p3, bo0, bo1);
+          mma_bf16(ak[i], a0, a1, a2, a3, bq0, bq1);
+          mma_bf16(av[i], p0, p1, p2, p3, bo0, bo1);
         }
+      }
+    }
+  }
+  __syncthreads();                            // phase 2 has read Qs: stage the dQ tile there
+  {
+    const int r0 = warp * 16;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int n2 = 0; n2 < NT_D / 2; ++n2) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int dim = n2 * 16 + half * 8 + 2 * t;
+        *reinterpret_cast<uint32_t*>(Qs + (r0 + g) * PD + dim) = dqr[n2][2 * half];
+        *reinterpret_cast<uint32_t*>(Qs + (r0 + g + 8) * PD + dim) = dqr[n2][2 * half + 1];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < BM_ROWS * (D / 8); i += 256) {
+    const int r = i / (D / 8), c = (i - r * (D / 8)) * 8;
+    if (q0 + r < S)
+      *reinterpret_cast<uint4*>(dQ + (static_cast<size_t>(b) * S + q0 + r) * C + h * D + c) = *reinterpret_cast<const uint4*>(Qs + r * PD + c);
+  }
+  }   // row tiles of this block
+
+  // ---- this block's dK / dV partials ----
+  {
+    const int g = lane >> 2, t = lane & 3;
+    float* dstK = part + ((static_cast<size_t>(chunk) * B + b) * H + h) * 2 * L * D;
+    float* dstV = dstK + static_cast<size_t>(L) * D;
+#pragma unroll
+    for (int i = 0; i < Cfg::TPW; ++i) {
+      const int tile = warp + 8 * i;
+      if (tile < Cfg::TILES) {
+        const int mt = tile / NT_D, nt = tile - mt * NT_D;
         const int key_a = mt * 16 + g, key_b = key_a + 8;
         const int dim = nt * 8 + 2 * t;
         if (dim < D) {
           if (key_a < L) {
-            *reinterpret_cast<float2*>(dstK + static_cast<size_t>(key_a) * D + dim) = make_float2(ak[0], ak[1]);
-            *reinterpret_cast<float2*>(dstV + static_cast<size_t>(key_a) * D + dim) = make_float2(av[0], av[1]);
+            *reinterpret_cast<float2*>(dstK + static_cast<size_t>(key_a) * D + dim) = make_float2(ak[i][0], ak[i][1]);
+            *reinterpret_cast<float2*>(dstV + static_cast<size_t>(key_a) * D + dim) = make_float2(av[i][0], av[i][1]);
           }
           if (key_b < L) {
-            *reinterpret_cast<float2*>(dstK + static_cast<size_t>(key_b) * D + dim) = make_float2(ak[2], ak[3]);
-            *reinterpret_cast<float2*>(dstV + static_cast<size_t>(key_b) * D + dim) = make_float2(av[2], av[3]);
+            *reinterpret_cast<float2*>(dstK + static_cast<size_t>(key_b) * D + dim) = make_float2(ak[i][2], ak[i][3]);
+            *reinterpret_cast<float2*>(dstV + static_cast<size_t>(key_b) * D + dim) = make_float2(av[i][2], av[i][3]);
           }
         }
       }
     }
   }
+}
+
+// 128-row tiles per block: the dK / dV accumulators of head_dim 160 (120 registers per thread) leave no room to carry them
+// next to phase 1's S / dP fragments, and its layers have S <= 576 anyway.
+int attn_bwd_mma_tiles(int S, int d) {
+  if (d > 80) return 1;
+  return S >= 2048 ? 4 : (S >= 512 ? 2 : 1);
+}
+int attn_bwd_mma_chunks(int S, int d) {
+  const int rows = BM_ROWS * attn_bwd_mma_tiles(S, d);
+  return (S + rows - 1) / rows;
 }
 
 template <int D>
@@ -274,17 +328,18 @@ static int launch_attn_bwd_mma(const void* dO, const void* Q, const float* kv_te
   const float scale = 1.f / sqrtf(static_cast<float>(D));
   kern<<<grid, 256, BwdMmaCfg<D>::SMEM_BYTES, stream>>>(static_cast<const __nv_bfloat16*>(dO), static_cast<const __nv_bfloat16*>(Q),
                                                        kv_text, kv_img, stats, static_cast<__nv_bfloat16*>(dQ), part, B, S, C, H,
-                                                       Lt, Li, w_text, w_img, scale, scale * 1.4426950408889634f);
+                                                       Lt, Li, w_text, w_img, scale, scale * 1.4426950408889634f,
+                                                       attn_bwd_mma_tiles(S, C / H));
   PV_LAUNCHED();
   return PV_OK;
 }
 
-// bf16 only; nchunk must be ceil(S / 128) (attn_bwd_chunks).  Needs 16-byte aligned Q / dO rows per head (C, head_dim % 8 == 0).
+// bf16 only; nchunk must be attn_bwd_mma_chunks(S, head_dim).  Needs 16-byte aligned Q / dO rows per head (C, head_dim % 8 == 0).
 int dual_attn_bwd_mma(const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats, void* dQ,
                       float* part, int nchunk, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
                       cudaStream_t stream) {
   const int d = C / H;
-  PV_REQUIRE(nchunk == (S + BM_ROWS - 1) / BM_ROWS, "chunk count mismatch (%d for S=%d)", nchunk, S);
+  PV_REQUIRE(nchunk == attn_bwd_mma_chunks(S, d), "chunk count mismatch (%d for S=%d)", nchunk, S);
   switch (d) {
     case 40: return launch_attn_bwd_mma<40>(dO, Q, kv_text, kv_img, stats, dQ, part, nchunk, B, S, C, H, Lt, Li, w_text, w_img, stream);
     case 80: return launch_attn_bwd_mma<80>(dO, Q, kv_text, kv_img, stats, dQ, part, nchunk, B, S, C, H, Lt, Li, w_text, w_img, stream);

@@ -171,7 +171,9 @@ class OverlappedGradReducer:
 
     def _make_hook(self, i):
         def hook(p):
-            if not self.active or self.seen[i]:
+            # an autograd Function that returns None for this parameter (a branch the fusion rule dropped) still
+            # runs the accumulate node, with nothing to accumulate
+            if not self.active or self.seen[i] or p.grad is None:
                 return
             self.buf.views[i].copy_(p.grad)
             self.seen[i] = True

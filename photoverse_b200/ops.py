@@ -254,6 +254,26 @@ def linear_bwd_weight(g: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tens
     return out
 
 
+def lora_bwd(x: torch.Tensor, g: torch.Tensor, lora_A: torch.Tensor, lora_B: torch.Tensor, scaling: float):
+    """(dA [r,in], dB [out,r]) fp32 of y = W x + scaling * B (A x), from x [M,in] and g = dL/dy [M,out] (row-strided ok),
+    in ONE pass (rank <= 16); returns None when the shape needs the tensor-core route."""
+    M, in_f = x.shape
+    out_f = g.shape[1]
+    r = lora_A.shape[0]
+    assert g.shape[0] == M and x.dtype == g.dtype and x.stride(1) == 1 and g.stride(1) == 1
+    assert lora_A.shape == (r, in_f) and lora_B.shape == (out_f, r)
+    lib = _lib.lib()
+    nbytes = int(lib.pv_lora_bwd_ws_bytes(M, in_f, out_f, r))
+    if nbytes < 0:
+        return None
+    a32, b32 = _f32(lora_A.detach().float().contiguous()), _f32(lora_B.detach().float().contiguous())
+    out = torch.empty(r * in_f + out_f * r, device=x.device, dtype=torch.float32)
+    ws = _workspace(nbytes, x.device)
+    check(lib.pv_lora_bwd(_dt(x), _ptr(x), _ptr(g), _ptr(a32), _ptr(b32), float(scaling), _ptr(out), _ptr(ws), M, in_f, out_f, r,
+                          x.stride(0), g.stride(0), _stream()), "pv_lora_bwd")
+    return out[:r * in_f].view(r, in_f), out[r * in_f:].view(out_f, r)
+
+
 def col_sum(g: torch.Tensor) -> torch.Tensor:
     M, N = g.shape
     assert g.stride(1) == 1

@@ -307,3 +307,31 @@ def test_tensor_core_backward_agrees_with_simt_backward(cuda_device):
     for k in grads[1]:
         e = _rel(grads[1][k], grads[0][k])
         assert e <= 2e-2, f"{k}: tensor-core vs SIMT backward relative difference {e:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("M,in_f,out_f,r", [(4096 + 7, 320, 320, 8), (1232, 768, 640, 8), (300, 1280, 1280, 4), (2048, 768, 1280, 16),
+                                            (65536, 320, 320, 8), (64, 640, 640, 1)])
+def test_lora_factor_gradients_fused_kernel(cuda_device, dtype, M, in_f, out_f, r):
+    """pv_lora_bwd: dA = s (G B)^T X and dB = s G^T (X A^T) of y = W x + s B (A x) (peft 0.10.0 lora.Linear) in one pass,
+    vs autograd through that formula in fp64; G is a strided column slice like the K / V halves of dkv_text."""
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(M + r)
+    x = torch.randn(M, in_f, generator=g).to(cuda_device, dtype)
+    gfull = torch.randn(M, 2 * out_f, generator=g).to(cuda_device, dtype)
+    gy = gfull[:, out_f:]                                     # row stride 2 * out
+    A = (torch.randn(r, in_f, generator=g) / in_f ** 0.5).to(cuda_device)
+    Bm = (torch.randn(out_f, r, generator=g) * 0.1).to(cuda_device)
+    s_ = 0.25
+    out = ops.lora_bwd(x, gy, A, Bm, s_)
+    assert out is not None
+    dA, dB = out
+    Ad, Bd = A.double().requires_grad_(True), Bm.double().requires_grad_(True)
+    y = s_ * (x.double() @ Ad.t()) @ Bd.t()
+    (y * gy.double()).sum().backward()
+    # fp32: FFMA path.  bf16: tensor-core path, the intermediate X A^T / G B (and A, B) rounded to bf16 like the activations
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert _rel(dA, Ad.grad) <= tol and _rel(dB, Bd.grad) <= tol
+    out2 = ops.lora_bwd(x, gy, A, Bm, s_)
+    assert torch.equal(out2[0], dA) and torch.equal(out2[1], dB)          # deterministic
+    assert ops.lora_bwd(x[:64], gy[:64], torch.zeros(128, in_f, device=cuda_device), torch.zeros(out_f, 128, device=cuda_device), 1.0) is None
