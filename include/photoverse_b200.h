@@ -202,6 +202,19 @@ int pv_inject_concept_fwd(pv_dtype dt, const void* inputs_embeds, const void* co
 int pv_inject_concept_bwd(pv_dtype dt, const void* d_out, const int* placeholder_idx, void* d_inputs_embeds,
                           void* d_concept, int B, int L, int T, int cols, void* stream);
 
+/* ---- training objective (train.py:509-535) ---------------------------------------------------------------
+ * loss = mean((noise_pred - noise)^2) + w_text * mean|concept| + w_vis * mean(v_ip_norms)     (reference: 0.01 / 0.001)
+ * noise_pred, noise: n elements; concept: m elements (text adapter output, :509); v_ip_norms: k elements (the stacked
+ * `to_v_ip_norm` side outputs of the attn2 processors, models/unet.py:38-47), all dt.  out4 (fp32, device) = {loss,
+ * l_mse, l_text, l_vis}.  Two launches, fixed summation order.  Backward: d_loss is a device scalar (fp32);
+ * d_noise_pred [n], d_concept [m], d_v_ip_norms [k] in dt.                                                              */
+int64_t pv_train_loss_ws_bytes(void);
+int pv_train_loss_fwd(pv_dtype dt, const void* noise_pred, const void* noise, int64_t n, const void* concept, int64_t m,
+                      const void* v_ip_norms, int64_t k, float w_text, float w_vis, float* out4, void* ws, void* stream);
+int pv_train_loss_bwd(pv_dtype dt, const void* noise_pred, const void* noise, int64_t n, const void* concept, int64_t m, int64_t k,
+                      float w_text, float w_vis, const float* d_loss, void* d_noise_pred, void* d_concept, void* d_v_ip_norms,
+                      void* stream);
+
 /* ---- LoRA dropout backward (peft==0.10.0 lora.Linear.forward `lora_B(lora_A(dropout(x))) * scaling`, configured at
  * train.py:264-269, 348-354) --------------------------------------------------------------------------
  * dst[i] += keep_mask[i] ? alpha * src[i] : 0, alpha = 1/(1-p).  dst, src: n elements (dt), n % 8 == 0;

@@ -55,6 +55,11 @@ int ln_lrelu_bwd(bool bf16, const void* da, const float* x, const float* mean, c
                  long long rows_per_group, int cols, float slope, cudaStream_t stream);
 int group_mean_bwd(bool bf16, const void* dy, void* dx, long long groups, int P, int cols, long long ldy, cudaStream_t stream);
 int attn_bwd_chunks(int S);
+long long train_loss_ws_bytes();
+int train_loss_fwd(bool bf16, const void* pred, const void* target, long long n, const void* concept, long long m, const void* vnorm,
+                   long long k, float w_text, float w_vis, float* out4, void* ws, cudaStream_t stream);
+int train_loss_bwd(bool bf16, const void* pred, const void* target, long long n, const void* concept, long long m, long long k,
+                   float w_text, float w_vis, const float* gloss, void* d_pred, void* d_concept, void* d_vnorm, cudaStream_t stream);
 bool lora_bwd_supported(int in_f, int out_f, int r);
 long long lora_bwd_ws_bytes(long long M, int in_f, int out_f, int r);
 int lora_bwd(bool bf16, const void* X, const void* G, const float* A, const float* Bm, float scaling, float* dAB, void* ws,
@@ -449,6 +454,22 @@ int pv_inject_concept_bwd(pv_dtype dt, const void* d_out, const int* placeholder
                           void* d_concept, int B, int L, int T, int cols, void* stream) {
   PV_REQUIRE(d_out && placeholder_idx && d_inputs_embeds && d_concept, "null pointer");
   return inject_concept_bwd(dt == PV_BF16, d_out, placeholder_idx, d_inputs_embeds, d_concept, B, L, T, cols, as_stream(stream));
+}
+
+int64_t pv_train_loss_ws_bytes(void) { return train_loss_ws_bytes(); }
+
+int pv_train_loss_fwd(pv_dtype dt, const void* noise_pred, const void* noise, int64_t n, const void* concept, int64_t m,
+                      const void* v_ip_norms, int64_t k, float w_text, float w_vis, float* out4, void* ws, void* stream) {
+  PV_REQUIRE(noise_pred && noise && out4 && (m == 0 || concept) && (k == 0 || v_ip_norms), "null pointer");
+  return train_loss_fwd(dt == PV_BF16, noise_pred, noise, n, concept, m, v_ip_norms, k, w_text, w_vis, out4, ws, as_stream(stream));
+}
+
+int pv_train_loss_bwd(pv_dtype dt, const void* noise_pred, const void* noise, int64_t n, const void* concept, int64_t m, int64_t k,
+                      float w_text, float w_vis, const float* d_loss, void* d_noise_pred, void* d_concept, void* d_v_ip_norms,
+                      void* stream) {
+  PV_REQUIRE(noise_pred && noise && d_loss && d_noise_pred && (m == 0 || (concept && d_concept)) && (k == 0 || d_v_ip_norms), "null pointer");
+  return train_loss_bwd(dt == PV_BF16, noise_pred, noise, n, concept, m, k, w_text, w_vis, d_loss, d_noise_pred, d_concept,
+                        d_v_ip_norms, as_stream(stream));
 }
 
 int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* keep_mask, float alpha, int64_t n,

@@ -24,6 +24,7 @@ from typing import List, Optional
 import torch
 import torch.nn.functional as F
 
+from ..loss import train_loss
 from ..unet import get_visual_cross_attention_values_norm
 from .parallel import FlatGradBuffer, OverlappedGradReducer, trainable_named_parameters
 
@@ -80,8 +81,11 @@ class Trainer:
             text = b.text
         img_tokens = self.image_adapter(b.clip_hidden)                                # train.py:502
         pred = self.unet(b.noisy_latents, b.timesteps, encoder_hidden_states=(text, img_tokens)).sample     # :505
+        vnorms = get_visual_cross_attention_values_norm(self.unet)                    # :512 (stack of the 16 side outputs)
+        if pred.is_cuda:      # :509-535 in one reduction kernel (+ one backward kernel): photoverse_b200.loss
+            return train_loss(pred, b.noise, concept, vnorms, 0.01, 0.001)
         l_text = concept.float().abs().mean()                                         # :509
-        l_vis = get_visual_cross_attention_values_norm(self.unet).float().mean()      # :512-513
+        l_vis = vnorms.float().mean()                                                 # :513
         l_mse = F.mse_loss(pred.float(), b.noise.float(), reduction="mean")           # :516
         return l_mse + 0.01 * l_text + 0.001 * l_vis, (l_mse, l_text, l_vis)          # :535
 

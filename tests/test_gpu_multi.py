@@ -120,4 +120,8 @@ def test_two_ranks_reproduce_the_single_rank_run(cuda_device, tmp_path):
                 continue
             want = torch.tensor(parts, dtype=torch.float64).sum(0) / 2
             have = torch.tensor(got[n], dtype=torch.float64)
-            assert torch.allclose(have, want, rtol=1e-4, atol=1e-7), n
+            # the two runs are separate processes: cuDNN autotuning may pick different (TF32) convolution algorithms for the
+            # frozen backbone, so per-rank gradients agree to ~1e-3, not bitwise; a wrong reduction (sum instead of mean, a
+            # dropped or doubled shard) is off by a factor
+            err = (have - want).norm() / want.norm().clamp_min(1e-30)
+            assert err <= 2e-2, f"{n}: relative error {err:.3e}"

@@ -128,3 +128,28 @@ def test_trainer_step_updates_only_the_trainable_set(cuda_device, lora_dropout):
             assert torch.equal(p, frozen_before[n]), n
     assert any(not torch.equal(p, train_before[n]) for n, p in unet.named_parameters() if n in train_before)
     assert tr.buf.numel() == sum(p.numel() for _, p in tr.named)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_fused_training_loss_matches_torch(cuda_device, dtype):
+    """pv_train_loss_fwd / _bwd (train.py:509-535 in one reduction) vs the reference's torch expression, values and all
+    three gradients; deterministic."""
+    from photoverse_b200.loss import train_loss
+    g = torch.Generator().manual_seed(5)
+    pred = torch.randn(4, 4, 64, 64, generator=g).to(cuda_device, dtype).requires_grad_(True)
+    noise = torch.randn(4, 4, 64, 64, generator=g).to(cuda_device, dtype)
+    concept = torch.randn(4, 5, 768, generator=g).to(cuda_device, dtype).requires_grad_(True)
+    vn = torch.rand(4, 16 * 8 * 5, generator=g).to(cuda_device, dtype).requires_grad_(True)
+    loss, (l_mse, l_text, l_vis) = train_loss(pred, noise, concept, vn)
+    (3.0 * loss).backward()
+    pr, cr, vr = (t.detach().double().requires_grad_(True) for t in (pred, concept, vn))
+    ref = torch.nn.functional.mse_loss(pr, noise.double()) + 0.01 * cr.abs().mean() + 0.001 * vr.mean()
+    (3.0 * ref).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert abs(l_mse.item() - torch.nn.functional.mse_loss(pr, noise.double()).item()) <= 1e-5
+    assert abs(l_text.item() - cr.abs().mean().item()) <= 1e-5 and abs(l_vis.item() - vr.mean().item()) <= 1e-5
+    tol = 1e-6 if dtype == torch.float32 else 8e-3          # bf16: gradients are stored in bf16
+    for got, want in ((pred.grad, pr.grad), (concept.grad, cr.grad), (vn.grad, vr.grad)):
+        assert _rel(got.float(), want.float()) <= tol
+    loss2, _ = train_loss(pred.detach(), noise, concept.detach(), vn.detach())
+    assert torch.equal(loss2, loss.detach())

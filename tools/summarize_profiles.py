@@ -67,7 +67,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "launch__occupancy_limit_shared_mem",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active"]
-for what in ("attn", "gemm"):
+for what in ("attn", "gemm", "adapter", "bwd"):
     rep = os.path.join(G, f"prof_{what}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -82,3 +82,19 @@ for what in ("attn", "gemm"):
         for r in rows[2:]:
             w.writerow([r[i][:100] for i in cols])
 print("profiles/:", sorted(os.listdir(P)))
+
+# pv:: kernels of one training step (tools/gpu_runs/r2_profiles.sh)
+p = os.path.join(G, f"launches_pv_train_{tag}.csv")
+if os.path.exists(p):
+    rows = read_launch_csv(p)
+    agg = collections.OrderedDict()
+    for k, g, b, v in rows:
+        a = agg.setdefault(short(k)[:70], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(P, f"{tag}_train_pv_kernels.txt"), "w") as f:
+        f.write("pv:: kernels of ONE training step (config 3, batch 16, LoRA r = 8, bf16) under ncu gpu__time_duration (serialised, cold)\n")
+        f.write(f"total pv ms {tot / 1e6:.2f}   launches {sum(a[0] for a in agg.values())}\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+            f.write(f"{k:72s} n={a[0]:4d} total={a[1] / 1e6:7.2f} ms avg={a[1] / a[0] / 1e3:8.1f} us\n")
