@@ -97,40 +97,64 @@ int ln_lrelu(bool out_bf16, const float* x, const float* gamma, const float* bet
   }
 }
 
-// x:[groups, P, cols] -> y:[groups, cols] ; thread = 2 adjacent columns, loop over the P rows (coalesced)
+// x:[groups, P, cols] -> y:[groups, cols].  A block owns 64 adjacent columns of one group: lane = 2 columns (one 4- / 8-byte
+// load, 128 / 256 contiguous bytes per warp and row), its 8 warps take the rows w, w + 8, ... with four independent
+// accumulator pairs (loads in flight instead of one serial chain of P round trips), and warp 0 adds the 8 slice sums in a
+// fixed order.  HBM-bound: x is read once.
 template <bool IN_BF16, bool OUT_BF16>
 __global__ void __launch_bounds__(256)
 group_mean_kernel(const void* __restrict__ x, void* __restrict__ y, int P, int cols, long long ldy) {
+  __shared__ float red[8][64];
   const long long g = blockIdx.y;
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (c >= cols) return;
-  float a0 = 0.f, a1 = 0.f;
-  if constexpr (IN_BF16) {
-    const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(static_cast<const __nv_bfloat16*>(x) + g * P * cols + c);
-    for (int r = 0; r < P; ++r) {
-      const float2 f = __bfloat1622float2(xp[static_cast<long long>(r) * (cols / 2)]);
-      a0 += f.x; a1 += f.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 64 + lane * 2;
+  float a[4][2] = {};
+  if (c < cols) {
+    auto ld = [&](int r, float& v0, float& v1) {
+      if constexpr (IN_BF16) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+            static_cast<const __nv_bfloat16*>(x) + (g * P + r) * static_cast<long long>(cols) + c));
+        v0 = f.x; v1 = f.y;
+      } else {
+        const float2 f = *reinterpret_cast<const float2*>(static_cast<const float*>(x) + (g * P + r) * static_cast<long long>(cols) + c);
+        v0 = f.x; v1 = f.y;
+      }
+    };
+    int r = warp;
+    for (; r + 24 < P; r += 32) {
+      float v[4][2];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ld(r + 8 * k, v[k][0], v[k][1]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k][0] += v[k][0]; a[k][1] += v[k][1]; }
     }
-  } else {
-    const float2* xp = reinterpret_cast<const float2*>(static_cast<const float*>(x) + g * P * cols + c);
-    for (int r = 0; r < P; ++r) {
-      const float2 f = xp[static_cast<long long>(r) * (cols / 2)];
-      a0 += f.x; a1 += f.y;
+    for (; r < P; r += 8) {
+      float v0, v1;
+      ld(r, v0, v1);
+      a[0][0] += v0; a[0][1] += v1;
     }
   }
-  const float inv = 1.f / static_cast<float>(P);
-  a0 *= inv; a1 *= inv;
-  if constexpr (OUT_BF16) {
-    *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(y) + g * ldy + c) = pack_bf16x2(a0, a1);
-  } else {
-    *reinterpret_cast<float2*>(static_cast<float*>(y) + g * ldy + c) = make_float2(a0, a1);
+  red[warp][2 * lane] = (a[0][0] + a[1][0]) + (a[2][0] + a[3][0]);
+  red[warp][2 * lane + 1] = (a[0][1] + a[1][1]) + (a[2][1] + a[3][1]);
+  __syncthreads();
+  if (warp == 0 && c < cols) {
+    float s0 = red[0][2 * lane], s1 = red[0][2 * lane + 1];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { s0 += red[w][2 * lane]; s1 += red[w][2 * lane + 1]; }
+    const float inv = 1.f / static_cast<float>(P);
+    s0 *= inv; s1 *= inv;
+    if constexpr (OUT_BF16) {
+      *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(y) + g * ldy + c) = pack_bf16x2(s0, s1);
+    } else {
+      *reinterpret_cast<float2*>(static_cast<float*>(y) + g * ldy + c) = make_float2(s0, s1);
+    }
   }
 }
 
 int group_mean(bool in_bf16, bool out_bf16, const void* x, void* y, long long groups, int P, int cols, long long ldy,
                cudaStream_t stream) {
   PV_REQUIRE(groups > 0 && groups <= 65535 && P > 0 && cols > 0 && cols % 2 == 0 && ldy % 2 == 0, "bad shape");
-  dim3 grid((cols / 2 + 255) / 256, static_cast<unsigned>(groups));
+  dim3 grid((cols + 63) / 64, static_cast<unsigned>(groups));
   if (in_bf16 && out_bf16) group_mean_kernel<true, true><<<grid, 256, 0, stream>>>(x, y, P, cols, ldy);
   else if (in_bf16) group_mean_kernel<true, false><<<grid, 256, 0, stream>>>(x, y, P, cols, ldy);
   else if (out_bf16) group_mean_kernel<false, true><<<grid, 256, 0, stream>>>(x, y, P, cols, ldy);
