@@ -34,6 +34,9 @@ out = {}
 # ---- generation: global batch 4 sharded over the ranks ----
 GB, LAT, STEPS = 4, 32, 6
 unet, ia, ta = bench.build_models(dev, torch.bfloat16)
+# separate processes must pick the same cuDNN / cuBLAS algorithms for the frozen backbone to be comparable bit for bit
+torch.backends.cudnn.benchmark = False
+torch.backends.cudnn.deterministic = True
 out["latents"] = {}
 eng = GenerationEngine(unet, ia, ta, GB // 2, LAT, STEPS, 3.0, 0, "batched", torch.bfloat16, dev)
 for shard in ([0, 1] if world == 1 else [rank]):      # world 1: the two shards one after the other on one GPU

@@ -14,6 +14,7 @@ S, C = int(os.environ.get("PV_S", "4096")), int(os.environ.get("PV_C", "320"))
 ROWS, LI = 16, 1
 g = torch.Generator().manual_seed(0)
 _lib.set_option("trace_block", int(os.environ.get("PV_BLOCK", "0")))
+_lib.set_option("fuse_out", 2)
 lib = _lib.lib()
 text = torch.randn(ROWS, 77, 768, generator=g).to(dev, dt)
 img = torch.randn(ROWS, LI, 768, generator=g).to(dev, dt)
@@ -63,9 +64,9 @@ names = {1: "prologue cycles (entry -> cluster sync) =", 2: "entry -> after grid
          32: "    A slot_free", 33: "    A s_full", 34: "    A p_ready", 35: "    A S loaded", 36: "    A exps done", 37: "    A exchanged", 38: "    A drained",
          45: "        B S loaded", 46: "        B exps done", 47: "        B exchanged", 48: "        B drained", 39: "        B wait q_full", 40: "        B q_full", 41: "        B conv done",
          42: "        B slot_free", 43: "        B s_full", 44: "        B p_ready",
-         50: "P2 producer start", 51: "P2 tile ready", 52: "P2 tile loads issued", 60: "  P2 mma first stage full", 61: "  P2 mma tile issued",
+         50: "P2 producer start", 51: "P2 tile ready", 52: "P2 tile loads issued", 53: "P2 tile posted", 60: "  P2 mma first stage full", 61: "  P2 mma tile issued",
          70: "    P2 epi acc_full", 73: "    P2 epi tmem loaded", 74: "    P2 epi staging free", 75: "    P2 epi packed", 71: "    P2 epi store issued", 72: "    P2 epi done",
-         80: "            E drain begin", 81: "            E drain end", 82: "            E wait stores", 83: "            E stores done",
+         80: "            E drain begin", 81: "            E drain end", 82: "            E wait stores", 83: "            E stores done", 86: "            E signalled",
          84: "            E all drained", 85: "            E all signalled"}
 only = os.environ.get("PV_EVENTS")
 if only:

@@ -15,6 +15,7 @@ ROWS, LI = int(os.environ.get("PV_ROWS", "16")), 1
 g = torch.Generator().manual_seed(0)
 lib = _lib.lib()
 _lib.set_option("trace_block", -1)
+_lib.set_option("fuse_out", 2)
 text = torch.randn(ROWS, 77, 768, generator=g).to(dev, dt)
 img = torch.randn(ROWS, LI, 768, generator=g).to(dev, dt)
 wq = (torch.randn(C, C, generator=g) / C ** 0.5).to(dev, dt)
