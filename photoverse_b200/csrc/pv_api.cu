@@ -13,7 +13,7 @@ namespace pv {
 // ---- forward declarations of the launchers -------------------------------------------------------
 int gemm_bf16(const void* A, const void* W, const float* bias, void* D, bool out_f32, long long M, long long N,
               long long K, long long batch, long long lda, long long ldw, long long ldd, long long strideA,
-              long long strideW, long long strideBias, long long strideD, cudaStream_t stream);
+              long long strideW, long long strideBias, long long strideD, cudaStream_t stream, bool w_static = false);
 int gemm_f32(const float* A, const float* W, const float* bias, float* D, long long M, long long N, long long K,
              long long batch, long long lda, long long ldw, long long ldd, long long strideA, long long strideW,
              long long strideBias, long long strideD, cudaStream_t stream);
@@ -325,7 +325,7 @@ int pv_dual_attn_fwd(pv_dtype dt, const void* X, const void* Wq, const void* Kp,
     bool fused = false;
     rc = attn_core_bf16(X, Wq, Kp, Vp, ws_o, stats, B, S, C, H, Lt, Li, w_text, w_img, st, Wo, bo, Y, ws_sync, &fused);
     if (rc || fused) return rc;
-    return gemm_bf16(ws_o, Wo, bo, Y, false, (long long)B * S, C, C, 1, C, C, C, 0, 0, 0, 0, st);
+    return gemm_bf16(ws_o, Wo, bo, Y, false, (long long)B * S, C, C, 1, C, C, C, 0, 0, 0, 0, st, /*w_static=*/true);
   }
   PV_REQUIRE(ws_q != nullptr, "PV_F32 needs the ws_q scratch");
   rc = gemm_f32(static_cast<const float*>(X), static_cast<const float*>(Wq), nullptr, ws_q, (long long)B * S, C, C, 1, C,

@@ -200,7 +200,7 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUte
 extern int g_opt_gemm_two_cta;
 extern int g_opt_gemm_persistent;
 int gemm3_bf16(const void* A, const void* W, const float* bias, void* D, long long M, long long N, long long K, long long lda,
-               long long ldw, long long ldd, cudaStream_t stream);
+               long long ldw, long long ldd, cudaStream_t stream, bool w_static);
 
 template <int BN>
 static int launch_bn(bool out_f32, bool swz, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD,
@@ -241,7 +241,7 @@ static int pick_bn(long long M, long long N, long long batch, bool two_cta) {
 // D[b] = A[b] W[b]^T + bias ; bf16 operands, bf16 or fp32 output.
 int gemm_bf16(const void* A, const void* W, const float* bias, void* D, bool out_f32, long long M, long long N,
               long long K, long long batch, long long lda, long long ldw, long long ldd, long long strideA,
-              long long strideW, long long strideBias, long long strideD, cudaStream_t stream) {
+              long long strideW, long long strideBias, long long strideD, cudaStream_t stream, bool w_static) {
   PV_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "empty problem M=%lld N=%lld K=%lld batch=%lld", M, N, K, batch);
   PV_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "bf16 rows must be 16-byte multiples (K=%lld lda=%lld ldw=%lld)",
              K, lda, ldw);
@@ -253,7 +253,7 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* D, bool out
   PV_REQUIRE(batch <= 65535 && (M + GEMM_BM - 1) / GEMM_BM <= 65535, "grid too large");
   // persistent CTA-pair kernel (pv_gemm3.cu): the out projection shapes (bf16 out, N % 160 == 0, K % 64 == 0, tall M)
   if (g_opt_gemm_persistent != 0 && g_opt_force_bn == 0 && !out_f32 && batch == 1 && M >= 512 && N % 160 == 0 && K % 64 == 0)
-    return gemm3_bf16(A, W, bias, D, M, N, K, lda, ldw, ldd, stream);
+    return gemm3_bf16(A, W, bias, D, M, N, K, lda, ldw, ldd, stream, w_static);
   const bool two_cta = g_opt_gemm_two_cta != 0 && (K + GEMM_BK - 1) / GEMM_BK <= 8;
   const int bn = pick_bn(M, N, batch, two_cta);
   const bool swz = g_opt_epi_swizzle != 0 || out_f32 || two_cta;

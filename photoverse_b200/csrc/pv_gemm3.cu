@@ -25,7 +25,8 @@ constexpr int G3_THREADS = 384;          // warp 0 TMA, warp 1 MMA (leader), war
 template <typename Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G3_THREADS, 1)
 gemm3_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                             const __grid_constant__ CUtensorMap tmD, const float* __restrict__ bias, int G, int V, int K) {
+                             const __grid_constant__ CUtensorMap tmD, const float* __restrict__ bias, int G, int V, int K,
+                             int w_static) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (Cfg::BYTES + 15) / 16 * 16);
@@ -50,7 +51,17 @@ gemm3_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // Nothing above reads global memory; W, bias, A and D are touched only after the predecessor kernel has completed.
+  const int u0 = static_cast<int>((static_cast<long long>(V) * r_pair) / npair_g);
+  const int u1 = static_cast<int>((static_cast<long long>(V) * (r_pair + 1)) / npair_g);
+  // Nothing above reads global memory.  `w_static` (set only by the processor's own out-projection call, whose Wo was
+  // packed many kernels earlier): the resident W half is requested before the dependency wait, under the predecessor's
+  // tail; on the generic pv_linear_fwd route W, bias, A and D are all touched only after the predecessor has completed.
+  if constexpr (Cfg::WSTAT) {
+    if (w_static && warp == 0 && u0 < u1) {
+      if (elect_one()) op_preload_w<Cfg>(smem, bars, &tmW, g, cluster_ctarank());
+      __syncwarp();
+    }
+  }
   pdl_wait();
   pdl_launch_dependents();
 
@@ -59,11 +70,11 @@ gemm3_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   oa.sync = nullptr;
   oa.G = G; oa.C = K; oa.V = V;
   oa.MTP = V > 0 ? V : 1;             // one "sample": tile u covers rows [256 u, 256 u + 256) of the flat [M, K] operand
-  oa.u0 = static_cast<int>((static_cast<long long>(V) * r_pair) / npair_g);
-  oa.u1 = static_cast<int>((static_cast<long long>(V) * (r_pair + 1)) / npair_g);
+  oa.u0 = u0;
+  oa.u1 = u1;
   oa.g = g;
   oa.ready_target = 0;
-  oa.w_preloaded = 0;
+  oa.w_preloaded = Cfg::WSTAT && w_static && u0 < u1;
   oa.trace = nullptr; oa.trace_cap = 0; oa.trace_block = 0;
   outproj_phase<Cfg>(smem, bars, tmem, &tmA, &tmW, &tmD, oa);
 
@@ -76,7 +87,7 @@ gemm3_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 
 template <int KB_RES, int STAGES>
 static int launch_g3(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmD, const float* bias, int G, int V,
-                     int K, cudaStream_t stream) {
+                     int K, int w_static, cudaStream_t stream) {
   using Cfg = OutProjCfg<KB_RES, STAGES>;
   constexpr int SMEM_BYTES = (Cfg::BYTES + 15) / 16 * 16 + 256 + 1024;
   static_assert(OP_BAR_BYTES + 8 <= 256 && SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -85,14 +96,14 @@ static int launch_g3(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUten
   const long long units = static_cast<long long>(G) * V;
   const long long max_pairs = sm_count() / 2;
   const int npairs = static_cast<int>(units < max_pairs ? units : max_pairs);
-  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(G3_THREADS), SMEM_BYTES, stream, tmA, tmW, tmD, bias, G, V, K));
+  PV_CUDA(launch_pdl(kern, dim3(2 * npairs), dim3(G3_THREADS), SMEM_BYTES, stream, tmA, tmW, tmD, bias, G, V, K, w_static));
   PV_LAUNCHED();
   return PV_OK;
 }
 
 // D[M,N] (bf16, row stride ldd) = A[M,K] (lda) * W[N,K]^T (ldw) + bias ; N % 160 == 0, K % 64 == 0
 int gemm3_bf16(const void* A, const void* W, const float* bias, void* D, long long M, long long N, long long K, long long lda,
-               long long ldw, long long ldd, cudaStream_t stream) {
+               long long ldw, long long ldd, cudaStream_t stream, bool w_static) {
   PV_REQUIRE(M > 0 && N % OP_BN == 0 && K % OP_BK == 0 && N > 0 && K > 0, "gemm3: need N %% 160 == 0 and K %% 64 == 0 (N=%lld K=%lld)", N, K);
   PV_REQUIRE((lda * 2) % 16 == 0 && (ldw * 2) % 16 == 0 && (ldd * 2) % 16 == 0, "row strides must be 16-byte multiples");
   CUtensorMap tmA, tmW, tmD;
@@ -102,9 +113,9 @@ int gemm3_bf16(const void* A, const void* W, const float* bias, void* D, long lo
   const int G = static_cast<int>(N / OP_BN);
   const long long V = (M + 255) / 256;
   PV_REQUIRE(V * G < (1ll << 30), "too many tiles");
-  if (K == 320) return launch_g3<5, 8>(tmA, tmW, tmD, bias, G, static_cast<int>(V), static_cast<int>(K), stream);
-  if (K == 640) return launch_g3<10, 5>(tmA, tmW, tmD, bias, G, static_cast<int>(V), static_cast<int>(K), stream);
-  return launch_g3<0, 7>(tmA, tmW, tmD, bias, G, static_cast<int>(V), static_cast<int>(K), stream);
+  if (K == 320) return launch_g3<5, 8>(tmA, tmW, tmD, bias, G, static_cast<int>(V), static_cast<int>(K), w_static, stream);
+  if (K == 640) return launch_g3<10, 5>(tmA, tmW, tmD, bias, G, static_cast<int>(V), static_cast<int>(K), w_static, stream);
+  return launch_g3<0, 7>(tmA, tmW, tmD, bias, G, static_cast<int>(V), static_cast<int>(K), w_static, stream);
 }
 
 }  // namespace pv
