@@ -215,6 +215,15 @@ int pv_train_loss_bwd(pv_dtype dt, const void* noise_pred, const void* noise, in
                       float w_text, float w_vis, const float* d_loss, void* d_noise_pred, void* d_concept, void* d_v_ip_norms,
                       void* stream);
 
+/* ---- self-attention of the `attn1` layers (reference models/unet.py:20-24 installs diffusers' stock AttnProcessor2_0
+ * there: O = softmax(Q K^T / sqrt(d)) V per (sample, head)) -----------------------------------------
+ * q, k, v: bf16 [B, S, *] views with a common row stride `ld` (elements; e.g. three slices of one fused [B,S,3C]
+ * projection, ld = 3C), head h in columns [h*d, (h+1)*d); out: bf16 [B,S,C] contiguous.  d = C / heads in {40, 80, 160}.
+ * ws: pv_self_attn_ws_bytes(B,S,C,heads) bytes of scratch (operand images).  Inference only (no statistics saved).  */
+int64_t pv_self_attn_ws_bytes(int B, int S, int C, int heads);
+int pv_self_attn_fwd(const void* q, const void* k, const void* v, int64_t ld, void* out, void* ws, int B, int S, int C,
+                     int heads, void* stream);
+
 /* ---- LoRA dropout backward (peft==0.10.0 lora.Linear.forward `lora_B(lora_A(dropout(x))) * scaling`, configured at
  * train.py:264-269, 348-354) --------------------------------------------------------------------------
  * dst[i] += keep_mask[i] ? alpha * src[i] : 0, alpha = 1/(1-p).  dst, src: n elements (dt), n % 8 == 0;

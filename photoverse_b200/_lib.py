@@ -42,6 +42,8 @@ _SIGNATURES = {
                                   c_void_p, c_void_p]),
     "pv_train_loss_bwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_float, c_float, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
+    "pv_self_attn_ws_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "pv_self_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pv_dropout_bwd_acc": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p]),
     "pv_pack_weight_t": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pv_transpose_2d": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),

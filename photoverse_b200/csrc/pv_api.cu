@@ -55,6 +55,9 @@ int ln_lrelu_bwd(bool bf16, const void* da, const float* x, const float* mean, c
                  long long rows_per_group, int cols, float slope, cudaStream_t stream);
 int group_mean_bwd(bool bf16, const void* dy, void* dx, long long groups, int P, int cols, long long ldy, cudaStream_t stream);
 int attn_bwd_chunks(int S);
+long long self_attn_ws_bytes(int B, int S, int C, int H);
+int self_attn_fwd_bf16(const void* q, const void* k, const void* v, long long ld, void* out, void* ws, int B, int S, int C, int H,
+                       cudaStream_t stream);
 long long train_loss_ws_bytes();
 int train_loss_fwd(bool bf16, const void* pred, const void* target, long long n, const void* concept, long long m, const void* vnorm,
                    long long k, float w_text, float w_vis, float* out4, void* ws, cudaStream_t stream);
@@ -470,6 +473,14 @@ int pv_train_loss_bwd(pv_dtype dt, const void* noise_pred, const void* noise, in
   PV_REQUIRE(noise_pred && noise && d_loss && d_noise_pred && (m == 0 || (concept && d_concept)) && (k == 0 || d_v_ip_norms), "null pointer");
   return train_loss_bwd(dt == PV_BF16, noise_pred, noise, n, concept, m, k, w_text, w_vis, d_loss, d_noise_pred, d_concept,
                         d_v_ip_norms, as_stream(stream));
+}
+
+int64_t pv_self_attn_ws_bytes(int B, int S, int C, int heads) { return self_attn_ws_bytes(B, S, C, heads); }
+
+int pv_self_attn_fwd(const void* q, const void* k, const void* v, int64_t ld, void* out, void* ws, int B, int S, int C,
+                     int heads, void* stream) {
+  PV_REQUIRE(q && k && v && out && ws, "null pointer");
+  return self_attn_fwd_bf16(q, k, v, ld, out, ws, B, S, C, heads, as_stream(stream));
 }
 
 int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* keep_mask, float alpha, int64_t n,

@@ -337,3 +337,32 @@ def dropout_bwd_acc(dst: torch.Tensor, src: torch.Tensor, keep_mask: torch.Tenso
     check(_lib.lib().pv_dropout_bwd_acc(_dt(dst), _ptr(dst), _ptr(src), _ptr(keep_mask), 1.0 / (1.0 - float(p)),
                                         dst.numel(), _stream()), "pv_dropout_bwd_acc")
     return dst
+
+
+_SA_WS = {}
+
+
+def self_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """softmax(Q K^T / sqrt(d)) V per (sample, head) -- the stock self-attention of the ``attn1`` layers (reference
+    models/unet.py:20-24 -> diffusers AttnProcessor2_0).  q, k, v: bf16 ``[B, S, C]`` views with unit channel stride and
+    one common row stride (e.g. the three slices of a fused ``[B, S, 3C]`` projection); returns bf16 ``[B, S, C]``.
+    Inference only (nothing is saved for a backward pass)."""
+    if not (q.is_cuda and q.dtype == torch.bfloat16 and k.dtype == v.dtype == q.dtype):
+        raise _lib.PhotoverseB200Error("self_attn: CUDA bfloat16 tensors required (there is no CPU path)")
+    B, S, C = q.shape
+    ld = q.stride(1)
+    for t in (q, k, v):
+        if t.shape != q.shape or t.stride(2) != 1 or t.stride(1) != ld or (B > 1 and t.stride(0) != S * ld):
+            raise _lib.PhotoverseB200Error("self_attn: q, k, v must be [B,S,C] views with the same row stride and batch stride S*ld")
+    lib = _lib.lib()
+    nbytes = int(lib.pv_self_attn_ws_bytes(B, S, C, heads))
+    if nbytes < 0:
+        raise _lib.PhotoverseB200Error(f"self_attn: unsupported shape B={B} S={S} C={C} heads={heads}")
+    key = (q.device.index, torch.cuda.current_stream(q.device).cuda_stream)
+    ws = _SA_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, device=q.device, dtype=torch.uint8)
+        _SA_WS[key] = ws
+    out = torch.empty(B, S, C, device=q.device, dtype=q.dtype)
+    _lib.check(lib.pv_self_attn_fwd(_ptr(q), _ptr(k), _ptr(v), ld, _ptr(out), _ptr(ws), B, S, C, heads, _stream()), "pv_self_attn_fwd")
+    return out
