@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from photoverse_b200 import ops  # noqa: E402
+from photoverse_b200 import _lib, ops  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = int(os.environ.get("PV_ROWS", "16"))
@@ -16,6 +16,8 @@ shapes = [(4096, 320), (1024, 640), (256, 1280), (64, 1280)]
 if os.environ.get("PV_SHAPES"):
     shapes = [tuple(int(x) for x in s.split(":")) for s in os.environ["PV_SHAPES"].split(",")]
 H = 8
+if os.environ.get("PV_POLY"):
+    _lib.set_option("sattn_poly", int(os.environ["PV_POLY"]))
 g = torch.Generator().manual_seed(0)
 
 
