@@ -46,7 +46,7 @@ const char* pv_last_error(void);
 /* Number of kernels this library has launched since it was loaded (bench.py: "gpu_launches"). */
 unsigned long long pv_launch_count(void);
 /* TEST-ONLY process-wide switches (not thread-safe; production code never calls this).  Every value selects among
- * kernels that compute the same result -- none changes results:
+ * kernels that compute the same result ("sattn_poly": to within the bf16 rounding of P):
  *   "fuse_out" 2|1|0      out projection as the second phase of the attention launch for every S > 128 shape | where it
  *                         is at least as fast as two launches (default: C <= 320) | always a separate GEMM launch
  *   "gemm_persistent" 1|0 persistent CTA-pair GEMM for out-projection-shaped pv_linear_fwd calls | single-CTA kernel
