@@ -286,6 +286,18 @@ def roofline_leg(device, rows_b, Li, scale):
         out["speedup_vs_gpu_eager"] = out["gpu_eager_us"] / out["proc_us"]
         fam[f"S{S}_C{C}"] = out
         del xs, os_, ys
+    # attn1: the opt-in self-attention kernel beside the stock SDPA call it would replace, same inputs
+    attn1 = {}
+    for (S, C) in sorted(set(LAYER_SHAPES), reverse=True):
+        H = 8
+        qkv = torch.randn(rows_b, S, 3 * C, generator=g).to(device, dt)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        hd = lambda t: t.reshape(rows_b, S, H, C // H).transpose(1, 2)
+        with torch.no_grad():
+            t_ours = _graph_time_us(lambda i: ops.self_attn(q, k, v, H), 1, reps=10)
+            t_sdpa = _graph_time_us(lambda i: torch.nn.functional.scaled_dot_product_attention(hd(q), hd(k), hd(v)), 1, reps=10)
+        attn1[f"S{S}_C{C}"] = {"ours_us": round(t_ours, 1), "sdpa_us": round(t_sdpa, 1), "ratio": round(t_sdpa / t_ours, 2)}
+        del qkv
     # aggregate over the 16 layers of one UNet evaluation
     tsum = lambda key: sum(fam[f"S{S}_C{C}"][key] for S, C in LAYER_SHAPES) * 1e-6
     t_attn, t_proc, t_eager = tsum("attn_us"), tsum("proc_us"), tsum("gpu_eager_us")
@@ -309,7 +321,10 @@ def roofline_leg(device, rows_b, Li, scale):
             "processor_frac": round(f_proc / t_proc / 1e12 / peaks["bf16_tflops"], 4),
             "processor_ms_per_unet_eval": round(t_proc * 1e3, 3),
             "gpu_eager_ms_per_unet_eval": round(t_eager * 1e3, 3),
-            "speedup_vs_gpu_eager": round(t_eager / t_proc, 2)}
+            "speedup_vs_gpu_eager": round(t_eager / t_proc, 2),
+            "attn1_self_attention": {"note": "pv_self_attn_fwd (opt-in SelfAttnProcessor, NOT used by the benchmarked step) vs the stock "
+                                             "F.scaled_dot_product_attention it would replace; ratio > 1 = ours faster",
+                                     "per_shape": attn1}}
     return roof
 
 

@@ -49,11 +49,8 @@ struct SaCfg {
   static constexpr int O_STAGE_BYTES = 128 * D * 2;      // bf16 output rows of one 128-row tile
   static constexpr int P_BYTES = P_TMEM ? O_STAGE_BYTES : (BN / 8) * 128 * 16;   // P_TMEM: only the output staging
   static constexpr int STAGES = D == 160 ? 2 : 4;
-  // setmaxnreg of the four control warps / the eight softmax warps (one CTA per SM only).  The increase is served from
-  // the CTA's OWN launch allocation (384 threads x 168), so what the control warps give up must cover it:
-  // 128 * (168 - 56) >= 256 * (216 - 168)
-  static constexpr int REGS_CTRL = 56;
-  static constexpr int REGS_SOFTMAX = 216;
+  // No setmaxnreg: with 64 keys per tile every role fits the launch-bound register count (168, resp. 80 with two CTAs
+  // per SM), and a kernel that re-allocates registers must serve the increase from its own launch allocation.
   static constexpr bool STAGE_IN_Q = O_STAGE_BYTES > P_BYTES;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_P = OFF_Q + 2 * Q_BYTES;
@@ -222,8 +219,6 @@ __global__ void __launch_bounds__(SA_THREADS, SaCfg<D>::CTAS_PER_SM) self_attn_f
 
   const int S = p.S, nKT = p.nKT;
 
-  if constexpr (!Cfg::ALIAS)
-    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_CTRL));   // see SaCfg
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
     if (elect_one()) {
@@ -370,7 +365,6 @@ __global__ void __launch_bounds__(SA_THREADS, SaCfg<D>::CTAS_PER_SM) self_attn_f
     a3_trace_done_raw(p.trace, tr, 0);
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- softmax groups: one thread per query row
-    if constexpr (!Cfg::ALIAS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_SOFTMAX));
     const int t = (warp - 4) >> 2;                 // tile / group
     const int wq = warp & 3;                       // TMEM lane quarter
     const int row = wq * 32 + lane;                // row inside the 128-row tile
@@ -539,7 +533,6 @@ __global__ void __launch_bounds__(SA_THREADS, SaCfg<D>::CTAS_PER_SM) self_attn_f
     a3_trace_done_raw(p.trace, tr, 1 + t);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
-    if constexpr (!Cfg::ALIAS) asm volatile("setmaxnreg.dec.sync.aligned.u32 168;");
   }
   pdl_launch_dependents();
   tc_fence_before();

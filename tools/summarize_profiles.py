@@ -1,7 +1,7 @@
 """Turn the raw ncu outputs in gpurun_out/ into the small, tracked summaries under profiles/.
     python tools/summarize_profiles.py <tag>      (e.g. r01a)
 Reads  gpurun_out/launches_layerstack_<tag>.csv, launches_bench_<tag>.csv, prof_attn_<tag>.ncu-rep, prof_gemm_<tag>.ncu-rep
-Writes profiles/<tag>_launches_layerstack.csv, <tag>_bench_kernel_shares.csv, <tag>_ncu_attn.csv, <tag>_ncu_gemm.csv"""
+Writes profiles/<tag>_launches_layerstack.csv, <tag>_bench_kernel_shares.csv, <tag>_ncu_{attn,gemm,adapter,bwd,sattn}.csv"""
 import collections
 import csv
 import os
@@ -67,7 +67,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "launch__occupancy_limit_shared_mem",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active"]
-for what in ("attn", "gemm", "adapter", "bwd"):
+for what in ("attn", "gemm", "adapter", "bwd", "sattn"):
     rep = os.path.join(G, f"prof_{what}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
