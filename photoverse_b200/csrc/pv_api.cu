@@ -95,7 +95,7 @@ int g_opt_fuse_out = 1;          // out projection as the second phase of the at
 int g_opt_bwd_mma = 1;           // bf16 attention backward on tensor cores (0: fp32-accurate SIMT kernel)
 unsigned long long* g_attn3_trace = nullptr;   // debug timeline buffer (pv_debug_trace; kernels record only in -DPV_TRACE builds)
 int g_attn3_trace_cap = 0;
-int g_opt_sattn_poly = 2;        // pv_sattn.cu: exponentials per 8 pairs computed on the FMA pipe instead of MUFU (0..4)
+int g_opt_sattn_poly = 2;        // pv_sattn.cu: exponentials per 8 pairs computed on the FMA pipe instead of MUFU (0 | 2 | 4)
 int g_opt_trace_block = 0;       // which leader CTA writes the debug timeline
 static thread_local std::string t_error;
 

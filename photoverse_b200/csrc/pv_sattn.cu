@@ -622,8 +622,6 @@ int self_attn_fwd_bf16(const void* q, const void* k, const void* v, long long ld
 #define PV_SA_DISPATCH(DD)                                                                          \
   switch (pf) {                                                                                     \
     case 0: return launch_sattn<DD, 0>(q, k, v, ld, out, ws, B, S, C, H, stream);                   \
-    case 1: return launch_sattn<DD, 1>(q, k, v, ld, out, ws, B, S, C, H, stream);                   \
-    case 3: return launch_sattn<DD, 3>(q, k, v, ld, out, ws, B, S, C, H, stream);                   \
     case 4: return launch_sattn<DD, 4>(q, k, v, ld, out, ws, B, S, C, H, stream);                   \
     default: return launch_sattn<DD, 2>(q, k, v, ld, out, ws, B, S, C, H, stream);                  \
   }
