@@ -53,6 +53,7 @@ unsigned long long pv_launch_count(void);
  *   "gemm_two_cta" 1|0, "force_bn" 0|64|128|160|256, "epi_swizzle" 1|0   tile choices of the single-CTA GEMM
  *   "pdl" 1|0             programmatic dependent launch of the persistent kernels
  *   "bwd_mma" 1|0         bf16 attention backward on tensor cores | the fp32-accurate SIMT kernel
+ *   "bwd_tc" 1|0          ... on tcgen05 with TMEM accumulators where supported (head_dim 40 / 80) | the mma.sync kernel
  *   "sattn_poly" 0|2|4    pv_self_attn_fwd: exponentials out of every 8 pairs computed by a degree-3 polynomial on the FMA
  *                         pipe instead of MUFU (default 2; 7.5e-5 relative, below the bf16 rounding of P)
  *   "trace_block" n       which leader CTA writes the debug timeline (PV_TRACE builds)

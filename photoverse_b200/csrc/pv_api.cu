@@ -95,6 +95,7 @@ int g_opt_fuse_out = 1;          // out projection as the second phase of the at
 int g_opt_bwd_mma = 1;           // bf16 attention backward on tensor cores (0: fp32-accurate SIMT kernel)
 unsigned long long* g_attn3_trace = nullptr;   // debug timeline buffer (pv_debug_trace; kernels record only in -DPV_TRACE builds)
 int g_attn3_trace_cap = 0;
+int g_opt_bwd_tc = 1;            // tcgen05 attention backward for head_dim 40 / 80 (0: the mma.sync kernel)
 int g_opt_sattn_poly = 2;        // pv_sattn.cu: exponentials per 8 pairs computed on the FMA pipe instead of MUFU (0 | 2 | 4)
 int g_opt_trace_block = 0;       // which leader CTA writes the debug timeline
 static thread_local std::string t_error;
@@ -114,7 +115,7 @@ int sm_count() {
   return n;
 }
 
-cudaError_t set_max_smem_once_impl(const void* kern, int bytes) {
+cudaError_t set_max_smem_once_impl(const void* kern, int bytes, bool max_carveout) {
   static std::mutex mu;
   static std::unordered_map<uint64_t, int> done;       // (kernel, device) -> bytes already granted
   int dev = 0;
@@ -125,6 +126,9 @@ cudaError_t set_max_smem_once_impl(const void* kern, int bytes) {
   auto it = done.find(key);
   if (it != done.end() && it->second >= bytes) return cudaSuccess;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  // several CTAs of this kernel are meant to share an SM: ask for the largest shared-memory carve-out
+  if (e == cudaSuccess && max_carveout)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) done[key] = bytes;
   return e;
 }
@@ -246,6 +250,7 @@ int pv_set_option(const char* name, int value) {
   if (!strcmp(name, "fuse_out")) { g_opt_fuse_out = value; return PV_OK; }
   if (!strcmp(name, "pdl")) { g_opt_pdl = value; return PV_OK; }
   if (!strcmp(name, "bwd_mma")) { g_opt_bwd_mma = value; return PV_OK; }
+  if (!strcmp(name, "bwd_tc")) { g_opt_bwd_tc = value; return PV_OK; }
   if (!strcmp(name, "sattn_poly")) { g_opt_sattn_poly = value; return PV_OK; }
   if (!strcmp(name, "trace_block")) { g_opt_trace_block = value; return PV_OK; }
   PV_FAIL(PV_ERR_INVALID, "unknown option '%s'", name);

@@ -313,7 +313,16 @@ int attn_bwd_mma_tiles(int S, int d) {
   if (d > 80) return 1;
   return S >= 2048 ? 4 : (S >= 512 ? 2 : 1);
 }
+// pv_bwd_tc.cu: the tcgen05 kernel (head_dim 40 / 80); this file's mma.sync kernel serves head_dim 160 and the A/B option
+int attn_bwd_tc_chunks(int S, int d);
+bool attn_bwd_tc_supported(int d, int C);
+int dual_attn_bwd_tc(const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats, void* dQ,
+                     float* part, int nchunk, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                     cudaStream_t stream);
+extern int g_opt_bwd_tc;
+
 int attn_bwd_mma_chunks(int S, int d) {
+  if (g_opt_bwd_tc != 0 && attn_bwd_tc_supported(d, d * 8)) return attn_bwd_tc_chunks(S, d);
   const int rows = BM_ROWS * attn_bwd_mma_tiles(S, d);
   return (S + rows - 1) / rows;
 }
@@ -340,6 +349,8 @@ int dual_attn_bwd_mma(const void* dO, const void* Q, const float* kv_text, const
                       cudaStream_t stream) {
   const int d = C / H;
   PV_REQUIRE(nchunk == attn_bwd_mma_chunks(S, d), "chunk count mismatch (%d for S=%d)", nchunk, S);
+  if (g_opt_bwd_tc != 0 && attn_bwd_tc_supported(d, d * 8))
+    return dual_attn_bwd_tc(dO, Q, kv_text, kv_img, stats, dQ, part, nchunk, B, S, C, H, Lt, Li, w_text, w_img, stream);
   switch (d) {
     case 40: return launch_attn_bwd_mma<40>(dO, Q, kv_text, kv_img, stats, dQ, part, nchunk, B, S, C, H, Lt, Li, w_text, w_img, stream);
     case 80: return launch_attn_bwd_mma<80>(dO, Q, kv_text, kv_img, stats, dQ, part, nchunk, B, S, C, H, Lt, Li, w_text, w_img, stream);

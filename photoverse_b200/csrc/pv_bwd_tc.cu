@@ -1,0 +1,382 @@
+// photoverse_b200 -- dual-branch attention backward core on tcgen05 (bf16 training path, head_dim 40 / 80).
+//
+// Same contract as attn_bwd_mma_kernel (pv_bwd_mma.cu) and attn_bwd_kernel (pv_bwd.cu): from dO, Q [B,S,C] (bf16), the fp32
+// K / V projections and the forward kernel's per-row statistics, dQ [B,S,C] and per-chunk partial dK / dV (fp32) that
+// kv_bwd_reduce_kernel sums.  Reference: the autograd graph of models/attention_processor.py:307-322, 400-420.
+//   p^ = 2^(s cs - m)/l per segment ; dp_k = dO.V_k ; delta_seg = sum_{k in seg} p^_k dp_k ; ds_k = w_seg p^_k (dp_k - delta_seg)
+//   dQ = scale ds K ; dK = scale ds^T Q ; dV = (w p^)^T dO
+// One CTA = T consecutive 128-query-row tiles of one (sample, head); all five contractions are tcgen05.mma (M = 128) with
+// fp32 accumulators in TMEM:
+//   S  = Q K^T   [rows x 96 keys]   A = Q tile  (TMA, 128-byte swizzle, K-major)       B = K image (K-major)
+//   dP = dO V^T  [rows x 96 keys]   A = dO tile                                        B = V image
+//   dQ = dS K    [rows x d]         A = dS image (K-major)                             B = K image read MN-major
+//   dK += dS^T Q [keys x d]         A = dS image read MN-major (transposed for free)   B = Q tile read MN-major
+//   dV += P^T dO [keys x d]         A = P image read MN-major                          B = dO tile read MN-major
+// dK / dV stay in TMEM across the CTA's tiles.  The transposes the mma.sync kernel does with ldmatrix.trans are a bit in
+// the instruction descriptor here (operand "major-ness"): every operand is stored once.
+// Warps: 0 TMA producer (Q / dO, two stages), 1 tcgen05 issuer, 2 TMEM allocator, 4-7 softmax / dS (one thread per query
+// row = TMEM lane), 8-11 dQ drain (and the final dK / dV drain, one thread per key).
+#include "pv_common.cuh"
+#include "pv_host.h"
+#include "pv_softmax.cuh"
+#include "../../include/photoverse_b200.h"
+
+namespace pv {
+
+constexpr int BT_KEYS = PV_KEYS_PAD;          // 96 key slots: keys [0, Lt) text, [Lt, Lt + Li) image, rest zero
+constexpr int BT_THREADS = 384;
+
+template <int D>
+struct BtCfg {
+  static constexpr int DP = (D + 15) / 16 * 16;            // 48 / 80
+  static constexpr int NBOX = (DP + 63) / 64;              // 64-column TMA boxes per Q / dO tile
+  static constexpr int BOX_BYTES = 128 * 128;              // 128 rows x 128 bytes
+  static constexpr int QT_BYTES = NBOX * BOX_BYTES;
+  static constexpr int NKC = DP / 8;                       // 16-byte chunks per key row
+  static constexpr int KV_BYTES = NKC * BT_KEYS * 16;      // K / V image [d chunk][key][8]
+  static constexpr int PS_BYTES = 16 * 128 * 16;           // P / dS image [key chunk (16: M = 128 keys)][row][8 keys]
+  static constexpr int OFF_Q = 0;                          // two stages
+  static constexpr int OFF_DO = OFF_Q + 2 * QT_BYTES;
+  static constexpr int OFF_P = OFF_DO + 2 * QT_BYTES;
+  static constexpr int OFF_DS = OFF_P + PS_BYTES;
+  static constexpr int OFF_K = OFF_DS + PS_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_BAR = OFF_V + KV_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static constexpr int TM_S = 0, TM_DP = BT_KEYS, TM_DQ = 2 * BT_KEYS, TM_DK = TM_DQ + DP, TM_DV = TM_DK + DP;
+  static_assert(TM_DV + DP <= 512, "TMEM columns");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
+
+struct BtParams {
+  const float* kv_text;
+  const float* kv_img;
+  const float* stats;
+  __nv_bfloat16* dQ;
+  float* part;
+  int B, S, C, H, Lt, Li, T;
+  float w_text, w_img, scale, scale_log2e;
+};
+
+template <int D>
+__global__ void __launch_bounds__(BT_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO, const BtParams p) {
+  using Cfg = BtCfg<D>;
+  constexpr int DP = Cfg::DP;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars;          // [2]  Q + dO tile landed
+  uint64_t* q_empty = bars + 2;     // [2]  the tile's last MMAs have completed
+  uint64_t* s_full = bars + 4;      // S and dP of a tile are in TMEM
+  uint64_t* ds_ready = bars + 5;    // P / dS images written (and S / dP read for the last time)
+  uint64_t* mma2_done = bars + 6;   // dQ, dK, dV contributions of a tile accumulated
+  uint64_t* dq_free = bars + 7;     // the dQ accumulator has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int L = p.Lt + p.Li, S = p.S;
+  const int MT = (S + 127) / 128;
+  const int t_begin = chunk * p.T;
+  const int nt = min(p.T, MT - t_begin);            // tiles of this CTA (>= 1 by construction of the grid)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(ds_ready, 4);
+    mbar_init(mma2_done, 1);
+    mbar_init(dq_free, 4);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  // ---- K / V images: fp32 projections -> bf16 (the rounding the forward kernel's tiles have), [d chunk][key][8] ----
+  {
+    const int C2 = 2 * p.C;
+    for (int i = threadIdx.x; i < Cfg::NKC * BT_KEYS; i += BT_THREADS) {
+      const int ch = i / BT_KEYS, k = i - ch * BT_KEYS;
+      uint4 kq = make_uint4(0, 0, 0, 0), vq = kq;
+      if (k < L && ch * 8 < D) {
+        const float* src = (k < p.Lt) ? p.kv_text + (static_cast<size_t>(b) * p.Lt + k) * C2
+                                      : p.kv_img + (static_cast<size_t>(b) * p.Li + (k - p.Lt)) * C2;
+        const float4 k0 = *reinterpret_cast<const float4*>(src + h * D + ch * 8);
+        const float4 k1 = *reinterpret_cast<const float4*>(src + h * D + ch * 8 + 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(src + p.C + h * D + ch * 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + p.C + h * D + ch * 8 + 4);
+        kq = make_uint4(pack_bf16x2(k0.x, k0.y), pack_bf16x2(k0.z, k0.w), pack_bf16x2(k1.x, k1.y), pack_bf16x2(k1.z, k1.w));
+        vq = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+      }
+      *reinterpret_cast<uint4*>(smem + Cfg::OFF_K + i * 16) = kq;
+      *reinterpret_cast<uint4*>(smem + Cfg::OFF_V + i * 16) = vq;
+    }
+    // key chunks 12..15 of the P / dS images (M = 128 keys, 96 real slots) only feed accumulator rows that are never
+    // read; cleared once so that those rows stay finite
+    for (int i = threadIdx.x; i < 4 * 128; i += BT_THREADS) {
+      *reinterpret_cast<uint4*>(smem + Cfg::OFF_P + (12 * 128 + i) * 16) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(smem + Cfg::OFF_DS + (12 * 128 + i) * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer
+    if (elect_one()) {
+      for (int t = 0; t < nt; ++t) {
+        const int s = t & 1;
+        if (t >= 2) mbar_wait(&q_empty[s], ((t >> 1) - 1) & 1);
+        mbar_expect_tx(&q_full[s], 2 * Cfg::QT_BYTES);
+        const int q0 = (t_begin + t) * 128;
+#pragma unroll
+        for (int bx = 0; bx < Cfg::NBOX; ++bx) {
+          tma_load_3d(smem + Cfg::OFF_Q + s * Cfg::QT_BYTES + bx * Cfg::BOX_BYTES, &tmQ, &q_full[s], h * D + bx * 64, q0, b);
+          tma_load_3d(smem + Cfg::OFF_DO + s * Cfg::QT_BYTES + bx * Cfg::BOX_BYTES, &tmdO, &q_full[s], h * D + bx * 64, q0, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- tcgen05 issuer
+    constexpr uint32_t ID_S = umma_idesc_bf16(128, BT_KEYS);                                  // A, B K-major
+    constexpr uint32_t ID_DQ = umma_idesc_bf16(128, DP) | (1u << 16);                         // B MN-major
+    constexpr uint32_t ID_DKV = umma_idesc_bf16(128, DP) | (1u << 15) | (1u << 16);           // A and B MN-major
+    const uint32_t q_addr = smem_u32(smem + Cfg::OFF_Q), do_addr = smem_u32(smem + Cfg::OFF_DO);
+    const uint32_t p_addr = smem_u32(smem + Cfg::OFF_P), ds_addr = smem_u32(smem + Cfg::OFF_DS);
+    const uint32_t k_addr = smem_u32(smem + Cfg::OFF_K), v_addr = smem_u32(smem + Cfg::OFF_V);
+    // K-major 128-byte-swizzled A operand of k step ks (16 dims = 32 bytes inside the swizzled row; 64 dims per box)
+    auto a_sw = [&](uint32_t tile, int ks) {
+      return umma_desc(tile + (ks >> 2) * Cfg::BOX_BYTES + (ks & 3) * 32, 16, 1024, UMMA_LAYOUT_SW128);
+    };
+    auto issue_s_dp = [&](int s) {
+      const uint32_t qt = q_addr + s * Cfg::QT_BYTES, ot = do_addr + s * Cfg::QT_BYTES;
+      const uint64_t kb = umma_desc(k_addr, BT_KEYS * 16, 128, UMMA_LAYOUT_NONE);    // [key][d]: K-major, chunk stride = LBO
+      const uint64_t vb = umma_desc(v_addr, BT_KEYS * 16, 128, UMMA_LAYOUT_NONE);
+#pragma unroll
+      for (int ks = 0; ks < DP / 16; ++ks)
+        umma_bf16_ss(tmem + Cfg::TM_S, a_sw(qt, ks), kb + static_cast<uint64_t>(ks * (2 * BT_KEYS * 16 >> 4)), ID_S, ks > 0);
+#pragma unroll
+      for (int ks = 0; ks < DP / 16; ++ks)
+        umma_bf16_ss(tmem + Cfg::TM_DP, a_sw(ot, ks), vb + static_cast<uint64_t>(ks * (2 * BT_KEYS * 16 >> 4)), ID_S, ks > 0);
+      umma_commit(s_full);
+    };
+    auto issue_grads = [&](int s, bool first) {
+      const uint32_t qt = q_addr + s * Cfg::QT_BYTES, ot = do_addr + s * Cfg::QT_BYTES;
+      // dQ = dS K: A = dS [row][key] K-major (key chunks 2048 bytes apart); B = K image read MN-major (n = dim, k = key):
+      // LBO = 8-key groups (128 bytes), SBO = 8-dim groups (one d chunk = 96 keys x 16 bytes)
+      const uint64_t a_ds = umma_desc(ds_addr, 128 * 16, 128, UMMA_LAYOUT_NONE);
+      const uint64_t b_k = umma_desc(k_addr, 128, BT_KEYS * 16, UMMA_LAYOUT_NONE);
+#pragma unroll
+      for (int ks = 0; ks < BT_KEYS / 16; ++ks)
+        umma_bf16_ss(tmem + Cfg::TM_DQ, a_ds + static_cast<uint64_t>(ks * (2 * 128 * 16 >> 4)), b_k + static_cast<uint64_t>(ks * (256 >> 4)),
+                     ID_DQ, ks > 0);
+      // dK += dS^T Q, dV += P^T dO: A = the same images read MN-major (m = key, k = row): SBO = 8-key groups (2048 bytes),
+      // LBO = 8-row groups (128 bytes); B = the swizzled Q / dO tile read MN-major (n = dim, k = row): 8-row groups 1024
+      // bytes apart (SBO), 64-dim boxes BOX_BYTES apart (LBO); 16 rows per k step
+      const uint64_t a_dst = umma_desc(ds_addr, 128, 128 * 16, UMMA_LAYOUT_NONE);
+      const uint64_t a_pt = umma_desc(p_addr, 128, 128 * 16, UMMA_LAYOUT_NONE);
+      const uint64_t b_q = umma_desc(qt, Cfg::BOX_BYTES, 1024, UMMA_LAYOUT_SW128);
+      const uint64_t b_o = umma_desc(ot, Cfg::BOX_BYTES, 1024, UMMA_LAYOUT_SW128);
+#pragma unroll
+      for (int ks = 0; ks < 128 / 16; ++ks)
+        umma_bf16_ss(tmem + Cfg::TM_DK, a_dst + static_cast<uint64_t>(ks * (256 >> 4)), b_q + static_cast<uint64_t>(ks * (2048 >> 4)),
+                     ID_DKV, (!first || ks > 0) ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 128 / 16; ++ks)
+        umma_bf16_ss(tmem + Cfg::TM_DV, a_pt + static_cast<uint64_t>(ks * (256 >> 4)), b_o + static_cast<uint64_t>(ks * (2048 >> 4)),
+                     ID_DKV, (!first || ks > 0) ? 1u : 0u);
+      umma_commit(mma2_done);
+      umma_commit(&q_empty[s]);
+    };
+    mbar_wait(&q_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) issue_s_dp(0);
+    __syncwarp();
+    for (int t = 0; t < nt; ++t) {
+      const int s = t & 1;
+      mbar_wait(ds_ready, t & 1);                       // also: S / dP of tile t have been read for the last time
+      if (t > 0) mbar_wait(dq_free, (t - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) issue_grads(s, t == 0);
+      __syncwarp();
+      if (t + 1 < nt) {
+        mbar_wait(&q_full[s ^ 1], ((t + 1) >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) issue_s_dp(s ^ 1);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ---------------------------------------------------------------- softmax / dS: one thread per query row
+    const int wq = warp & 3, row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t s_t = tmem + lane_base + Cfg::TM_S, dp_t = tmem + lane_base + Cfg::TM_DP;
+    const uint32_t p_row = smem_u32(smem + Cfg::OFF_P) + row * 16, ds_row = smem_u32(smem + Cfg::OFF_DS) + row * 16;
+    const int Lt = p.Lt;
+    for (int t = 0; t < nt; ++t) {
+      const int grow = (t_begin + t) * 128 + row;
+      float4 st = make_float4(0.f, 1.f, 0.f, 1.f);
+      if (grow < S) st = reinterpret_cast<const float4*>(p.stats)[(static_cast<size_t>(b) * p.H + h) * S + grow];
+      const float ilt = grow < S ? 1.f / st.y : 0.f, ili = grow < S ? 1.f / st.w : 0.f;     // rows past S: p^ = 0
+      mbar_wait(s_full, t & 1);
+      tc_fence_after();
+      // pass 1: p^ (kept in registers) and the two segment sums of p^ dp
+      uint32_t ph[BT_KEYS];
+      tmem_ld32_raw(s_t, ph);
+      tmem_ld32_raw(s_t + 32, ph + 32);
+      tmem_ld32_raw(s_t + 64, ph + 64);
+      tmem_ld_wait();
+      float dsum_t = 0.f, dsum_i = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
+        uint32_t dp[32];
+        tmem_ld32_raw(dp_t + c0, dp);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int key = c0 + i;
+          const bool is_t = key < Lt;
+          const float e = fast_exp2(fmaf(__uint_as_float(ph[key]), p.scale_log2e, is_t ? -st.x : -st.z)) * (is_t ? ilt : ili);
+          ph[key] = __float_as_uint(key < L ? e : 0.f);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int key = c0 + i;
+          const float pd = __uint_as_float(ph[key]) * __uint_as_float(dp[i]);
+          if (key < Lt) dsum_t += pd; else dsum_i += pd;
+        }
+      }
+      // the previous tile's dK / dV contractions have read the P / dS images
+      if (t > 0) mbar_wait(mma2_done, (t - 1) & 1);
+      // pass 2: w p^ and scale w p^ (dp - delta), packed to bf16, 8 keys (16 bytes) at a time
+      const float swt = p.scale * p.w_text, swi = p.scale * p.w_img;
+#pragma unroll
+      for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
+        uint32_t dp[32];
+        tmem_ld32_raw(dp_t + c0, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pw[4], dw[4];
+#pragma unroll
+          for (int q2 = 0; q2 < 4; ++q2) {
+            float pv2[2], dv2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = 8 * c + 2 * q2 + e, key = c0 + i;
+              const bool is_t = key < Lt;
+              const float pe = __uint_as_float(ph[key]);
+              pv2[e] = (is_t ? p.w_text : p.w_img) * pe;
+              dv2[e] = (is_t ? swt : swi) * pe * (__uint_as_float(dp[i]) - (is_t ? dsum_t : dsum_i));
+            }
+            pw[q2] = pack_bf16x2(pv2[0], pv2[1]);
+            dw[q2] = pack_bf16x2(dv2[0], dv2[1]);
+          }
+          const int kc = c0 / 8 + c;
+          st_shared_v4_a(p_row + kc * 2048, pw[0], pw[1], pw[2], pw[3]);
+          st_shared_v4_a(ds_row + kc * 2048, dw[0], dw[1], dw[2], dw[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
+    }
+  } else if (warp >= 8) {
+    // ---------------------------------------------------------------- dQ drain; at the end dK / dV
+    const int wq = warp & 3, row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    for (int t = 0; t < nt; ++t) {
+      mbar_wait(mma2_done, t & 1);
+      tc_fence_after();
+      const int grow = (t_begin + t) * 128 + row;
+      __nv_bfloat16* dst = p.dQ + (static_cast<size_t>(b) * S + grow) * p.C + h * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint32_t o[8];
+        tmem_ld_x8(tmem + lane_base + Cfg::TM_DQ + c, o);
+        tmem_ld_wait();
+        if (grow < S)
+          st_global_v4(dst + c, pack_bf16x2(__uint_as_float(o[0]), __uint_as_float(o[1])), pack_bf16x2(__uint_as_float(o[2]), __uint_as_float(o[3])),
+                       pack_bf16x2(__uint_as_float(o[4]), __uint_as_float(o[5])), pack_bf16x2(__uint_as_float(o[6]), __uint_as_float(o[7])));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+    }
+    // dK / dV: TMEM lane = key.  (tcgen05.ld is warp-collective: every lane loads, only the lanes of real keys store.)
+    const int key = row;
+    float* dstK = p.part + ((static_cast<size_t>(chunk) * p.B + b) * p.H + h) * 2 * L * D + static_cast<size_t>(key) * D;
+    float* dstV = dstK + static_cast<size_t>(L) * D;
+#pragma unroll
+    for (int c = 0; c < D; c += 8) {
+      uint32_t kk[8], vv[8];
+      tmem_ld_x8(tmem + lane_base + Cfg::TM_DK + c, kk);
+      tmem_ld_x8(tmem + lane_base + Cfg::TM_DV + c, vv);
+      tmem_ld_wait();
+      if (key < L) {
+        *reinterpret_cast<uint4*>(dstK + c) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+        *reinterpret_cast<uint4*>(dstK + c + 4) = make_uint4(kk[4], kk[5], kk[6], kk[7]);
+        *reinterpret_cast<uint4*>(dstV + c) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+        *reinterpret_cast<uint4*>(dstV + c + 4) = make_uint4(vv[4], vv[5], vv[6], vv[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// 128-row tiles per CTA (a function of the layer shape only: kv_bwd_reduce must know the chunk count)
+int attn_bwd_tc_tiles(int S, int d) {
+  (void)d;
+  return S >= 2048 ? 8 : (S >= 512 ? 4 : 2);
+}
+int attn_bwd_tc_chunks(int S, int d) {
+  const int rows = 128 * attn_bwd_tc_tiles(S, d);
+  return (S + rows - 1) / rows;
+}
+bool attn_bwd_tc_supported(int d, int C) { return (d == 40 || d == 80) && C % 8 == 0; }
+
+template <int D>
+static int launch_attn_bwd_tc(const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats, void* dQ,
+                              float* part, int nchunk, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                              cudaStream_t stream) {
+  using Cfg = BtCfg<D>;
+  CUtensorMap tmQ, tmdO;
+  if (make_tmap_3d(&tmQ, Q, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, 64, 128, 1, Swz::B128)) return PV_ERR_CUDA;
+  if (make_tmap_3d(&tmdO, dO, 2, C, S, B, C * 2ull, static_cast<uint64_t>(S) * C * 2, 64, 128, 1, Swz::B128)) return PV_ERR_CUDA;
+  BtParams p;
+  p.kv_text = kv_text; p.kv_img = kv_img; p.stats = stats;
+  p.dQ = static_cast<__nv_bfloat16*>(dQ); p.part = part;
+  p.B = B; p.S = S; p.C = C; p.H = H; p.Lt = Lt; p.Li = Li; p.T = attn_bwd_tc_tiles(S, D);
+  p.w_text = w_text; p.w_img = w_img;
+  p.scale = 1.f / sqrtf(static_cast<float>(D));
+  p.scale_log2e = p.scale * 1.4426950408889634f;
+  auto kern = attn_bwd_tc_kernel<D>;
+  PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES));
+  kern<<<dim3(nchunk, H, B), BT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmdO, p);
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
+int dual_attn_bwd_tc(const void* dO, const void* Q, const float* kv_text, const float* kv_img, const float* stats, void* dQ,
+                     float* part, int nchunk, int B, int S, int C, int H, int Lt, int Li, float w_text, float w_img,
+                     cudaStream_t stream) {
+  const int d = C / H;
+  PV_REQUIRE(nchunk == attn_bwd_tc_chunks(S, d), "chunk count mismatch (%d for S=%d)", nchunk, S);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(dO) | reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(dQ)) % 16 == 0,
+             "pointers must be 16-byte aligned");
+  if (d == 40) return launch_attn_bwd_tc<40>(dO, Q, kv_text, kv_img, stats, dQ, part, nchunk, B, S, C, H, Lt, Li, w_text, w_img, stream);
+  if (d == 80) return launch_attn_bwd_tc<80>(dO, Q, kv_text, kv_img, stats, dQ, part, nchunk, B, S, C, H, Lt, Li, w_text, w_img, stream);
+  PV_FAIL(PV_ERR_UNSUPPORTED, "head_dim %d: tcgen05 backward supports 40 / 80", d);
+}
+
+}  // namespace pv

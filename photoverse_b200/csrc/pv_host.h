@@ -56,9 +56,11 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0
 
 int sm_count();                       // SM count of the CURRENT device (cached per device)
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set once per (kernel, device)
-cudaError_t set_max_smem_once_impl(const void* kern, int bytes);
+cudaError_t set_max_smem_once_impl(const void* kern, int bytes, bool max_carveout);
 template <typename K>
-cudaError_t set_max_smem_once(K kern, int bytes) { return set_max_smem_once_impl(reinterpret_cast<const void*>(kern), bytes); }
+cudaError_t set_max_smem_once(K kern, int bytes, bool max_carveout = false) {
+  return set_max_smem_once_impl(reinterpret_cast<const void*>(kern), bytes, max_carveout);
+}
 
 extern int g_opt_pdl;
 // Launch with programmatic stream serialisation (PDL) when enabled: the kernel must call pdl_wait() before touching any

@@ -15,8 +15,6 @@
 //
 // The same K / V image serves both contractions: as the K-major B operand of Q K^T (rows = keys, 16-byte chunks along d)
 // and as the MN-major B operand of P V (rows = the contraction index, chunks along the output columns) -- no transpose.
-#include <stdlib.h>
-
 #include "pv_common.cuh"
 #include "pv_host.h"
 #include "pv_softmax.cuh"
@@ -568,25 +566,9 @@ static int launch_sattn(const void* q, const void* k, const void* v, long long l
   PV_REQUIRE(units < (1ll << 30), "too many work units");
   p.units = static_cast<int>(units);
   auto kern = self_attn_fwd_kernel<D, PF>;
-  PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES));
-  if (Cfg::CTAS_PER_SM > 1) {
-    static bool once = false;
-    if (!once) {
-      PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      int nb = 0;
-      PV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SA_THREADS, Cfg::SMEM_BYTES));
-      if (getenv("PV_SATTN_VERBOSE")) {
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, kern);
-        int nb0 = 0, nb64 = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, kern, SA_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb64, kern, SA_THREADS, 64 * 1024);
-        fprintf(stderr, "self_attn_fwd_kernel<%d>: %d CTAs per SM (smem %d B; with 0 B: %d, with 64 KB: %d; numRegs %d static smem %zu maxThreads %d)\n",
-                D, nb, Cfg::SMEM_BYTES, nb0, nb64, fa.numRegs, fa.sharedSizeBytes, fa.maxThreadsPerBlock);
-      }
-      once = true;
-    }
-  }
+  // (cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for every kernel that allocates tensor memory; two CTAs of
+  // 256 columns each do share an SM -- tools/ubench/occ_test.cu)
+  PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES, Cfg::CTAS_PER_SM > 1));
   const long long sms = static_cast<long long>(sm_count()) * Cfg::CTAS_PER_SM;
   const int grid = static_cast<int>(units < sms ? units : sms);
   PV_CUDA(launch_pdl(kern, dim3(grid), dim3(SA_THREADS), Cfg::SMEM_BYTES, stream, tmO, p));
