@@ -58,7 +58,7 @@ struct BtParams {
   float w_text, w_img, scale, scale_log2e;
 };
 
-template <int D>
+template <int D, bool LT77>      // LT77: 77 text keys (CLIP) -- the segment of every key slot is known at compile time
 __global__ void __launch_bounds__(BT_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO, const BtParams p) {
   using Cfg = BtCfg<D>;
@@ -226,61 +226,156 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float ilt = grow < S ? 1.f / st.y : 0.f, ili = grow < S ? 1.f / st.w : 0.f;     // rows past S: p^ = 0
       mbar_wait(s_full, t & 1);
       tc_fence_after();
-      // pass 1: p^ (kept in registers) and the two segment sums of p^ dp
-      uint32_t ph[BT_KEYS];
-      tmem_ld32_raw(s_t, ph);
-      tmem_ld32_raw(s_t + 32, ph + 32);
-      tmem_ld32_raw(s_t + 64, ph + 64);
-      tmem_ld_wait();
-      float dsum_t = 0.f, dsum_i = 0.f;
-#pragma unroll
-      for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
-        uint32_t dp[32];
-        tmem_ld32_raw(dp_t + c0, dp);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int key = c0 + i;
-          const bool is_t = key < Lt;
-          const float e = fast_exp2(fmaf(__uint_as_float(ph[key]), p.scale_log2e, is_t ? -st.x : -st.z)) * (is_t ? ilt : ili);
-          ph[key] = __float_as_uint(key < L ? e : 0.f);
+      if constexpr (LT77) {
+        // ---- 77 text keys: packed fp32x2 arithmetic, no per-key selects.  Pairs (k, k+1): k + 1 < 77 text, k >= 78 image
+        // (masked by k < L), the pair (76, 77) straddles the boundary and is done in scalar form.
+        float e[BT_KEYS];
+        {
+          uint32_t* eu = reinterpret_cast<uint32_t*>(e);
+          tmem_ld32_raw(s_t, eu);
+          tmem_ld32_raw(s_t + 32, eu + 32);
+          tmem_ld32_raw(s_t + 64, eu + 64);
+          tmem_ld_wait();
         }
-        tmem_ld_wait();
+        const uint64_t sc2 = f2_pack(p.scale_log2e, p.scale_log2e);
+        const uint64_t nmt2 = f2_pack(-st.x, -st.x), nmi2 = f2_pack(-st.z, -st.z);
+        const uint64_t ilt2 = f2_pack(ilt, ilt), ili2 = f2_pack(ili, ili);
+        uint64_t dt2 = f2_pack(0.f, 0.f), di2 = dt2;
+        float dt1 = 0.f, di1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int key = c0 + i;
-          const float pd = __uint_as_float(ph[key]) * __uint_as_float(dp[i]);
-          if (key < Lt) dsum_t += pd; else dsum_i += pd;
-        }
-      }
-      // the previous tile's dK / dV contractions have read the P / dS images
-      if (t > 0) mbar_wait(mma2_done, (t - 1) & 1);
-      // pass 2: w p^ and scale w p^ (dp - delta), packed to bf16, 8 keys (16 bytes) at a time
-      const float swt = p.scale * p.w_text, swi = p.scale * p.w_img;
+        for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
+          uint32_t dp[32];
+          tmem_ld32_raw(dp_t + c0, dp);
 #pragma unroll
-      for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
-        uint32_t dp[32];
-        tmem_ld32_raw(dp_t + c0, dp);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pw[4], dw[4];
-#pragma unroll
-          for (int q2 = 0; q2 < 4; ++q2) {
-            float pv2[2], dv2[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int i = 8 * c + 2 * q2 + e, key = c0 + i;
-              const bool is_t = key < Lt;
-              const float pe = __uint_as_float(ph[key]);
-              pv2[e] = (is_t ? p.w_text : p.w_img) * pe;
-              dv2[e] = (is_t ? swt : swi) * pe * (__uint_as_float(dp[i]) - (is_t ? dsum_t : dsum_i));
+          for (int i = 0; i < 32; i += 2) {
+            const int key = c0 + i;
+            if (key + 1 < 77) {
+              float a, b2;
+              f2_unpack(f2_fma(f2_pack(e[key], e[key + 1]), sc2, nmt2), a, b2);
+              f2_unpack(f2_mul(f2_pack(fast_exp2(a), fast_exp2(b2)), ilt2), e[key], e[key + 1]);
+            } else if (key >= 78) {
+              float a, b2;
+              f2_unpack(f2_fma(f2_pack(e[key], e[key + 1]), sc2, nmi2), a, b2);
+              f2_unpack(f2_mul(f2_pack(fast_exp2(a), fast_exp2(b2)), ili2), a, b2);
+              e[key] = key < L ? a : 0.f;
+              e[key + 1] = key + 1 < L ? b2 : 0.f;
+            } else {                                                      // keys 76 (text) and 77 (image, always present)
+              e[76] = fast_exp2(fmaf(e[76], p.scale_log2e, -st.x)) * ilt;
+              e[77] = fast_exp2(fmaf(e[77], p.scale_log2e, -st.z)) * ili;
             }
-            pw[q2] = pack_bf16x2(pv2[0], pv2[1]);
-            dw[q2] = pack_bf16x2(dv2[0], dv2[1]);
           }
-          const int kc = c0 / 8 + c;
-          st_shared_v4_a(p_row + kc * 2048, pw[0], pw[1], pw[2], pw[3]);
-          st_shared_v4_a(ds_row + kc * 2048, dw[0], dw[1], dw[2], dw[3]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int key = c0 + i;
+            const uint64_t pd = f2_pack(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1]));
+            if (key + 1 < 77) dt2 = f2_fma(f2_pack(e[key], e[key + 1]), pd, dt2);
+            else if (key >= 78) di2 = f2_fma(f2_pack(e[key], e[key + 1]), pd, di2);
+            else { dt1 = e[76] * __uint_as_float(dp[i]); di1 = e[77] * __uint_as_float(dp[i + 1]); }
+          }
+        }
+        float s0, s1;
+        f2_unpack(dt2, s0, s1);
+        const float dsum_t = s0 + s1 + dt1;
+        f2_unpack(di2, s0, s1);
+        const float dsum_i = s0 + s1 + di1;
+        // the previous tile's dK / dV contractions have read the P / dS images
+        if (t > 0) mbar_wait(mma2_done, (t - 1) & 1);
+        const float swt = p.scale * p.w_text, swi = p.scale * p.w_img;
+        const uint64_t wt2 = f2_pack(p.w_text, p.w_text), wi2 = f2_pack(p.w_img, p.w_img);
+        const uint64_t swt2 = f2_pack(swt, swt), swi2 = f2_pack(swi, swi);
+        const uint64_t ndt2 = f2_pack(-dsum_t, -dsum_t), ndi2 = f2_pack(-dsum_i, -dsum_i);
+#pragma unroll
+        for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
+          uint32_t dp[32];
+          tmem_ld32_raw(dp_t + c0, dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pw[4], dw[4];
+#pragma unroll
+            for (int q2 = 0; q2 < 4; ++q2) {
+              const int i = 8 * c + 2 * q2, key = c0 + i;
+              const uint64_t e2 = f2_pack(e[key], e[key + 1]);
+              const uint64_t pd = f2_pack(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1]));
+              float a, b2, c1, d1;
+              if (key + 1 < 77) {
+                f2_unpack(f2_mul(e2, wt2), a, b2);
+                f2_unpack(f2_mul(f2_mul(e2, swt2), f2_add(pd, ndt2)), c1, d1);
+              } else if (key >= 78) {
+                f2_unpack(f2_mul(e2, wi2), a, b2);
+                f2_unpack(f2_mul(f2_mul(e2, swi2), f2_add(pd, ndi2)), c1, d1);
+              } else {
+                a = p.w_text * e[76];
+                b2 = p.w_img * e[77];
+                c1 = swt * e[76] * (__uint_as_float(dp[i]) - dsum_t);
+                d1 = swi * e[77] * (__uint_as_float(dp[i + 1]) - dsum_i);
+              }
+              pw[q2] = pack_bf16x2(a, b2);
+              dw[q2] = pack_bf16x2(c1, d1);
+            }
+            const int kc = c0 / 8 + c;
+            st_shared_v4_a(p_row + kc * 2048, pw[0], pw[1], pw[2], pw[3]);
+            st_shared_v4_a(ds_row + kc * 2048, dw[0], dw[1], dw[2], dw[3]);
+          }
+        }
+      } else {
+        // pass 1: p^ (kept in registers) and the two segment sums of p^ dp
+        uint32_t ph[BT_KEYS];
+        tmem_ld32_raw(s_t, ph);
+        tmem_ld32_raw(s_t + 32, ph + 32);
+        tmem_ld32_raw(s_t + 64, ph + 64);
+        tmem_ld_wait();
+        float dsum_t = 0.f, dsum_i = 0.f;
+  #pragma unroll
+        for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
+          uint32_t dp[32];
+          tmem_ld32_raw(dp_t + c0, dp);
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = c0 + i;
+            const bool is_t = key < Lt;
+            const float e = fast_exp2(fmaf(__uint_as_float(ph[key]), p.scale_log2e, is_t ? -st.x : -st.z)) * (is_t ? ilt : ili);
+            ph[key] = __float_as_uint(key < L ? e : 0.f);
+          }
+          tmem_ld_wait();
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = c0 + i;
+            const float pd = __uint_as_float(ph[key]) * __uint_as_float(dp[i]);
+            if (key < Lt) dsum_t += pd; else dsum_i += pd;
+          }
+        }
+        // the previous tile's dK / dV contractions have read the P / dS images
+        if (t > 0) mbar_wait(mma2_done, (t - 1) & 1);
+        // pass 2: w p^ and scale w p^ (dp - delta), packed to bf16, 8 keys (16 bytes) at a time
+        const float swt = p.scale * p.w_text, swi = p.scale * p.w_img;
+  #pragma unroll
+        for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
+          uint32_t dp[32];
+          tmem_ld32_raw(dp_t + c0, dp);
+          tmem_ld_wait();
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pw[4], dw[4];
+  #pragma unroll
+            for (int q2 = 0; q2 < 4; ++q2) {
+              float pv2[2], dv2[2];
+  #pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int i = 8 * c + 2 * q2 + e, key = c0 + i;
+                const bool is_t = key < Lt;
+                const float pe = __uint_as_float(ph[key]);
+                pv2[e] = (is_t ? p.w_text : p.w_img) * pe;
+                dv2[e] = (is_t ? swt : swi) * pe * (__uint_as_float(dp[i]) - (is_t ? dsum_t : dsum_i));
+              }
+              pw[q2] = pack_bf16x2(pv2[0], pv2[1]);
+              dw[q2] = pack_bf16x2(dv2[0], dv2[1]);
+            }
+            const int kc = c0 / 8 + c;
+            st_shared_v4_a(p_row + kc * 2048, pw[0], pw[1], pw[2], pw[3]);
+            st_shared_v4_a(ds_row + kc * 2048, dw[0], dw[1], dw[2], dw[3]);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -360,9 +455,15 @@ static int launch_attn_bwd_tc(const void* dO, const void* Q, const float* kv_tex
   p.w_text = w_text; p.w_img = w_img;
   p.scale = 1.f / sqrtf(static_cast<float>(D));
   p.scale_log2e = p.scale * 1.4426950408889634f;
-  auto kern = attn_bwd_tc_kernel<D>;
-  PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES));
-  kern<<<dim3(nchunk, H, B), BT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmdO, p);
+  if (Lt == 77) {
+    auto kern = attn_bwd_tc_kernel<D, true>;
+    PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES));
+    kern<<<dim3(nchunk, H, B), BT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmdO, p);
+  } else {
+    auto kern = attn_bwd_tc_kernel<D, false>;
+    PV_CUDA(set_max_smem_once(kern, Cfg::SMEM_BYTES));
+    kern<<<dim3(nchunk, H, B), BT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmdO, p);
+  }
   PV_LAUNCHED();
   return PV_OK;
 }
