@@ -201,16 +201,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int t = 0; t < nt; ++t) {
       const int s = t & 1;
       mbar_wait(ds_ready, t & 1);                       // also: S / dP of tile t have been read for the last time
-      if (t > 0) mbar_wait(dq_free, (t - 1) & 1);
-      tc_fence_after();
-      if (elect_one()) issue_grads(s, t == 0);
-      __syncwarp();
+      // the next tile's S / dP first: its softmax (the longest stage) then runs under this tile's gradient contractions
       if (t + 1 < nt) {
         mbar_wait(&q_full[s ^ 1], ((t + 1) >> 1) & 1);
         tc_fence_after();
         if (elect_one()) issue_s_dp(s ^ 1);
         __syncwarp();
       }
+      if (t > 0) mbar_wait(dq_free, (t - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) issue_grads(s, t == 0);
+      __syncwarp();
     }
   } else if (warp >= 4 && warp < 8) {
     // ---------------------------------------------------------------- softmax / dS: one thread per query row
@@ -219,10 +220,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t s_t = tmem + lane_base + Cfg::TM_S, dp_t = tmem + lane_base + Cfg::TM_DP;
     const uint32_t p_row = smem_u32(smem + Cfg::OFF_P) + row * 16, ds_row = smem_u32(smem + Cfg::OFF_DS) + row * 16;
     const int Lt = p.Lt;
+    auto load_stats = [&](int t) {
+      const int r = (t_begin + t) * 128 + row;
+      float4 v = make_float4(0.f, 1.f, 0.f, 1.f);
+      if (t < nt && r < S) v = __ldg(reinterpret_cast<const float4*>(p.stats) + (static_cast<size_t>(b) * p.H + h) * S + r);
+      return v;
+    };
+    float4 st_next = load_stats(0);
     for (int t = 0; t < nt; ++t) {
       const int grow = (t_begin + t) * 128 + row;
-      float4 st = make_float4(0.f, 1.f, 0.f, 1.f);
-      if (grow < S) st = reinterpret_cast<const float4*>(p.stats)[(static_cast<size_t>(b) * p.H + h) * S + grow];
+      const float4 st = st_next;
+      st_next = load_stats(t + 1);                   // one tile ahead: the load's latency hides under this tile's work
       const float ilt = grow < S ? 1.f / st.y : 0.f, ili = grow < S ? 1.f / st.w : 0.f;     // rows past S: p^ = 0
       mbar_wait(s_full, t & 1);
       tc_fence_after();
