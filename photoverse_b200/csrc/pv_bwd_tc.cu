@@ -14,8 +14,10 @@
 //   dV += P^T dO [keys x d]         A = P image read MN-major                          B = dO tile read MN-major
 // dK / dV stay in TMEM across the CTA's tiles.  The transposes the mma.sync kernel does with ldmatrix.trans are a bit in
 // the instruction descriptor here (operand "major-ness"): every operand is stored once.
-// Warps: 0 TMA producer (Q / dO, two stages), 1 tcgen05 issuer, 2 TMEM allocator, 4-7 softmax / dS (one thread per query
-// row = TMEM lane), 8-11 dQ drain (and the final dK / dV drain, one thread per key).
+// Warps: 0 TMA producer (Q / dO, two stages), 1 tcgen05 issuer, 2 TMEM allocator, 4-7 and 8-11 two groups with one thread
+// per query row (= TMEM lane) each: softmax / dS of half the key slots, half of the dQ drain, dK resp. dV drain at the end.
+#include <type_traits>
+
 #include "pv_common.cuh"
 #include "pv_host.h"
 #include "pv_softmax.cuh"
@@ -41,7 +43,8 @@ struct BtCfg {
   static constexpr int OFF_DS = OFF_P + PS_BYTES;
   static constexpr int OFF_K = OFF_DS + PS_BYTES;
   static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_BAR = OFF_V + KV_BYTES;
+  static constexpr int OFF_XCH = OFF_V + KV_BYTES;        // partial segment sums exchanged by the two groups
+  static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * 128 * 2 * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
   static constexpr int TM_S = 0, TM_DP = BT_KEYS, TM_DQ = 2 * BT_KEYS, TM_DK = TM_DQ + DP, TM_DV = TM_DK + DP;
   static_assert(TM_DV + DP <= 512, "TMEM columns");
@@ -71,7 +74,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* ds_ready = bars + 5;    // P / dS images written (and S / dP read for the last time)
   uint64_t* mma2_done = bars + 6;   // dQ, dK, dV contributions of a tile accumulated
   uint64_t* dq_free = bars + 7;     // the dQ accumulator has been read
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sdp_free = bars + 8;    // S and dP of a tile are in registers: the next tile's may overwrite them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -86,9 +90,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&q_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(ds_ready, 4);
+    mbar_init(ds_ready, 8);
     mbar_init(mma2_done, 1);
-    mbar_init(dq_free, 4);
+    mbar_init(dq_free, 8);
+    mbar_init(sdp_free, 8);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmdO);
@@ -200,25 +205,31 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
     for (int t = 0; t < nt; ++t) {
       const int s = t & 1;
-      mbar_wait(ds_ready, t & 1);                       // also: S / dP of tile t have been read for the last time
-      // the next tile's S / dP first: its softmax (the longest stage) then runs under this tile's gradient contractions
+      // the next tile's S / dP as soon as this tile's are in registers: they are ready when the groups come back
       if (t + 1 < nt) {
         mbar_wait(&q_full[s ^ 1], ((t + 1) >> 1) & 1);
+        mbar_wait(sdp_free, t & 1);
         tc_fence_after();
         if (elect_one()) issue_s_dp(s ^ 1);
         __syncwarp();
       }
+      mbar_wait(ds_ready, t & 1);
       if (t > 0) mbar_wait(dq_free, (t - 1) & 1);
       tc_fence_after();
       if (elect_one()) issue_grads(s, t == 0);
       __syncwarp();
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ---------------------------------------------------------------- softmax / dS: one thread per query row
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax / dS / drains: two groups of 128 threads, one
+    // thread per query row (= TMEM lane) in each; group 0 takes key slots [0, 48), group 1 [48, 96) of every row (the dS pass
+    // is the longest stage of the pipeline and a serial instruction stream per warp); they exchange their partial
+    // segment sums through shared memory, split the dQ drain by columns, and drain dK (group 0) / dV (group 1) at the end.
+    const int wg = (warp - 4) >> 2;
     const int wq = warp & 3, row = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
     const uint32_t s_t = tmem + lane_base + Cfg::TM_S, dp_t = tmem + lane_base + Cfg::TM_DP;
     const uint32_t p_row = smem_u32(smem + Cfg::OFF_P) + row * 16, ds_row = smem_u32(smem + Cfg::OFF_DS) + row * 16;
+    float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_XCH);            // [parity][group][row][2]
     const int Lt = p.Lt;
     auto load_stats = [&](int t) {
       const int r = (t_begin + t) * 128 + row;
@@ -226,182 +237,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (t < nt && r < S) v = __ldg(reinterpret_cast<const float4*>(p.stats) + (static_cast<size_t>(b) * p.H + h) * S + r);
       return v;
     };
-    float4 st_next = load_stats(0);
-    for (int t = 0; t < nt; ++t) {
-      const int grow = (t_begin + t) * 128 + row;
-      const float4 st = st_next;
-      st_next = load_stats(t + 1);                   // one tile ahead: the load's latency hides under this tile's work
-      const float ilt = grow < S ? 1.f / st.y : 0.f, ili = grow < S ? 1.f / st.w : 0.f;     // rows past S: p^ = 0
-      mbar_wait(s_full, t & 1);
-      tc_fence_after();
-      if constexpr (LT77) {
-        // ---- 77 text keys: packed fp32x2 arithmetic, no per-key selects.  Pairs (k, k+1): k + 1 < 77 text, k >= 78 image
-        // (masked by k < L), the pair (76, 77) straddles the boundary and is done in scalar form.
-        float e[BT_KEYS];
-        {
-          uint32_t* eu = reinterpret_cast<uint32_t*>(e);
-          tmem_ld32_raw(s_t, eu);
-          tmem_ld32_raw(s_t + 32, eu + 32);
-          tmem_ld32_raw(s_t + 64, eu + 64);
-          tmem_ld_wait();
-        }
-        const uint64_t sc2 = f2_pack(p.scale_log2e, p.scale_log2e);
-        const uint64_t nmt2 = f2_pack(-st.x, -st.x), nmi2 = f2_pack(-st.z, -st.z);
-        const uint64_t ilt2 = f2_pack(ilt, ilt), ili2 = f2_pack(ili, ili);
-        uint64_t dt2 = f2_pack(0.f, 0.f), di2 = dt2;
-        float dt1 = 0.f, di1 = 0.f;
-#pragma unroll
-        for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
-          uint32_t dp[32];
-          tmem_ld32_raw(dp_t + c0, dp);
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const int key = c0 + i;
-            if (key + 1 < 77) {
-              float a, b2;
-              f2_unpack(f2_fma(f2_pack(e[key], e[key + 1]), sc2, nmt2), a, b2);
-              f2_unpack(f2_mul(f2_pack(fast_exp2(a), fast_exp2(b2)), ilt2), e[key], e[key + 1]);
-            } else if (key >= 78) {
-              float a, b2;
-              f2_unpack(f2_fma(f2_pack(e[key], e[key + 1]), sc2, nmi2), a, b2);
-              f2_unpack(f2_mul(f2_pack(fast_exp2(a), fast_exp2(b2)), ili2), a, b2);
-              e[key] = key < L ? a : 0.f;
-              e[key + 1] = key + 1 < L ? b2 : 0.f;
-            } else {                                                      // keys 76 (text) and 77 (image, always present)
-              e[76] = fast_exp2(fmaf(e[76], p.scale_log2e, -st.x)) * ilt;
-              e[77] = fast_exp2(fmaf(e[77], p.scale_log2e, -st.z)) * ili;
-            }
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const int key = c0 + i;
-            const uint64_t pd = f2_pack(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1]));
-            if (key + 1 < 77) dt2 = f2_fma(f2_pack(e[key], e[key + 1]), pd, dt2);
-            else if (key >= 78) di2 = f2_fma(f2_pack(e[key], e[key + 1]), pd, di2);
-            else { dt1 = e[76] * __uint_as_float(dp[i]); di1 = e[77] * __uint_as_float(dp[i + 1]); }
-          }
-        }
-        float s0, s1;
-        f2_unpack(dt2, s0, s1);
-        const float dsum_t = s0 + s1 + dt1;
-        f2_unpack(di2, s0, s1);
-        const float dsum_i = s0 + s1 + di1;
-        // the previous tile's dK / dV contractions have read the P / dS images
-        if (t > 0) mbar_wait(mma2_done, (t - 1) & 1);
-        const float swt = p.scale * p.w_text, swi = p.scale * p.w_img;
-        const uint64_t wt2 = f2_pack(p.w_text, p.w_text), wi2 = f2_pack(p.w_img, p.w_img);
-        const uint64_t swt2 = f2_pack(swt, swt), swi2 = f2_pack(swi, swi);
-        const uint64_t ndt2 = f2_pack(-dsum_t, -dsum_t), ndi2 = f2_pack(-dsum_i, -dsum_i);
-#pragma unroll
-        for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
-          uint32_t dp[32];
-          tmem_ld32_raw(dp_t + c0, dp);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t pw[4], dw[4];
-#pragma unroll
-            for (int q2 = 0; q2 < 4; ++q2) {
-              const int i = 8 * c + 2 * q2, key = c0 + i;
-              const uint64_t e2 = f2_pack(e[key], e[key + 1]);
-              const uint64_t pd = f2_pack(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1]));
-              float a, b2, c1, d1;
-              if (key + 1 < 77) {
-                f2_unpack(f2_mul(e2, wt2), a, b2);
-                f2_unpack(f2_mul(f2_mul(e2, swt2), f2_add(pd, ndt2)), c1, d1);
-              } else if (key >= 78) {
-                f2_unpack(f2_mul(e2, wi2), a, b2);
-                f2_unpack(f2_mul(f2_mul(e2, swi2), f2_add(pd, ndi2)), c1, d1);
-              } else {
-                a = p.w_text * e[76];
-                b2 = p.w_img * e[77];
-                c1 = swt * e[76] * (__uint_as_float(dp[i]) - dsum_t);
-                d1 = swi * e[77] * (__uint_as_float(dp[i + 1]) - dsum_i);
-              }
-              pw[q2] = pack_bf16x2(a, b2);
-              dw[q2] = pack_bf16x2(c1, d1);
-            }
-            const int kc = c0 / 8 + c;
-            st_shared_v4_a(p_row + kc * 2048, pw[0], pw[1], pw[2], pw[3]);
-            st_shared_v4_a(ds_row + kc * 2048, dw[0], dw[1], dw[2], dw[3]);
-          }
-        }
-      } else {
-        // pass 1: p^ (kept in registers) and the two segment sums of p^ dp
-        uint32_t ph[BT_KEYS];
-        tmem_ld32_raw(s_t, ph);
-        tmem_ld32_raw(s_t + 32, ph + 32);
-        tmem_ld32_raw(s_t + 64, ph + 64);
-        tmem_ld_wait();
-        float dsum_t = 0.f, dsum_i = 0.f;
-  #pragma unroll
-        for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
-          uint32_t dp[32];
-          tmem_ld32_raw(dp_t + c0, dp);
-  #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int key = c0 + i;
-            const bool is_t = key < Lt;
-            const float e = fast_exp2(fmaf(__uint_as_float(ph[key]), p.scale_log2e, is_t ? -st.x : -st.z)) * (is_t ? ilt : ili);
-            ph[key] = __float_as_uint(key < L ? e : 0.f);
-          }
-          tmem_ld_wait();
-  #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int key = c0 + i;
-            const float pd = __uint_as_float(ph[key]) * __uint_as_float(dp[i]);
-            if (key < Lt) dsum_t += pd; else dsum_i += pd;
-          }
-        }
-        // the previous tile's dK / dV contractions have read the P / dS images
-        if (t > 0) mbar_wait(mma2_done, (t - 1) & 1);
-        // pass 2: w p^ and scale w p^ (dp - delta), packed to bf16, 8 keys (16 bytes) at a time
-        const float swt = p.scale * p.w_text, swi = p.scale * p.w_img;
-  #pragma unroll
-        for (int c0 = 0; c0 < BT_KEYS; c0 += 32) {
-          uint32_t dp[32];
-          tmem_ld32_raw(dp_t + c0, dp);
-          tmem_ld_wait();
-  #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t pw[4], dw[4];
-  #pragma unroll
-            for (int q2 = 0; q2 < 4; ++q2) {
-              float pv2[2], dv2[2];
-  #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int i = 8 * c + 2 * q2 + e, key = c0 + i;
-                const bool is_t = key < Lt;
-                const float pe = __uint_as_float(ph[key]);
-                pv2[e] = (is_t ? p.w_text : p.w_img) * pe;
-                dv2[e] = (is_t ? swt : swi) * pe * (__uint_as_float(dp[i]) - (is_t ? dsum_t : dsum_i));
-              }
-              pw[q2] = pack_bf16x2(pv2[0], pv2[1]);
-              dw[q2] = pack_bf16x2(dv2[0], dv2[1]);
-            }
-            const int kc = c0 / 8 + c;
-            st_shared_v4_a(p_row + kc * 2048, pw[0], pw[1], pw[2], pw[3]);
-            st_shared_v4_a(ds_row + kc * 2048, dw[0], dw[1], dw[2], dw[3]);
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ds_ready);
-    }
-  } else if (warp >= 8) {
-    // ---------------------------------------------------------------- dQ drain; at the end dK / dV
-    const int wq = warp & 3, row = wq * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    for (int t = 0; t < nt; ++t) {
+    // this group's share of the dQ accumulator of tile t -> global memory
+    auto drain_dq = [&](int t) {
       mbar_wait(mma2_done, t & 1);
       tc_fence_after();
       const int grow = (t_begin + t) * 128 + row;
       __nv_bfloat16* dst = p.dQ + (static_cast<size_t>(b) * S + grow) * p.C + h * D;
+      constexpr int CSPLIT = D == 40 ? 24 : D / 2;
+      const int cb = wg == 0 ? 0 : CSPLIT, ce = wg == 0 ? CSPLIT : D;
 #pragma unroll
       for (int c = 0; c < D; c += 8) {
+        if (c < cb || c >= ce) continue;                 // (group-uniform)
         uint32_t o[8];
         tmem_ld_x8(tmem + lane_base + Cfg::TM_DQ + c, o);
         tmem_ld_wait();
@@ -412,22 +258,146 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
-    }
-    // dK / dV: TMEM lane = key.  (tcgen05.ld is warp-collective: every lane loads, only the lanes of real keys store.)
-    const int key = row;
-    float* dstK = p.part + ((static_cast<size_t>(chunk) * p.B + b) * p.H + h) * 2 * L * D + static_cast<size_t>(key) * D;
-    float* dstV = dstK + static_cast<size_t>(L) * D;
+    };
+    auto run = [&](auto k0c) {
+      constexpr int K0 = decltype(k0c)::value;            // first key slot of this group; 48 slots
+      float4 st_next = load_stats(0);
+      for (int t = 0; t < nt; ++t) {
+        const int grow = (t_begin + t) * 128 + row;
+        const float4 st = st_next;
+        st_next = load_stats(t + 1);                      // one tile ahead: the load's latency hides under this tile's work
+        const float ilt = grow < S ? 1.f / st.y : 0.f, ili = grow < S ? 1.f / st.w : 0.f;     // rows past S: p^ = 0
+        mbar_wait(s_full, t & 1);
+        tc_fence_after();
+        // ---- pass 1: p^ of my 48 key slots (kept in registers) and my part of the two segment sums of p^ dp
+        float e[48];
+        uint32_t dp[48];
+        {
+          uint32_t* eu = reinterpret_cast<uint32_t*>(e);
+          tmem_ld32_raw(s_t + K0, eu);
+          tmem_ld16_raw(s_t + K0 + 32, eu + 32);
+          tmem_ld32_raw(dp_t + K0, dp);
+          tmem_ld16_raw(dp_t + K0 + 32, dp + 32);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_free);
+        }
+        float dsum_t = 0.f, dsum_i = 0.f;
+        if constexpr (LT77) {
+          // 77 text keys: the segment of every slot is a compile-time fact; packed fp32x2 arithmetic.  Pairs (k, k+1):
+          // k + 1 < 77 text, k >= 78 image (masked by k < L); the pair (76, 77) straddles the boundary (scalar form).
+          const uint64_t sc2 = f2_pack(p.scale_log2e, p.scale_log2e);
+          const uint64_t nmt2 = f2_pack(-st.x, -st.x), nmi2 = f2_pack(-st.z, -st.z);
+          const uint64_t ilt2 = f2_pack(ilt, ilt), ili2 = f2_pack(ili, ili);
+          uint64_t dt2 = f2_pack(0.f, 0.f), di2 = dt2;
 #pragma unroll
-    for (int c = 0; c < D; c += 8) {
-      uint32_t kk[8], vv[8];
-      tmem_ld_x8(tmem + lane_base + Cfg::TM_DK + c, kk);
-      tmem_ld_x8(tmem + lane_base + Cfg::TM_DV + c, vv);
-      tmem_ld_wait();
-      if (key < L) {
-        *reinterpret_cast<uint4*>(dstK + c) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
-        *reinterpret_cast<uint4*>(dstK + c + 4) = make_uint4(kk[4], kk[5], kk[6], kk[7]);
-        *reinterpret_cast<uint4*>(dstV + c) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-        *reinterpret_cast<uint4*>(dstV + c + 4) = make_uint4(vv[4], vv[5], vv[6], vv[7]);
+          for (int i = 0; i < 48; i += 2) {
+            const int key = K0 + i;
+            const uint64_t pd = f2_pack(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1]));
+            if (key + 1 < 77) {
+              float a, b2;
+              f2_unpack(f2_fma(f2_pack(e[i], e[i + 1]), sc2, nmt2), a, b2);
+              const uint64_t v2 = f2_mul(f2_pack(fast_exp2(a), fast_exp2(b2)), ilt2);
+              f2_unpack(v2, e[i], e[i + 1]);
+              dt2 = f2_fma(v2, pd, dt2);
+            } else if (key >= 78) {
+              float a, b2;
+              f2_unpack(f2_fma(f2_pack(e[i], e[i + 1]), sc2, nmi2), a, b2);
+              f2_unpack(f2_mul(f2_pack(fast_exp2(a), fast_exp2(b2)), ili2), a, b2);
+              e[i] = key < L ? a : 0.f;
+              e[i + 1] = key + 1 < L ? b2 : 0.f;
+              di2 = f2_fma(f2_pack(e[i], e[i + 1]), pd, di2);
+            } else {                                                      // keys 76 (text) and 77 (image, always present)
+              e[i] = fast_exp2(fmaf(e[i], p.scale_log2e, -st.x)) * ilt;
+              e[i + 1] = fast_exp2(fmaf(e[i + 1], p.scale_log2e, -st.z)) * ili;
+              dsum_t = e[i] * __uint_as_float(dp[i]);
+              dsum_i = e[i + 1] * __uint_as_float(dp[i + 1]);
+            }
+          }
+          float s0, s1;
+          f2_unpack(dt2, s0, s1);
+          dsum_t += s0 + s1;
+          f2_unpack(di2, s0, s1);
+          dsum_i += s0 + s1;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 48; ++i) {
+            const int key = K0 + i;
+            const bool is_t = key < Lt;
+            const float v = fast_exp2(fmaf(e[i], p.scale_log2e, is_t ? -st.x : -st.z)) * (is_t ? ilt : ili);
+            e[i] = key < L ? v : 0.f;
+            const float pd = e[i] * __uint_as_float(dp[i]);
+            if (is_t) dsum_t += pd; else dsum_i += pd;
+          }
+        }
+        // ---- the other group's part of the sums
+        {
+          float* mine = xch + (((t & 1) * 2 + wg) * 128 + row) * 2;
+          const float* theirs = xch + (((t & 1) * 2 + (wg ^ 1)) * 128 + row) * 2;
+          mine[0] = dsum_t;
+          mine[1] = dsum_i;
+          named_bar_sync(1, 256);
+          dsum_t += theirs[0];
+          dsum_i += theirs[1];
+        }
+        // ---- the previous tile: its gradient contractions have completed (the P / dS images are free again) -> my share of dQ
+        if (t > 0) drain_dq(t - 1);
+        // ---- pass 2: w p^ and scale w p^ (dp - delta) as bf16, 8 keys (16 bytes) at a time
+        const float swt = p.scale * p.w_text, swi = p.scale * p.w_img;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          uint32_t pw[4], dw[4];
+#pragma unroll
+          for (int q2 = 0; q2 < 4; ++q2) {
+            const int i = 8 * c + 2 * q2, key = K0 + i;
+            float a, b2, c1, d1;
+            if (LT77 && (key + 1 < 77 || key >= 78)) {
+              const bool txt = key + 1 < 77;
+              const uint64_t e2 = f2_pack(e[i], e[i + 1]);
+              const uint64_t pd = f2_pack(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1]));
+              const float w = txt ? p.w_text : p.w_img, sw = txt ? swt : swi, nd = txt ? -dsum_t : -dsum_i;
+              f2_unpack(f2_mul(e2, f2_pack(w, w)), a, b2);
+              f2_unpack(f2_mul(f2_mul(e2, f2_pack(sw, sw)), f2_add(pd, f2_pack(nd, nd))), c1, d1);
+            } else {
+              const bool t0 = LT77 ? true : key < Lt, t1 = LT77 ? false : key + 1 < Lt;
+              a = (t0 ? p.w_text : p.w_img) * e[i];
+              b2 = (t1 ? p.w_text : p.w_img) * e[i + 1];
+              c1 = (t0 ? swt : swi) * e[i] * (__uint_as_float(dp[i]) - (t0 ? dsum_t : dsum_i));
+              d1 = (t1 ? swt : swi) * e[i + 1] * (__uint_as_float(dp[i + 1]) - (t1 ? dsum_t : dsum_i));
+            }
+            pw[q2] = pack_bf16x2(a, b2);
+            dw[q2] = pack_bf16x2(c1, d1);
+          }
+          const int kc = K0 / 8 + c;
+          st_shared_v4_a(p_row + kc * 2048, pw[0], pw[1], pw[2], pw[3]);
+          st_shared_v4_a(ds_row + kc * 2048, dw[0], dw[1], dw[2], dw[3]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_ready);
+      }
+      drain_dq(nt - 1);
+    };
+    if (wg == 0) run(std::integral_constant<int, 0>{});
+    else run(std::integral_constant<int, 48>{});
+    // ---- dK (group 0) / dV (group 1): TMEM lane = key.  (tcgen05.ld is warp-collective: every lane loads, only the lanes
+    // of real keys store.)
+    {
+      const int key = row;
+      float* dst = p.part + ((static_cast<size_t>(chunk) * p.B + b) * p.H + h) * 2 * L * D + static_cast<size_t>(wg) * L * D +
+                   static_cast<size_t>(key) * D;
+      const uint32_t src = tmem + lane_base + (wg == 0 ? Cfg::TM_DK : Cfg::TM_DV);
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint32_t kk[8];
+        tmem_ld_x8(src + c, kk);
+        tmem_ld_wait();
+        if (key < L) {
+          *reinterpret_cast<uint4*>(dst + c) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+          *reinterpret_cast<uint4*>(dst + c + 4) = make_uint4(kk[4], kk[5], kk[6], kk[7]);
+        }
       }
     }
   }

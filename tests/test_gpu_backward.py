@@ -309,6 +309,43 @@ def test_tensor_core_backward_agrees_with_simt_backward(cuda_device):
         assert e <= 2e-2, f"{k}: tensor-core vs SIMT backward relative difference {e:.3e}"
 
 
+@pytest.mark.parametrize("case", [
+    cases.ProcCase("tc_c320_ragged", B=2, S=700, C=320, Li=5, lora_r=8, seed=81),          # 77 text keys: compile-time segments
+    cases.ProcCase("tc_c640_lt60", B=2, S=384, C=640, Li=3, Lt=60, lora_r=4, seed=82),       # other text lengths: generic path
+    cases.ProcCase("tc_c320_li16", B=1, S=2304, C=320, Li=16, seed=83),                      # 9 tiles -> two CTAs per (b, h)
+], ids=lambda c: c.name)
+def test_tcgen05_backward_agrees_with_the_other_backward_kernels(cuda_device, case):
+    """bf16 training path: the tcgen05 attention backward (pv_bwd_tc.cu, default for head_dim 40 / 80), the mma.sync
+    kernel (pv_set_option('bwd_tc', 0)) and the fp32-accumulating SIMT kernel ('bwd_mma', 0) -- three independent
+    implementations of the derivative of reference :317-420 -- on identical inputs."""
+    from photoverse_b200 import _lib
+    grads = {}
+    for name, opts in (("tc", {"bwd_tc": 1, "bwd_mma": 1}), ("mma", {"bwd_tc": 0, "bwd_mma": 1}), ("simt", {"bwd_tc": 0, "bwd_mma": 0})):
+        for k, v in opts.items():
+            _lib.set_option(k, v)
+        try:
+            attn, proc = build_product_layer(case, cuda_device)
+            for n, p in attn.named_parameters():
+                p.requires_grad_("lora_" in n or "to_k_ip" in n or "to_v_ip" in n)
+            x, text, img = (t.to(cuda_device, torch.bfloat16) for t in cases.proc_inputs(case, torch.float32))
+            x.requires_grad_(True)
+            text.requires_grad_(True)
+            img.requires_grad_(True)
+            force_fusion_seed(1.0, 1.0)
+            with torch.enable_grad():
+                y = attn(x, encoder_hidden_states=(text, img))
+                (y.float().square().sum() + proc.to_v_ip_norm.float().sum()).backward()
+            grads[name] = {"x": x.grad.clone(), "text": text.grad.clone(), "img": img.grad.clone(),
+                           "kip": proc.to_k_ip[0].weight.grad.clone(), "vip": proc.to_v_ip[0].weight.grad.clone()}
+        finally:
+            _lib.set_option("bwd_tc", 1)
+            _lib.set_option("bwd_mma", 1)
+    for other in ("mma", "simt"):
+        for k in grads["tc"]:
+            e = _rel(grads["tc"][k], grads[other][k])
+            assert e <= 2e-2, f"{k}: tcgen05 vs {other} backward relative difference {e:.3e}"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("M,in_f,out_f,r", [(4096 + 7, 320, 320, 8), (1232, 768, 640, 8), (300, 1280, 1280, 4), (2048, 768, 1280, 16),
                                             (65536, 320, 320, 8), (64, 640, 640, 1)])
