@@ -97,6 +97,8 @@ unsigned long long* g_attn3_trace = nullptr;   // debug timeline buffer (pv_debu
 int g_attn3_trace_cap = 0;
 int g_opt_bwd_tc = 1;            // tcgen05 attention backward for head_dim 40 / 80 (0: the mma.sync kernel)
 int g_opt_sattn_poly = 2;        // pv_sattn.cu: exponentials per 8 pairs computed on the FMA pipe instead of MUFU (0 | 2 | 4)
+int g_opt_attn6_prefetch = 1;    // pv_attn6.cu: softmax warps fetch the next head's S row under the current head's P pack
+int g_opt_attn6_token = 1;       // pv_attn6.cu, head_dim 40: the two softmax groups take turns on the exponentials (MUFU token)
 int g_opt_trace_block = 0;       // which leader CTA writes the debug timeline
 static thread_local std::string t_error;
 
@@ -252,6 +254,8 @@ int pv_set_option(const char* name, int value) {
   if (!strcmp(name, "bwd_mma")) { g_opt_bwd_mma = value; return PV_OK; }
   if (!strcmp(name, "bwd_tc")) { g_opt_bwd_tc = value; return PV_OK; }
   if (!strcmp(name, "sattn_poly")) { g_opt_sattn_poly = value; return PV_OK; }
+  if (!strcmp(name, "attn6_prefetch")) { g_opt_attn6_prefetch = value; return PV_OK; }
+  if (!strcmp(name, "attn6_token")) { g_opt_attn6_token = value; return PV_OK; }
   if (!strcmp(name, "trace_block")) { g_opt_trace_block = value; return PV_OK; }
   PV_FAIL(PV_ERR_INVALID, "unknown option '%s'", name);
 }

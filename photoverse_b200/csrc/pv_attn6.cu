@@ -17,6 +17,8 @@
 //     slot_free.  The eight softmax warps do nothing but softmax.
 // Shared-memory operands, TMEM maps, the pair protocol (cta_group::2, leader-side barriers, multicast commits) and the
 // softmax arithmetic are those of pv_attn4.cu.
+#include <type_traits>
+
 #include "pv_common.cuh"
 #include "pv_softmax.cuh"
 #include "pv_outproj.cuh"
@@ -86,6 +88,8 @@ struct Attn6Params {
   // fused out projection (FUSE kernels only)
   const float* bias;       // [C] or nullptr
   unsigned int* sync;      // [2 * V] row-block counters, zero between launches (pv_outproj.cuh)
+  int prefetch_s;          // softmax warps fetch the next head's S row under the current head's P pack
+  int mufu_token;          // d = 40: the two softmax groups take turns on the exponentials
 };
 
 template <int D, bool LT77, bool FUSE>
@@ -114,8 +118,10 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
   uint64_t* kv_both = kv_full + 1;              // 1  (leader) count 2
   uint64_t* kv_free = kv_both + 1;              // 1  multicast commit after the last PV of a sample
   uint64_t* q_full = kv_free + 1;               // [2] multicast commit: Q accumulators of a slot complete
-  uint64_t* q_ready = q_full + 2;               // [2] (leader) packed bf16 Q in both CTAs' TMEM     count 8 (epilogue warps)
-  uint64_t* slot_free = q_ready + 2;            // [2] (leader) every O of the unit has left TMEM      count 8 (epilogue warps)
+  uint64_t* q_ready = q_full + 2;               // [2][4] (leader) packed bf16 Q of head j of the slot in both CTAs' TMEM: count 8
+                                                //        (epilogue warps).  Per HEAD: the first QK^T of a unit does not wait for
+                                                //        the conversion of the other heads (~450 cycles each, serial per warp)
+  uint64_t* slot_free = q_ready + 8;            // [2] (leader) every O of the unit has left TMEM      count 8 (epilogue warps)
   uint64_t* s_full = slot_free + 2;             // [2] multicast commit, per softmax group
   uint64_t* s_free = s_full + 2;                // [2] (leader) S buffer in registers in both CTAs     count 8 (softmax warps)
   uint64_t* p_ready = s_free + 2;               // [2] (leader) P tile + row scales in shared memory   count 8 (softmax warps)
@@ -161,7 +167,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     mbar_init(kv_free, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_ready[i], 8);
+      for (int j = 0; j < 4; ++j) mbar_init(&q_ready[4 * i + j], 8);
       mbar_init(&slot_free[i], 8);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 8);
@@ -316,7 +322,6 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         int kv_end = 0;
 #pragma unroll 1
         for (int i = 0; i < nunits; ++i) {
-          mbar_wait(&q_ready[i & 1], (i >> 1) & 1);
           if (i >= kv_end) {
             mbar_wait(kv_both, kv_gen & 1);
             ++kv_gen;
@@ -326,6 +331,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
 #pragma unroll 1
           for (int j = 0; j < A6_HPC; ++j) {
             const int nn = i * A6_HPC + j;
+            mbar_wait(&q_ready[4 * (i & 1) + j], (i >> 1) & 1);
             if (nn >= 2) mbar_wait(&s_free[j & 1], ((nn - 2) >> 1) & 1);
             tc_fence_after();
             if (elect_one()) {
@@ -350,8 +356,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
       constexpr uint32_t idesc_o = umma_idesc_bf16(2 * A6_BM, A6_DPAD);
       const uint64_t vdesc0 = umma_desc(smem_u32(kv + A6_KH_BYTES), (A6_DPAD / 2) * 16, 128, UMMA_LAYOUT_NONE);
       const uint64_t pdesc0 = umma_desc(smem_u32(smem + A6_OFF_P), A6_BM * 16, 128, UMMA_LAYOUT_NONE);
-      A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 1, p.trace_block);
-      tr.base = nullptr;
+      A3Trace tr = a3_trace_init_raw(p.trace, p.trace_cap, 6, p.trace_block);   // (role 6 belongs to phase 2 in the fused kernels)
+      if (FUSE || rank != 0) tr.base = nullptr;
       uint32_t kv_gen = 0;
       int kv_end = 0;
 #pragma unroll 1
@@ -365,6 +371,10 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         }
         if (rank != 0) continue;
         const uint32_t tslot = tmem + (i & 1) * A6_BN;
+        // d = 40: the O accumulators [48 w, +48) reach into the fp32 Q columns of the NEXT head (head 1: [40, 80), head 2:
+        // [80, 120)), which the epilogue warps must have converted; they convert in head order, so the last head's
+        // barrier covers all (long complete by the time a softmax has finished).
+        mbar_wait(&q_ready[4 * (i & 1) + A6_HPC - 1], (i >> 1) & 1);
 #pragma unroll 1
         for (int j = 0; j < A6_HPC; ++j) {
           const int nn = i * A6_HPC + j;
@@ -383,8 +393,10 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
             if (j == A6_HPC - 1 && i + 1 < nunits && i + 1 == kv_end) umma_commit_2sm(kv_free);
           }
           __syncwarp();
+          a3_trace(tr, 21, nn);
         }
       }
+      a3_trace_done_raw(p.trace, tr, 6);
     }
     // the second phase runs every warp on the launch allocation again (blocks until the softmax warps have released theirs)
     if constexpr (FUSE) { __syncwarp(); asm volatile("setmaxnreg.inc.sync.aligned.u32 128;"); }
@@ -410,6 +422,28 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     int kv_end = 0;                                  // only to track the sample index of a unit without dividing per head
     int b = u0 / p.MTP - 1;
 
+    // The S row of the group's NEXT head is fetched from tensor memory while the current head's P is packed (the
+    // registers of a packed key chunk are dead): the TMEM round trip (~400 cycles) leaves the per-head chain
+    // load -> max -> exponentials -> pack, which is what bounds the kernel at head_dim 40.
+    uint32_t sr[A6_KEYS];                            // S row (fp32 bits), later the exponentials
+    const int gheads = nunits * (A6_HPC / 2);        // heads this group serves: nn = wg + 2 k, barrier parity k & 1
+    const bool prefetch_s = p.prefetch_s != 0;
+    const bool mufu_token = p.mufu_token != 0;
+    auto release_s = [&]() {                         // the row is in registers: QK^T(nn + 2) may overwrite the S buffer
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) mbar_arrive_cluster(s_free_l);
+    };
+    if (gheads > 0) {
+      mbar_wait_a(s_full_a, 0);
+      tc_fence_after();
+      tmem_ld32_raw(sbuf, sr);
+      tmem_ld32_raw(sbuf + 32, sr + 32);
+      tmem_ld32_raw(sbuf + 64, sr + 64);
+      release_s();
+    }
+
 #pragma unroll 1
     for (int i = 0; i < nunits; ++i) {
       if (i >= kv_end) {
@@ -424,17 +458,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         const int j = wg + 2 * jj;                   // this group's heads of the unit
         const int nn = i * A6_HPC + j;
         const uint32_t par = (nn >> 1) & 1;
-        mbar_wait_a(s_full_a, par);
-        tc_fence_after();
+        const bool has_next = (nn >> 1) + 1 < gheads;
         a3_trace(tr, 33 + 10 * wg, nn);
-        uint32_t sr[A6_KEYS];                        // S row (fp32 bits), later the exponentials
-        tmem_ld32_raw(sbuf, sr);
-        tmem_ld32_raw(sbuf + 32, sr + 32);
-        tmem_ld32_raw(sbuf + 64, sr + 64);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (elect_one()) mbar_arrive_cluster(s_free_l);   // QK^T(nn + 2) may overwrite the S buffer from here on
         float fi = 1.f, oscale = 1.f;
         {
           auto tvalid = [&](int c) -> bool { if constexpr (LT77) return c < 77; else return c < Lt; };
@@ -463,10 +488,12 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
           // share one scheduler: a token (two producer/consumer named barriers) makes them take turns, so that one
           // warp's exponentials overlap the other's TMEM loads, max pass, packing and stores instead of its exponentials.
           // (d = 80 has one head per group and unit: there the unit's latency matters, not the MUFU throughput.)
-          if constexpr (D == 40) {
+          a3_trace(tr, 38 + 10 * wg, nn);
+          if (D == 40 && mufu_token) {
             if (wg == 0) { if (nn >= 2) named_bar_sync(5 + q, 64); }
             else         { named_bar_sync(1 + q, 64); }
           }
+          a3_trace(tr, 32 + 10 * wg, nn);
 #pragma unroll
           for (int k = 0; k < A6_IMG_OFF / 2; ++k) {
             const int c = 2 * k;
@@ -481,7 +508,6 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
               a = tvalid(c) ? a : 0.f;
               b2 = tvalid(c + 1) ? b2 : 0.f;
             }
-            lacc[k & 1] = f2_add(lacc[k & 1], f2_pack(a, b2));
             sr[c] = __float_as_uint(a);
             sr[c + 1] = __float_as_uint(b2);
           }
@@ -493,7 +519,6 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
               f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmi2), a, b2);
               a = (2 * k < Li) ? fast_exp2(a) : 0.f;
               b2 = (2 * k + 1 < Li) ? fast_exp2(b2) : 0.f;
-              iacc = f2_add(iacc, f2_pack(a, b2));
               sr[c] = __float_as_uint(a);
               sr[c + 1] = __float_as_uint(b2);
             }
@@ -503,7 +528,6 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
             f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmi2), a, b2);
             a = fast_exp2(a);
             b2 = (Li > 1) ? fast_exp2(b2) : 0.f;
-            iacc = f2_pack(a, b2);
             sr[c] = __float_as_uint(a);
             sr[c + 1] = __float_as_uint(b2);
 #pragma unroll
@@ -516,16 +540,30 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
               f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), cs2, nmi2), a, b2);
               a = (2 * k < Li) ? fast_exp2(a) : 0.f;
               b2 = (2 * k + 1 < Li) ? fast_exp2(b2) : 0.f;
-              iacc = f2_add(iacc, f2_pack(a, b2));
               sr[c] = __float_as_uint(a);
               sr[c + 1] = __float_as_uint(b2);
             }
 #pragma unroll
             for (int c = A6_IMG_OFF + 8; c < A6_KEYS; ++c) sr[c] = 0u;
           }
-          if constexpr (D == 40) {
+          if (D == 40 && mufu_token) {
             if (wg == 0) { named_bar_arrive(1 + q, 64); }
             else         { if (nn + 2 < nheads) named_bar_arrive(5 + q, 64); }
+          }
+          // Row sums AFTER the token has been handed on: inside the exponent loop every add waited for its two MUFU
+          // results (in-order issue: ~15 cycles of XU bubble per pair, the phase took ~1150 cycles for 640 of MUFU work);
+          // here they are FMA-pipe work that overlaps the other group's exponentials.  Masked slots hold zeros.
+#pragma unroll
+          for (int k = 0; k < A6_IMG_OFF / 2; ++k) {
+            if (LT77 && 2 * k >= 77) continue;
+            lacc[k & 1] = f2_add_v(lacc[k & 1], f2_pack(__uint_as_float(sr[2 * k]), __uint_as_float(sr[2 * k + 1])));
+          }
+          if (Li <= 2) {
+            iacc = f2_pack(__uint_as_float(sr[A6_IMG_OFF]), __uint_as_float(sr[A6_IMG_OFF + 1]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < (A6_KEYS - A6_IMG_OFF) / 2; ++k)
+              iacc = f2_add_v(iacc, f2_pack(__uint_as_float(sr[A6_IMG_OFF + 2 * k]), __uint_as_float(sr[A6_IMG_OFF + 2 * k + 1])));
           }
           float l0, l1, l2, l3, li0, li1;
           f2_unpack(lacc[0], l0, l1);
@@ -549,37 +587,65 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         // completed, and the epilogue has read the scales of head nn - 4 long before (it drained O(nn - 2) since).
         if (nn >= 2) mbar_wait_a(o_full_a, par ^ 1);
         st_shared_f32_a(osc_a + par * (A6_BM * 4), oscale);
-        if (text_on) {
+        // key chunks [c0, c1) of this row (8 keys = 16 bytes each): text chunks unscaled, image chunks * fi
+        const uint64_t fi2 = f2_pack(fi, fi);
+        auto pack_chunks = [&](auto text_, auto c0_, auto c1_) {
+          constexpr bool text = decltype(text_)::value;
+          constexpr int c0 = decltype(c0_)::value, c1 = decltype(c1_)::value;
 #pragma unroll
-          for (int c = 0; c < A6_IMG_OFF / 8; ++c) {   // key chunk c: 8 keys = 16 bytes of this row
+          for (int c = c0; c < c1; ++c) {
             uint32_t pk[4];
+            if (c < A6_IMG_OFF / 8) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              pk[k] = pack_bf16x2(__uint_as_float(sr[8 * c + 2 * k]), __uint_as_float(sr[8 * c + 2 * k + 1]));
-            st_shared_v4_a(ptile_a + c * (A6_BM * 16), pk[0], pk[1], pk[2], pk[3]);
-          }
-        } else {
+              for (int k = 0; k < 4; ++k)
+                pk[k] = text ? pack_bf16x2(__uint_as_float(sr[8 * c + 2 * k]), __uint_as_float(sr[8 * c + 2 * k + 1])) : 0u;
+            } else {
 #pragma unroll
-          for (int c = 0; c < A6_IMG_OFF / 8; ++c) st_shared_v4_a(ptile_a + c * (A6_BM * 16), 0u, 0u, 0u, 0u);
-        }
-        {
-          const uint64_t fi2 = f2_pack(fi, fi);
-#pragma unroll
-          for (int c = A6_IMG_OFF / 8; c < A6_KEYS / 8; ++c) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float a, b2;
-              f2_unpack(f2_mul(f2_pack(__uint_as_float(sr[8 * c + 2 * k]), __uint_as_float(sr[8 * c + 2 * k + 1])), fi2), a, b2);
-              pk[k] = pack_bf16x2(a, b2);
+              for (int k = 0; k < 4; ++k) {
+                float a, b2;
+                f2_unpack(f2_mul(f2_pack(__uint_as_float(sr[8 * c + 2 * k]), __uint_as_float(sr[8 * c + 2 * k + 1])), fi2), a, b2);
+                pk[k] = pack_bf16x2(a, b2);
+              }
             }
             st_shared_v4_a(ptile_a + c * (A6_BM * 16), pk[0], pk[1], pk[2], pk[3]);
           }
+        };
+        using std::integral_constant;
+        using std::true_type;
+        using std::false_type;
+        // S(nn + 2) was issued when this head's row reached the registers, ~2000 cycles ago: normally it is there.  If it
+        // is not (pipeline fill, a late projection), P is not held back for it.  (The image-only fusion branch, a
+        // training-time event, takes the plain path.)
+        const bool pre = prefetch_s && has_next && text_on && __all_sync(0xffffffffu, mbar_test_wait_a(s_full_a, par ^ 1));
+        a3_trace(tr, 37 + 10 * wg, pre ? 1 : 0);
+        if (pre) {
+          tc_fence_after();
+          pack_chunks(true_type{}, integral_constant<int, 0>{}, integral_constant<int, 4>{});
+          tmem_ld32_raw(sbuf, sr);                   // keys 0..31 are packed: their registers take the next row
+          pack_chunks(true_type{}, integral_constant<int, 4>{}, integral_constant<int, 8>{});
+          tmem_ld32_raw(sbuf + 32, sr + 32);
+          pack_chunks(true_type{}, integral_constant<int, 8>{}, integral_constant<int, A6_KEYS / 8>{});
+          tmem_ld32_raw(sbuf + 64, sr + 64);
+        } else if (text_on) {
+          pack_chunks(true_type{}, integral_constant<int, 0>{}, integral_constant<int, A6_KEYS / 8>{});
+        } else {
+          pack_chunks(false_type{}, integral_constant<int, 0>{}, integral_constant<int, A6_KEYS / 8>{});
         }
         fence_proxy_async_smem();                    // generic-proxy stores -> visible to the tensor core's operand reads
         __syncwarp();
         if (elect_one()) mbar_arrive_cluster(p_ready_l);
         a3_trace(tr, 34 + 10 * wg, nn);
+        if (has_next) {
+          if (!pre) {
+            mbar_wait_a(s_full_a, par ^ 1);
+            tc_fence_after();
+            tmem_ld32_raw(sbuf, sr);
+            tmem_ld32_raw(sbuf + 32, sr + 32);
+            tmem_ld32_raw(sbuf + 64, sr + 64);
+          }
+          release_s();
+          a3_trace(tr, 35 + 10 * wg, nn + 2);
+        }
       }
     }
     a3_trace_done_raw(p.trace, tr, 2 + wg);
@@ -593,6 +659,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     const uint32_t osc_a = smem_u32(smem + A6_OFF_OSC) + (q * 32 + lane) * 4;
     int converted = 0, drained = 0;
     const uint64_t pol_o = l2_policy_evict_last();     // O is read back by the out projection: keep it in L2
+    A3Trace etr = a3_trace_init_raw(p.trace, p.trace_cap, 7, p.trace_block);   // (role 7: phase 2 in the fused kernels)
+    if (FUSE || q != 0) etr.base = nullptr;
     int kv_end_d = 0;                                // sample tracking for the drain stream
     int b_d = u0 / p.MTP - 1;
     int m0_d = 0;
@@ -603,6 +671,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     auto convert_unit = [&](int iu) {
       const uint32_t tslot = tlane + (iu & 1) * A6_BN;
       tc_fence_after();
+      a3_trace(etr, 30, iu);
 #pragma unroll
       for (int j = 0; j < A6_HPC; ++j) {
         if constexpr (D == 40) {
@@ -628,10 +697,11 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
             tmem_st_x4(tslot + 80 * j + 40 + 20 * hh + 16, o + 16);
           }
         }
+        tmem_st_wait();
+        tc_fence_before();
+        arrive_leader(&q_ready[4 * (iu & 1) + j]);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      arrive_leader(&q_ready[iu & 1]);
+      a3_trace(etr, 31, iu);
     };
     // O(nn): TMEM -> registers (accumulator released at once) -> * row scale -> bf16 -> staging slab -> TMA store
     auto drain_head = [&](int nn) {
@@ -646,6 +716,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         m0_d = (2 * (u0 + i - b_d * p.MTP) + static_cast<int>(rank)) * A6_BM;
       }
       tc_fence_after();
+      a3_trace(etr, 80, nn);
       const uint32_t taddr = tlane + (i & 1) * A6_BN + Cfg::o_col(w);
       const float oscale = ld_shared_f32_a(osc_a + (w * 2 + par) * (A6_BM * 4));   // read before the release below: the slot is rewritten two heads on
       uint8_t* slab = ost + w * A6_OST_BYTES;
@@ -687,6 +758,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
         bulk_commit();
       }
       __syncwarp();
+      a3_trace(etr, 81, nn);
     };
 
     while (drained < nheads) {
@@ -710,6 +782,7 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
     }
     if (elect_one()) bulk_wait_read<0>();             // the staging slabs are free (the stores may still be in flight)
     __syncwarp();
+    a3_trace_done_raw(p.trace, etr, 7);
     if constexpr (FUSE) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
   }
 
@@ -762,6 +835,8 @@ dual_attn_fwd_pair_roles_kernel(const __grid_constant__ CUtensorMap tmX, const _
 extern unsigned long long* g_attn3_trace;
 extern int g_attn3_trace_cap;
 extern int g_opt_trace_block;
+extern int g_opt_attn6_prefetch;
+extern int g_opt_attn6_token;
 
 template <int D, bool LT77, bool FUSE>
 static int launch_attn6(const CUtensorMap& tmX, const CUtensorMap& tmWq, const CUtensorMap& tmO, const CUtensorMap& tmOa,
@@ -835,6 +910,8 @@ int dual_attn_core_bf16_pair_roles(const void* X, const void* Wq, const void* Kp
   p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(d));
   p.bias = bo;
   p.sync = sync;
+  p.prefetch_s = g_opt_attn6_prefetch;
+  p.mufu_token = g_opt_attn6_token;
 #define PV_A6_LAUNCH(DD, LT, FU) launch_attn6<DD, LT, FU>(tmX, tmWq, tmO, tmOa, tmWo, tmY, p, unit_pairs, stream)
   if (d == 40) {
     if (fuse) return Lt == 77 ? PV_A6_LAUNCH(40, true, true) : PV_A6_LAUNCH(40, false, true);

@@ -121,6 +121,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Non-blocking probe on a precomputed 32-bit shared address.
+__device__ __forceinline__ bool mbar_test_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 // The same wait on a precomputed 32-bit shared address: hot loops keep their barrier addresses in registers instead of
 // re-deriving them (generic -> shared conversion of a pointer costs ~8 uniform-datapath instructions per use).
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {

@@ -40,6 +40,12 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// the same add as a volatile statement: keeps its place relative to barriers / other volatile statements
+__device__ __forceinline__ uint64_t f2_add_v(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));

@@ -61,9 +61,9 @@ ev.sort()
 n = len(ev)
 t0 = ev[0][0]
 names = {1: "prologue cycles (entry -> cluster sync) =", 2: "entry -> after griddepcontrol.wait =", 12: " qp full", 13: " qp mma issued", 14: " qp committed", 22: "  qk begin", 23: "  qk mmas issued", 25: "  pv wait p_ready", 26: "  pv p_ready ok", 27: "  pv mmas issued", 10: "QP start", 11: "QP issued", 20: "  QK issued", 21: "  PV issued", 29: "    A wait q_full", 30: "    A q_full", 31: "    A conv done",
-         32: "    A slot_free", 33: "    A s_full", 34: "    A p_ready", 35: "    A S loaded", 36: "    A exps done", 37: "    A exchanged", 38: "    A drained",
-         45: "        B S loaded", 46: "        B exps done", 47: "        B exchanged", 48: "        B drained", 39: "        B wait q_full", 40: "        B q_full", 41: "        B conv done",
-         42: "        B slot_free", 43: "        B s_full", 44: "        B p_ready",
+         32: "    A slot_free", 33: "    A head begin", 34: "    A p_ready", 35: "    A next S in registers", 36: "    A exps done", 37: "    A pack begin, prefetch =", 38: "    A drained",
+         45: "        B next S in registers", 46: "        B exps done", 47: "        B pack begin, prefetch =", 48: "        B drained", 39: "        B wait q_full", 40: "        B q_full", 41: "        B conv done",
+         42: "        B slot_free", 43: "        B head begin", 44: "        B p_ready",
          50: "P2 producer start", 51: "P2 tile ready", 52: "P2 tile loads issued", 53: "P2 tile posted", 60: "  P2 mma first stage full", 61: "  P2 mma tile issued",
          70: "    P2 epi acc_full", 73: "    P2 epi tmem loaded", 74: "    P2 epi staging free", 75: "    P2 epi packed", 71: "    P2 epi store issued", 72: "    P2 epi done",
          80: "            E drain begin", 81: "            E drain end", 82: "            E wait stores", 83: "            E stores done", 86: "            E signalled",
