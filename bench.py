@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--train-steps", type=int, default=20, help="timed steps of each training sub-record")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="keep the host UNet in NCHW (default: channels_last)")
+    ap.add_argument("--stock-epilogues", action="store_true",
+                    help="stock PyTorch GroupNorm / SiLU / GEGLU in the host UNet instead of the pv_backbone.cu kernels (A/B)")
     ap.add_argument("--workload", default="generate", choices=["generate", "train"],
                     help="generate: BASELINE config[1] (the headline line);  train: config[3] training step")
     ap.add_argument("--train-batch", type=int, default=16, help="samples per GPU per training step (config[3])")
@@ -538,7 +540,10 @@ def main():
                           f"processors on 16 attn2 layers + image/text adapters",
               "batch_per_gpu": args.batch, "denoise_steps": args.denoise_steps, "latent": args.latent,
               "unet_evals_per_step": "uncond+cond (reference infer.py:103-114)", "image_tokens": Li,
-              "token_index": token_index, "l2": "step working set >> L2 (126 MB); roofline leg rotates buffers > L2"}
+              "token_index": token_index, "l2": "step working set >> L2 (126 MB); roofline leg rotates buffers > L2",
+              "backbone": ("channels-last host UNet; " if not args.nchw else "NCHW host UNet; ")
+              + ("stock PyTorch GroupNorm / SiLU / GEGLU" if (args.stock_epilogues or args.nchw or args.impl != "ours")
+                 else "GroupNorm(+SiLU) and GEGLU epilogues as photoverse_b200 kernels (pv_backbone.cu)")}
 
     if args.workload == "train" and args.impl == "ours":
         return run_train(args, rank, world, local_rank)
@@ -582,6 +587,8 @@ def main():
 
     dtype = torch.bfloat16
     unet, image_adapter, text_adapter = build_models(device, dtype, channels_last=not args.nchw)
+    if args.stock_epilogues:
+        unet.set_fused_epilogues(False)
     eng = GenerationEngine(unet, image_adapter, text_adapter, args.batch, args.latent, args.denoise_steps, 1.0,
                            token_index, args.mode, dtype, device, use_cuda_graph=not args.no_graph)
     host = shard_inputs(args.batch * world, world, rank, args.latent, dtype)       # per-sample seeds by GLOBAL index

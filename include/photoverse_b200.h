@@ -234,6 +234,31 @@ int pv_self_attn_fwd(const void* q, const void* k, const void* v, int64_t ld, vo
 int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* keep_mask, float alpha, int64_t n,
                        void* stream);
 
+/* ---- HBM-bound epilogues of the UNet evaluation that calls the path (reference models/infer.py:103-116
+ * runs diffusers' UNet2DConditionModel: ResnetBlock2D `norm -> SiLU -> conv`, Transformer2DModel `norm -> proj_in`,
+ * FeedForward GEGLU).  Inference only, bf16. ---------------------------------------------------------------------------
+ * pv_group_norm_nhwc_fwd: y = [SiLU](GroupNorm_groups(x + add) * gamma + beta) on a CHANNELS-LAST activation: x, y are
+ * [B, HW, C] dense (the memory of a torch.channels_last [B, C, H, W] tensor), gamma / beta fp32 [C]; add_bc: optional fp32
+ * [B, C] addend broadcast over the pixels (NULL = none) -- ResnetBlock2D's `conv1 bias + time_emb_proj(temb)` between
+ * conv1 and norm2; statistics in fp32 over the HW * C / groups elements of a (sample, group), biased variance, `eps`
+ * inside the square root (torch.nn.GroupNorm).  C % 8 == 0, C % groups == 0, groups <= 64, C <= 4096.
+ * ws: pv_group_norm_nhwc_ws_bytes(...) bytes of scratch (partial sums; -1 = unsupported shape).  Two launches, fixed
+ * summation order.
+ * pv_add_bias_nhwc_fwd: out[r, c] = a[r, c] + b[r, c] + bias[c] (rows x C dense, bias fp32, C % 8 == 0; out may alias a
+ * or b) -- a block's residual sum together with the bias of its last convolution.
+ * pv_layer_norm_fwd: y = LayerNorm(x) * gamma + beta over the last dimension of x [rows, C] dense, C % 8 == 0, C <= 1280,
+ * gamma / beta fp32 (BasicTransformerBlock norm1 / norm2 / norm3).
+ * pv_geglu_fwd: y[m, n] = h[m, n] * gelu(h[m, N + n]) with the exact (erf) GELU, gelu(.) rounded to bf16 before the
+ * product like the two-kernel torch sequence; h: [M, 2N] with row stride ldh (elements), y: [M, N] dense; N % 8 == 0. */
+int64_t pv_group_norm_nhwc_ws_bytes(int64_t B, int64_t HW, int C, int groups);
+int pv_group_norm_nhwc_fwd(pv_dtype dt, const void* x, const float* add_bc, const float* gamma, const float* beta, void* y,
+                           void* ws, int64_t B, int64_t HW, int C, int groups, float eps, int silu, void* stream);
+int pv_add_bias_nhwc_fwd(pv_dtype dt, const void* a, const void* b, const float* bias, void* out, int64_t rows, int C,
+                         void* stream);
+int pv_layer_norm_fwd(pv_dtype dt, const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C,
+                      float eps, void* stream);
+int pv_geglu_fwd(pv_dtype dt, const void* h, void* y, int64_t M, int N, int64_t ldh, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

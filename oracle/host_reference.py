@@ -90,6 +90,8 @@ def clone_with_oracle_processors(unet, device=None, dtype=None, compute_dtype=No
             op.to_v_ip[0].weight = proc.to_v_ip[0].weight
             op.compute_dtype = compute_dtype
             m.set_processor(op)
+    if hasattr(ref, "set_fused_epilogues"):
+        ref.set_fused_epilogues(False)           # the reference arm runs stock PyTorch ops only
     if device is not None or dtype is not None:
         ref.to(device=device, dtype=dtype)
     return ref

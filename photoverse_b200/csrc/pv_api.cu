@@ -78,6 +78,13 @@ int inject_concept_fwd(bool bf16, const void* in, const void* concept, const int
                        int cols, cudaStream_t stream);
 int inject_concept_bwd(bool bf16, const void* dout, const int* idx, void* din, void* dconcept, int B, int L, int T, int cols,
                        cudaStream_t stream);
+long long group_norm_nhwc_ws_bytes(long long B, long long HW, int C, int G);
+int group_norm_nhwc(const void* x, const float* add_bc, const float* gamma, const float* beta, void* y, void* ws, long long B,
+                    long long HW, int C, int G, float eps, bool silu, cudaStream_t stream);
+int add_bias_nhwc(const void* a, const void* b, const float* bias, void* out, long long rows, int C, cudaStream_t stream);
+int layer_norm_bf16(const void* x, const float* gamma, const float* beta, void* y, long long rows, int C, float eps,
+                    cudaStream_t stream);
+int geglu(const void* h, void* y, long long M, int N, long long ldh, cudaStream_t stream);
 int dropout_bwd_acc(bool bf16, void* dst, const void* src, const uint8_t* mask, float alpha, long long n,
                     cudaStream_t stream);
 
@@ -498,6 +505,35 @@ int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* k
                        void* stream) {
   PV_REQUIRE(dst && src && keep_mask, "null pointer");
   return dropout_bwd_acc(dt == PV_BF16, dst, src, keep_mask, alpha, n, as_stream(stream));
+}
+
+int64_t pv_group_norm_nhwc_ws_bytes(int64_t B, int64_t HW, int C, int groups) { return group_norm_nhwc_ws_bytes(B, HW, C, groups); }
+
+int pv_group_norm_nhwc_fwd(pv_dtype dt, const void* x, const float* add_bc, const float* gamma, const float* beta, void* y,
+                           void* ws, int64_t B, int64_t HW, int C, int groups, float eps, int silu, void* stream) {
+  PV_REQUIRE(x && gamma && beta && y && ws, "null pointer");
+  PV_REQUIRE(dt == PV_BF16, "bf16 activations only (the fp32 parity mode keeps the stock GroupNorm)");
+  return group_norm_nhwc(x, add_bc, gamma, beta, y, ws, B, HW, C, groups, eps, silu != 0, as_stream(stream));
+}
+
+int pv_add_bias_nhwc_fwd(pv_dtype dt, const void* a, const void* b, const float* bias, void* out, int64_t rows, int C,
+                         void* stream) {
+  PV_REQUIRE(a && b && bias && out, "null pointer");
+  PV_REQUIRE(dt == PV_BF16, "bf16 activations only");
+  return add_bias_nhwc(a, b, bias, out, rows, C, as_stream(stream));
+}
+
+int pv_layer_norm_fwd(pv_dtype dt, const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C,
+                      float eps, void* stream) {
+  PV_REQUIRE(x && gamma && beta && y, "null pointer");
+  PV_REQUIRE(dt == PV_BF16, "bf16 activations only");
+  return layer_norm_bf16(x, gamma, beta, y, rows, C, eps, as_stream(stream));
+}
+
+int pv_geglu_fwd(pv_dtype dt, const void* h, void* y, int64_t M, int N, int64_t ldh, void* stream) {
+  PV_REQUIRE(h && y, "null pointer");
+  PV_REQUIRE(dt == PV_BF16, "bf16 activations only");
+  return geglu(h, y, M, N, ldh, as_stream(stream));
 }
 
 }  // extern "C"

@@ -18,6 +18,57 @@ import torch.nn.functional as F
 from torch import nn
 
 
+# Inference-time epilogues of the backbone as photoverse_b200 kernels (csrc/pv_backbone.cu): GroupNorm (+ SiLU) directly on
+# the channels-last activation (the stock sequence is NHWC -> NCHW copy, moments, normalise, SiLU, NCHW -> NHWC copy: 16 %
+# of a generation step's GPU time) and the GEGLU product.  Used for CUDA bf16 channels-last activations with autograd
+# off; training, fp32 parity runs and NCHW models keep the stock PyTorch ops.  ``FUSED_EPILOGUES = False`` restores the
+# stock sequence everywhere; ``UNetSD15.set_fused_epilogues(False)`` does so for one model (bench.py --stock-epilogues;
+# the oracle arm of the parity tests; tests compare the two).
+FUSED_EPILOGUES = True
+
+
+def _fused(mod: nn.Module, x: torch.Tensor) -> bool:
+    return (FUSED_EPILOGUES and getattr(mod, "_pv_fused", True) and x.is_cuda and x.dtype == torch.bfloat16
+            and not torch.is_grad_enabled())
+
+
+def _f32_params(mod: nn.Module, *names):
+    """fp32 copies of a module's (bf16) parameters for the kernels' affine terms, refreshed when a parameter changes."""
+    ps = [getattr(mod, n) for n in names]
+    key = tuple((p.data_ptr(), p._version) for p in ps)
+    cached = getattr(mod, "_pv_f32", None)
+    if cached is None or cached[0] != key:
+        cached = (key, [p.detach().float().contiguous() for p in ps])
+        mod._pv_f32 = cached
+    return cached[1]
+
+
+def _nhwc(x: torch.Tensor) -> bool:
+    return (x.dim() == 4 and x.shape[1] % 8 == 0 and x.shape[1] <= 4096 and x.is_contiguous(memory_format=torch.channels_last)
+            and not x.is_contiguous())
+
+
+def group_norm_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``silu(norm(x + add[:, :, None, None]))`` / ``norm(...)`` -- one fused pass over a channels-last activation when the
+    kernel applies (``add``: fp32 ``[B, C]``)."""
+    if _fused(norm, x) and _nhwc(x):
+        from .. import ops
+        gamma, beta = _f32_params(norm, "weight", "bias")
+        return ops.group_norm_nhwc(x, gamma, beta, norm.num_groups, norm.eps, silu, add)
+    if add is not None:
+        x = x + add.to(x.dtype)[:, :, None, None]
+    y = norm(x)
+    return F.silu(y) if silu else y
+
+
+def layer_norm(norm: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    if _fused(norm, x) and x.is_contiguous() and x.shape[-1] % 8 == 0 and x.shape[-1] <= 1280:
+        from .. import ops
+        gamma, beta = _f32_params(norm, "weight", "bias")
+        return ops.layer_norm(x, gamma, beta, norm.eps)
+    return norm(x)
+
+
 class AttnProcessor2_0:
     """Stock SDPA processor for the self-attention (attn1) layers -- library code, outside the hot path."""
 
@@ -77,7 +128,11 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        x, gate = self.proj(x).chunk(2, dim=-1)
+        h = self.proj(x)
+        if _fused(self, h) and h.is_contiguous() and h.shape[-1] % 16 == 0:
+            from .. import ops
+            return ops.geglu(h)
+        x, gate = h.chunk(2, dim=-1)
         return x * F.gelu(gate)
 
 
@@ -103,9 +158,9 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x, encoder_hidden_states):
-        x = self.attn1(self.norm1(x)) + x
-        x = self.attn2(self.norm2(x), encoder_hidden_states=encoder_hidden_states) + x
-        return self.ff(self.norm3(x)) + x
+        x = self.attn1(layer_norm(self.norm1, x)) + x
+        x = self.attn2(layer_norm(self.norm2, x), encoder_hidden_states=encoder_hidden_states) + x
+        return self.ff(layer_norm(self.norm3, x)) + x
 
 
 class Transformer2DModel(nn.Module):
@@ -119,7 +174,17 @@ class Transformer2DModel(nn.Module):
     def forward(self, x, encoder_hidden_states):
         B, C, H, W = x.shape
         res = x
-        h = self.proj_in(self.norm(x))
+        if _fused(self.norm, x) and _nhwc(x):
+            # channels-last: the 1x1 convolutions are Linears on the [B, HW, C] view (bias in the GEMM epilogue instead of a
+            # broadcast-add launch), the residual sum runs on the same view
+            h = group_norm_act(self.norm, x, False).permute(0, 2, 3, 1).reshape(B, H * W, C)
+            h = F.linear(h, self.proj_in.weight.view(C, C), self.proj_in.bias)
+            for blk in self.transformer_blocks:
+                h = blk(h, encoder_hidden_states)
+            h = F.linear(h, self.proj_out.weight.view(C, C), self.proj_out.bias)
+            h = h + res.permute(0, 2, 3, 1).reshape(B, H * W, C)
+            return h.reshape(B, H, W, C).permute(0, 3, 1, 2)
+        h = self.proj_in(group_norm_act(self.norm, x, False))
         h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
         for blk in self.transformer_blocks:
             h = blk(h, encoder_hidden_states)
@@ -139,12 +204,40 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
-        h = self.conv1(F.silu(self.norm1(x)))
+        if _fused(self.norm1, x) and _nhwc(x) and self.conv1.out_channels % 8 == 0:
+            # the convolutions run bias-free; conv1's bias and the time-embedding projection enter norm2's two passes as a
+            # per-(sample, channel) addend, conv2's (and the shortcut's) bias enters the residual sum: 2 launches instead
+            # of 4 broadcast adds that each re-read and re-write the activation
+            c1, c2, cs = self.conv1, self.conv2, self.conv_shortcut
+            h = F.conv2d(group_norm_act(self.norm1, x, True), c1.weight, None, c1.stride, c1.padding)
+            add = self.time_emb_proj(F.silu(temb)).float() + _f32_params(c1, "bias")[0]
+            h = F.conv2d(group_norm_act(self.norm2, h, True, add), c2.weight, None, c2.stride, c2.padding)
+            bias = _f32_params(c2, "bias")[0]
+            if cs is not None:
+                x = F.conv2d(x, cs.weight, None, cs.stride, cs.padding)
+                bias = self._shortcut_bias()
+            from .. import ops
+            return ops.add_bias_nhwc(x, h, bias)
+        h = self.conv1(group_norm_act(self.norm1, x, True))
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
-        h = self.conv2(self.dropout(F.silu(self.norm2(h))))
+        h = self.conv2(self.dropout(group_norm_act(self.norm2, h, True)))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
+
+
+def _resnet_shortcut_bias(self):
+    """conv2.bias + conv_shortcut.bias in fp32 (cached by parameter versions)."""
+    c2, cs = self.conv2, self.conv_shortcut
+    key = (c2.bias.data_ptr(), c2.bias._version, cs.bias.data_ptr(), cs.bias._version)
+    cached = getattr(self, "_pv_sum_bias", None)
+    if cached is None or cached[0] != key:
+        cached = (key, (c2.bias.detach().float() + cs.bias.detach().float()).contiguous())
+        self._pv_sum_bias = cached
+    return cached[1]
+
+
+ResnetBlock2D._shortcut_bias = _resnet_shortcut_bias
 
 
 class Downsample2D(nn.Module):
@@ -296,6 +389,14 @@ class UNetSD15(nn.Module):
             for m in mods.values():
                 m.set_processor(processor)
 
+    def set_fused_epilogues(self, enabled: bool):
+        """photoverse_b200 epilogue kernels (GroupNorm + SiLU, LayerNorm, GEGLU, bias / residual sums) for this model's
+        inference passes (default on) or the stock PyTorch ops."""
+        for m in self.modules():
+            if isinstance(m, (nn.GroupNorm, nn.LayerNorm, GEGLU)):
+                m._pv_fused = bool(enabled)
+        return self
+
     def forward(self, sample, timestep, encoder_hidden_states):
         if not torch.is_tensor(timestep):
             timestep = torch.tensor([timestep], device=sample.device)
@@ -309,5 +410,5 @@ class UNetSD15(nn.Module):
         x = self.mid_block(x, temb, encoder_hidden_states)
         for blk in self.up_blocks:
             x = blk(x, skips, temb, encoder_hidden_states)
-        x = self.conv_out(F.silu(self.conv_norm_out(x)))
+        x = self.conv_out(group_norm_act(self.conv_norm_out, x, True))
         return SimpleNamespace(sample=x)

@@ -366,3 +366,79 @@ def self_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> 
     out = torch.empty(B, S, C, device=q.device, dtype=q.dtype)
     _lib.check(lib.pv_self_attn_fwd(_ptr(q), _ptr(k), _ptr(v), ld, _ptr(out), _ptr(ws), B, S, C, heads, _stream()), "pv_self_attn_fwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# epilogues of the UNet evaluation around the path (SURVEY 8 row f1; inference only)
+# ------------------------------------------------------------------------------------------------------------
+def group_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+                    add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[SiLU](GroupNorm(x + add) * gamma + beta) of a ``torch.channels_last`` bf16 activation ``[B, C, H, W]`` (also accepts
+    the equivalent dense ``[B, HW, C]``); gamma / beta fp32 ``[C]``; ``add``: optional fp32 ``[B, C]`` broadcast over the
+    pixels.  The result has the layout of ``x``."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16):
+        raise _lib.PhotoverseB200Error("group_norm_nhwc: CUDA bfloat16 activations required (there is no CPU path)")
+    if x.dim() == 4:
+        B, C, H, W = x.shape
+        HW = H * W
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            raise _lib.PhotoverseB200Error("group_norm_nhwc: the activation must be channels_last-contiguous")
+    else:
+        B, HW, C = x.shape
+        if not x.is_contiguous():
+            raise _lib.PhotoverseB200Error("group_norm_nhwc: [B, HW, C] input must be contiguous")
+    assert gamma.dtype == beta.dtype == torch.float32 and gamma.is_contiguous() and beta.is_contiguous() and gamma.numel() == C
+    if add is not None:
+        assert add.dtype == torch.float32 and add.is_contiguous() and add.shape == (B, C) and add.is_cuda
+    lib = _lib.lib()
+    nbytes = int(lib.pv_group_norm_nhwc_ws_bytes(B, HW, C, groups))
+    if nbytes < 0:
+        raise _lib.PhotoverseB200Error(f"group_norm_nhwc: unsupported shape B={B} HW={HW} C={C} groups={groups}")
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    y = torch.empty_like(x)                     # preserve_format: channels_last stays channels_last
+    check(lib.pv_group_norm_nhwc_fwd(PV_BF16, _ptr(x), _ptr(add), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(ws), B, HW, C, groups,
+                                     float(eps), 1 if silu else 0, _stream()), "pv_group_norm_nhwc_fwd")
+    return y
+
+
+def add_bias_nhwc(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """``a + b + bias[c]`` for two bf16 activations of one shape and memory layout whose FASTEST dimension is the channel
+    (channels_last ``[B, C, H, W]`` or dense ``[..., C]``); bias fp32 ``[C]``."""
+    if not (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape == b.shape):
+        raise _lib.PhotoverseB200Error("add_bias_nhwc: two CUDA bfloat16 tensors of one shape required (there is no CPU path)")
+    if a.dim() == 4:
+        if not (a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous(memory_format=torch.channels_last)):
+            raise _lib.PhotoverseB200Error("add_bias_nhwc: 4-D operands must be channels_last-contiguous")
+        C = a.shape[1]
+    else:
+        if not (a.is_contiguous() and b.is_contiguous()):
+            raise _lib.PhotoverseB200Error("add_bias_nhwc: operands must be contiguous")
+        C = a.shape[-1]
+    assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == C
+    out = torch.empty_like(a)
+    check(_lib.lib().pv_add_bias_nhwc_fwd(PV_BF16, _ptr(a), _ptr(b), _ptr(bias), _ptr(out), a.numel() // C, C, _stream()),
+          "pv_add_bias_nhwc_fwd")
+    return out
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
+    """LayerNorm over the last dimension of a contiguous bf16 ``[..., C]`` tensor (C <= 1280); gamma / beta fp32 ``[C]``."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()):
+        raise _lib.PhotoverseB200Error("layer_norm: contiguous CUDA bfloat16 input required (there is no CPU path)")
+    C = x.shape[-1]
+    assert gamma.dtype == beta.dtype == torch.float32 and gamma.is_contiguous() and beta.is_contiguous() and gamma.numel() == C
+    y = torch.empty_like(x)
+    check(_lib.lib().pv_layer_norm_fwd(PV_BF16, _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // C, C, float(eps), _stream()),
+          "pv_layer_norm_fwd")
+    return y
+
+
+def geglu(h: torch.Tensor) -> torch.Tensor:
+    """``h[..., :N] * gelu(h[..., N:])`` (exact GELU) of a bf16 projection ``[..., 2N]`` with contiguous rows."""
+    if not (h.is_cuda and h.dtype == torch.bfloat16 and h.is_contiguous()):
+        raise _lib.PhotoverseB200Error("geglu: contiguous CUDA bfloat16 input required (there is no CPU path)")
+    N = h.shape[-1] // 2
+    M = h.numel() // (2 * N)
+    y = torch.empty(*h.shape[:-1], N, device=h.device, dtype=h.dtype)
+    check(_lib.lib().pv_geglu_fwd(PV_BF16, _ptr(h), _ptr(y), M, N, 2 * N, _stream()), "pv_geglu_fwd")
+    return y

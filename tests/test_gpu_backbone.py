@@ -1,0 +1,139 @@
+"""GPU (B200): the inference-time epilogue kernels of the host UNet (csrc/pv_backbone.cu) against the
+stock PyTorch ops they replace -- GroupNorm (+ SiLU) on channels-last activations and the GEGLU product -- through the
+C ABI, and the UNet with / without them."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (B, C, H, W): every GroupNorm width of the SD-1.5 UNet (320 ... 2560 with the skip concatenations), ragged pixel counts
+GN_SHAPES = [(2, 320, 64, 64), (2, 640, 32, 32), (2, 960, 32, 32), (1, 1280, 16, 16), (1, 1920, 16, 16), (2, 2560, 8, 8),
+             (3, 1280, 8, 8), (2, 320, 7, 9), (1, 640, 1, 3), (16, 640, 64, 64)]
+
+
+@pytest.mark.parametrize("shape", GN_SHAPES, ids=[f"B{b}_C{c}_{h}x{w}" for b, c, h, w in GN_SHAPES])
+@pytest.mark.parametrize("silu,with_add", [(True, False), (False, False), (True, True)], ids=["silu", "plain", "silu-addend"])
+def test_group_norm_nhwc_matches_torch(cuda_device, shape, silu, with_add):
+    from photoverse_b200 import ops
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(B * 1000 + C + H)
+    # per-channel offsets far from zero: the statistics must survive |mean| >> std
+    x = (torch.randn(B, C, H, W, generator=g) * 0.7 + torch.randn(1, C, 1, 1, generator=g) * 4.0 + 3.0)
+    x = x.to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gamma = (1.0 + 0.3 * torch.randn(C, generator=g)).to(cuda_device)
+    beta = (0.2 * torch.randn(C, generator=g)).to(cuda_device)
+    eps = 1e-5 if silu else 1e-6
+    # ResnetBlock2D: conv1 bias + time-embedding projection, one value per (sample, channel), added before the statistics
+    add = (torch.randn(B, C, generator=g) * 1.5).to(cuda_device) if with_add else None
+    y = ops.group_norm_nhwc(x, gamma, beta, 32, eps, silu, add)
+    assert y.shape == x.shape and y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    xin = x.float() if add is None else x.float() + add[:, :, None, None]
+    ref = F.group_norm(xin, 32, gamma, beta, eps)              # fp32 torch reference on the same bf16 input
+    if silu:
+        ref = F.silu(ref)
+    err = (y.float() - ref).abs()
+    tol = 1e-2 + 1e-2 * ref.abs()                              # bf16 output: 2^-8 relative + the affine cancellation
+    assert bool((err <= tol).all()), f"max err {err.max().item():.4e} at |ref| {ref.abs().flatten()[err.argmax()].item():.3f}"
+    # bit-reproducible (fixed summation order)
+    assert torch.equal(y, ops.group_norm_nhwc(x, gamma, beta, 32, eps, silu, add))
+
+
+def test_group_norm_nhwc_rejects_what_it_cannot_do(cuda_device):
+    from photoverse_b200 import _lib, ops
+    x = torch.randn(2, 320, 8, 8, device=cuda_device, dtype=torch.bfloat16)
+    w = torch.ones(320, device=cuda_device)
+    with pytest.raises(_lib.PhotoverseB200Error):
+        ops.group_norm_nhwc(x, w, w, 32, 1e-5, True)                       # NCHW-contiguous
+    with pytest.raises(_lib.PhotoverseB200Error):
+        ops.group_norm_nhwc(x.float().contiguous(memory_format=torch.channels_last), w, w, 32, 1e-5, True)   # fp32
+    assert _lib.lib().pv_group_norm_nhwc_ws_bytes(2, 64, 324, 32) == -1      # C % 8, C % groups
+
+
+@pytest.mark.parametrize("M,N", [(16 * 4096, 1280), (16 * 1024, 2560), (4096, 5120), (1024, 5120), (7, 16)])
+def test_geglu_matches_torch(cuda_device, M, N):
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(N + M)
+    h = (torch.randn(M, 2 * N, generator=g) * 1.5).to(cuda_device, torch.bfloat16)
+    y = ops.geglu(h)
+    a, gate = h.chunk(2, dim=-1)
+    ref = a * F.gelu(gate)                                     # the stock two-kernel bf16 sequence
+    assert y.shape == ref.shape
+    # same rounding points (gelu rounded to bf16, then the product): differences are last-place flips of erf
+    err = (y.float() - ref.float()).abs()
+    assert bool((err <= 2e-3 + 8e-3 * ref.float().abs()).all()), err.max().item()
+    ref32 = a.float() * F.gelu(gate.float())
+    assert bool(((y.float() - ref32).abs() <= 2e-3 + 1.2e-2 * ref32.abs()).all())
+
+
+@pytest.mark.parametrize("rows,C", [(16 * 4096, 320), (16 * 1024, 640), (4096, 1280), (77, 1280), (3, 8), (5, 328)])
+def test_layer_norm_matches_torch(cuda_device, rows, C):
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn(rows, C, generator=g) * 2.0 + torch.randn(rows, 1, generator=g) * 3.0).to(cuda_device, torch.bfloat16)
+    gamma = (1.0 + 0.3 * torch.randn(C, generator=g)).to(cuda_device)
+    beta = (0.2 * torch.randn(C, generator=g)).to(cuda_device)
+    y = ops.layer_norm(x, gamma, beta, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    err = (y.float() - ref).abs()
+    assert y.dtype == torch.bfloat16 and bool((err <= 1e-2 + 1e-2 * ref.abs()).all()), err.max().item()
+    stock = F.layer_norm(x, (C,), gamma.to(torch.bfloat16), beta.to(torch.bfloat16), 1e-5)
+    assert (y.float() - ref).abs().max() <= (stock.float() - ref).abs().max() + 1e-2     # no worse than the op it replaces
+
+
+@pytest.mark.parametrize("shape", [(16, 320, 64, 64), (2, 1280, 8, 8), (3, 640, 5, 7)])
+def test_add_bias_nhwc_matches_torch(cuda_device, shape):
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(shape[1])
+    a = torch.randn(*shape, generator=g).to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(*shape, generator=g).to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(shape[1], generator=g).to(cuda_device)
+    y = ops.add_bias_nhwc(a, b, bias)
+    ref = a.float() + b.float() + bias[None, :, None, None]
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert bool(((y.float() - ref).abs() <= 4e-3 * ref.abs() + 1e-6).all())            # one bf16 rounding of the exact sum
+    d = torch.randn(7, 33, 64, generator=g).to(cuda_device, torch.bfloat16)
+    assert torch.equal(ops.add_bias_nhwc(d, d, bias[:64].contiguous()).float(),
+                       (2 * d.float() + bias[:64]).to(torch.bfloat16).float())
+
+
+def test_unet_with_fused_epilogues_matches_stock(cuda_device):
+    """One UNet evaluation (channels-last bf16, random init, batch 2, latent 32) with the fused epilogues against the same
+    model with the stock ops; and the fused kernels really run (native launch count)."""
+    import photoverse_b200 as pv
+    from photoverse_b200 import _lib
+    from photoverse_b200.host.unet_sd15 import UNetSD15
+    torch.manual_seed(3)
+    unet = UNetSD15()
+    pv.set_visual_cross_attention_adapter(unet, num_tokens=(5,))
+    unet.requires_grad_(False).eval().to(device=cuda_device, dtype=torch.bfloat16).to(memory_format=torch.channels_last)
+    x = torch.randn(2, 4, 32, 32, device=cuda_device, dtype=torch.bfloat16)
+    text = torch.randn(2, 77, 768, device=cuda_device, dtype=torch.bfloat16)
+    img = torch.randn(2, 5, 768, device=cuda_device, dtype=torch.bfloat16)
+    t = torch.tensor([500], device=cuda_device)
+    with torch.no_grad():
+        unet(x, t, (text, img))                     # first call packs the processors' weights: keep it out of the counts
+        unet.set_fused_epilogues(False)
+        n0 = _lib.launch_count()
+        stock = unet(x, t, (text, img)).sample
+        n_stock = _lib.launch_count() - n0
+        unet.set_fused_epilogues(True)
+        n0 = _lib.launch_count()
+        fused = unet(x, t, (text, img)).sample
+        n_fused = _lib.launch_count() - n0
+    # 61 GroupNorms x 2 launches + 16 GEGLUs + 48 LayerNorms + 22 residual sums
+    assert n_fused == n_stock + 2 * 61 + 16 + 48 + 22, (n_stock, n_fused)
+    cos = F.cosine_similarity(stock.double().flatten(1), fused.double().flatten(1), dim=1).min().item()
+    rel = ((stock.float() - fused.float()).norm() / stock.float().norm()).item()
+    print(f"UNet eval, fused vs stock epilogues: cosine {cos:.6f} relative L2 {rel:.4e}; native launches {n_stock} -> {n_fused}")
+    assert cos >= 0.9995 and rel <= 3e-2
+    # with autograd on (training) the stock ops run: the kernels are inference-only
+    from photoverse_b200.host.unet_sd15 import group_norm_act
+    norm = unet.conv_norm_out
+    h = torch.randn(2, 320, 8, 8, device=cuda_device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    n0 = _lib.launch_count()
+    group_norm_act(norm, h, True)
+    assert _lib.launch_count() == n0
+    with torch.no_grad():
+        group_norm_act(norm, h, True)
+    assert _lib.launch_count() == n0 + 2

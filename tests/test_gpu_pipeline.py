@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _models(device, dtype, T=5, seed=0):
+def _models(device, dtype, T=5, seed=0, channels_last=False):
     import photoverse_b200 as pv
     from photoverse_b200.host.unet_sd15 import UNetSD15
     torch.manual_seed(seed)
@@ -16,6 +16,8 @@ def _models(device, dtype, T=5, seed=0):
     ia, ta = pv.PhotoVerseAdapter(num_tokens=T), pv.PhotoVerseAdapter(num_tokens=T)
     for m in (unet, ia, ta):
         m.requires_grad_(False).eval().to(device=device, dtype=dtype)
+    if channels_last:        # the benchmarked configuration: NHWC backbone with the fused GroupNorm / GEGLU epilogues
+        unet.to(memory_format=torch.channels_last)
     return unet, ia, ta
 
 
@@ -24,15 +26,16 @@ def _cos(a, b):
     return torch.nn.functional.cosine_similarity(a, b, dim=1).min().item()
 
 
-@pytest.mark.parametrize("dtype,mode,token_index,batch,guidance", [
-    (torch.bfloat16, "batched", 0, 1, 1.0), (torch.float32, "two_call", "full", 1, 1.0),
-    (torch.bfloat16, "batched", 0, 8, 1.0),          # BASELINE config[1]: batch 8, guidance 1.0
-    (torch.bfloat16, "batched", 0, 2, 7.5),          # BASELINE config[2]: classifier-free guidance 7.5 (doubled batch)
-], ids=["bf16-batched-idx0", "f32-two_call-full", "bf16-batch8-config1", "bf16-cfg7.5-config2"])
-def test_final_latent_cosine_50_steps(cuda_device, dtype, mode, token_index, batch, guidance):
+@pytest.mark.parametrize("dtype,mode,token_index,batch,guidance,nhwc", [
+    (torch.bfloat16, "batched", 0, 1, 1.0, False), (torch.float32, "two_call", "full", 1, 1.0, False),
+    (torch.bfloat16, "batched", 0, 8, 1.0, False),          # BASELINE config[1]: batch 8, guidance 1.0
+    (torch.bfloat16, "batched", 0, 2, 7.5, False),          # BASELINE config[2]: classifier-free guidance 7.5 (doubled batch)
+    (torch.bfloat16, "batched", 0, 2, 1.0, True),           # as bench.py runs it: channels-last backbone, fused epilogues
+], ids=["bf16-batched-idx0", "f32-two_call-full", "bf16-batch8-config1", "bf16-cfg7.5-config2", "bf16-nhwc-fused-epilogues"])
+def test_final_latent_cosine_50_steps(cuda_device, dtype, mode, token_index, batch, guidance, nhwc):
     from oracle.host_reference import clone_adapter_as_oracle, clone_with_oracle_processors
     from photoverse_b200.host.pipeline import run_generation, synthetic_inputs
-    unet, ia, ta = _models(cuda_device, dtype)
+    unet, ia, ta = _models(cuda_device, dtype, channels_last=nhwc)
     ref_unet = clone_with_oracle_processors(unet)
     ref_ia, ref_ta = clone_adapter_as_oracle(ia, cuda_device, dtype), clone_adapter_as_oracle(ta, cuda_device, dtype)
     inp = synthetic_inputs(batch, 64, seed=5, device=cuda_device, dtype=dtype)
