@@ -243,7 +243,10 @@ int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* k
  * conv1 and norm2; statistics in fp32 over the HW * C / groups elements of a (sample, group), biased variance, `eps`
  * inside the square root (torch.nn.GroupNorm).  C % 8 == 0, C % groups == 0, groups <= 64, C <= 4096.
  * ws: pv_group_norm_nhwc_ws_bytes(...) bytes of scratch (partial sums; -1 = unsupported shape).  Two launches, fixed
- * summation order.
+ * summation order.  save_stats: optional fp32 [B, groups, 2] = (mean, rstd) kept for the backward pass (NULL in inference).
+ * pv_group_norm_nhwc_bwd: dx = d loss / d x of the same expression from dy (layout of x), x, add_bc and the saved stats;
+ * gamma / beta are frozen on the PhotoVerse path (train.py:348-370 trains adapters, to_k_ip / to_v_ip and LoRA factors
+ * only), so no affine gradients are produced.  Same workspace size, two launches.
  * pv_add_bias_nhwc_fwd: out[r, c] = a[r, c] + b[r, c] + bias[c] (rows x C dense, bias fp32, C % 8 == 0; out may alias a
  * or b) -- a block's residual sum together with the bias of its last convolution.
  * pv_layer_norm_fwd: y = LayerNorm(x) * gamma + beta over the last dimension of x [rows, C] dense, C % 8 == 0, C <= 1280,
@@ -252,7 +255,11 @@ int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* k
  * product like the two-kernel torch sequence; h: [M, 2N] with row stride ldh (elements), y: [M, N] dense; N % 8 == 0. */
 int64_t pv_group_norm_nhwc_ws_bytes(int64_t B, int64_t HW, int C, int groups);
 int pv_group_norm_nhwc_fwd(pv_dtype dt, const void* x, const float* add_bc, const float* gamma, const float* beta, void* y,
-                           void* ws, int64_t B, int64_t HW, int C, int groups, float eps, int silu, void* stream);
+                           float* save_stats, void* ws, int64_t B, int64_t HW, int C, int groups, float eps, int silu,
+                           void* stream);
+int pv_group_norm_nhwc_bwd(pv_dtype dt, const void* x, const float* add_bc, const void* dy, const float* stats,
+                           const float* gamma, const float* beta, void* dx, void* ws, int64_t B, int64_t HW, int C, int groups,
+                           int silu, void* stream);
 int pv_add_bias_nhwc_fwd(pv_dtype dt, const void* a, const void* b, const float* bias, void* out, int64_t rows, int C,
                          void* stream);
 int pv_layer_norm_fwd(pv_dtype dt, const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C,

@@ -61,7 +61,8 @@ _SIGNATURES = {
     "pv_dual_attn_bwd": (c_int, [c_int] + [c_void_p] * 7 + [c_int] * 6 + [c_float, c_float, c_void_p]),
     "pv_kv_pack_bwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
     "pv_group_norm_nhwc_ws_bytes": (c_int64, [c_int64, c_int64, c_int, c_int]),
-    "pv_group_norm_nhwc_fwd": (c_int, [c_int] + [c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_float, c_int, c_void_p]),
+    "pv_group_norm_nhwc_fwd": (c_int, [c_int] + [c_void_p] * 7 + [c_int64, c_int64, c_int, c_int, c_float, c_int, c_void_p]),
+    "pv_group_norm_nhwc_bwd": (c_int, [c_int] + [c_void_p] * 8 + [c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "pv_add_bias_nhwc_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "pv_layer_norm_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "pv_geglu_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p]),

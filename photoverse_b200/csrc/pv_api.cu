@@ -79,8 +79,11 @@ int inject_concept_fwd(bool bf16, const void* in, const void* concept, const int
 int inject_concept_bwd(bool bf16, const void* dout, const int* idx, void* din, void* dconcept, int B, int L, int T, int cols,
                        cudaStream_t stream);
 long long group_norm_nhwc_ws_bytes(long long B, long long HW, int C, int G);
-int group_norm_nhwc(const void* x, const float* add_bc, const float* gamma, const float* beta, void* y, void* ws, long long B,
-                    long long HW, int C, int G, float eps, bool silu, cudaStream_t stream);
+int group_norm_nhwc(const void* x, const float* add_bc, const float* gamma, const float* beta, void* y, float* save_stats,
+                    void* ws, long long B, long long HW, int C, int G, float eps, bool silu, cudaStream_t stream);
+int group_norm_nhwc_bwd(const void* x, const float* add_bc, const void* dy, const float* stats, const float* gamma,
+                        const float* beta, void* dx, void* ws, long long B, long long HW, int C, int G, bool silu,
+                        cudaStream_t stream);
 int add_bias_nhwc(const void* a, const void* b, const float* bias, void* out, long long rows, int C, cudaStream_t stream);
 int layer_norm_bf16(const void* x, const float* gamma, const float* beta, void* y, long long rows, int C, float eps,
                     cudaStream_t stream);
@@ -510,10 +513,19 @@ int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* k
 int64_t pv_group_norm_nhwc_ws_bytes(int64_t B, int64_t HW, int C, int groups) { return group_norm_nhwc_ws_bytes(B, HW, C, groups); }
 
 int pv_group_norm_nhwc_fwd(pv_dtype dt, const void* x, const float* add_bc, const float* gamma, const float* beta, void* y,
-                           void* ws, int64_t B, int64_t HW, int C, int groups, float eps, int silu, void* stream) {
+                           float* save_stats, void* ws, int64_t B, int64_t HW, int C, int groups, float eps, int silu,
+                           void* stream) {
   PV_REQUIRE(x && gamma && beta && y && ws, "null pointer");
   PV_REQUIRE(dt == PV_BF16, "bf16 activations only (the fp32 parity mode keeps the stock GroupNorm)");
-  return group_norm_nhwc(x, add_bc, gamma, beta, y, ws, B, HW, C, groups, eps, silu != 0, as_stream(stream));
+  return group_norm_nhwc(x, add_bc, gamma, beta, y, save_stats, ws, B, HW, C, groups, eps, silu != 0, as_stream(stream));
+}
+
+int pv_group_norm_nhwc_bwd(pv_dtype dt, const void* x, const float* add_bc, const void* dy, const float* stats,
+                           const float* gamma, const float* beta, void* dx, void* ws, int64_t B, int64_t HW, int C, int groups,
+                           int silu, void* stream) {
+  PV_REQUIRE(x && dy && stats && gamma && beta && dx && ws, "null pointer");
+  PV_REQUIRE(dt == PV_BF16, "bf16 activations only");
+  return group_norm_nhwc_bwd(x, add_bc, dy, stats, gamma, beta, dx, ws, B, HW, C, groups, silu != 0, as_stream(stream));
 }
 
 int pv_add_bias_nhwc_fwd(pv_dtype dt, const void* a, const void* b, const float* bias, void* out, int64_t rows, int C,

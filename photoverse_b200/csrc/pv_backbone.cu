@@ -25,6 +25,7 @@ namespace pv {
 
 constexpr int GN_THREADS_MAX = 512;
 constexpr int GN_MAX_G = 64;
+constexpr int GN_UNROLL = 4;
 
 __device__ __forceinline__ void bf16x8_unpack(const uint4& v, float* f) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -70,14 +71,27 @@ gn_stats_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
   const long long p0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long p1 = p0 + rows_per_cta < HW ? p0 + rows_per_cta : HW;
   const uint4* xv = reinterpret_cast<const uint4*>(xb);
-  for (long long p = p0 + pl; p < p1; p += k) {
-    float f[8];
-    bf16x8_unpack(__ldg(xv + p * vecs + v), f);
+  // GN_UNROLL independent 16-byte loads in flight per thread (one load per iteration left the kernels latency-bound:
+  // 27 % of the DRAM rate under ncu)
+  for (long long p = p0 + pl; p < p1; p += static_cast<long long>(GN_UNROLL) * k) {
+    uint4 raw[GN_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float d = f[j] - shift[j];
-      s[j] += d;
-      q[j] = fmaf(d, d, q[j]);
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const long long pp = p + static_cast<long long>(u) * k;
+      if (pp < p1) raw[u] = __ldg(xv + pp * vecs + v);
+    }
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      if (p + static_cast<long long>(u) * k < p1) {
+        float f[8];
+        bf16x8_unpack(raw[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[j] - shift[j];
+          s[j] += d;
+          q[j] = fmaf(d, d, q[j]);
+        }
+      }
     }
   }
   float* ss = gn_smem;
@@ -116,7 +130,8 @@ template <bool SILU>
 __global__ void __launch_bounds__(GN_THREADS_MAX)
 gn_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ addv, const float* __restrict__ part,
                      const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                     long long HW, int C, int G, int stat_chunks, int rows_per_cta, int k, float eps) {
+                     float* __restrict__ save_stats, long long HW, int C, int G, int stat_chunks, int rows_per_cta, int k,
+                     float eps) {
   __shared__ float s_mean[GN_MAX_G], s_rstd[GN_MAX_G];
   const int vecs = C >> 3;
   const int v = threadIdx.x % vecs;
@@ -137,6 +152,10 @@ gn_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     const float var = fmaxf(d / n - m * m, 0.f);
     s_mean[g] = __bfloat162float(xb[g * cpg]) + (addv != nullptr ? addv[static_cast<size_t>(b) * C + g * cpg] : 0.f) + m;
     s_rstd[g] = rsqrtf(var + eps);
+    if (save_stats != nullptr && blockIdx.x == 0) {          // (mean, rstd) of (sample, group) for the backward pass
+      save_stats[(static_cast<size_t>(b) * G + g) * 2] = s_mean[g];
+      save_stats[(static_cast<size_t>(b) * G + g) * 2 + 1] = s_rstd[g];
+    }
   }
   __syncthreads();
   float sc[8], sf[8];
@@ -152,16 +171,28 @@ gn_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
   const long long p1 = p0 + rows_per_cta < HW ? p0 + rows_per_cta : HW;
   const uint4* xv = reinterpret_cast<const uint4*>(xb);
   uint4* yv = reinterpret_cast<uint4*>(y + static_cast<size_t>(b) * HW * C);
-  for (long long p = p0 + pl; p < p1; p += k) {
-    float f[8];
-    bf16x8_unpack(__ldg(xv + p * vecs + v), f);
+  for (long long p = p0 + pl; p < p1; p += static_cast<long long>(GN_UNROLL) * k) {
+    uint4 raw[GN_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = fmaf(f[j], sc[j], sf[j]);
-      if (SILU) t = __fdividef(t, 1.f + __expf(-t));
-      f[j] = t;
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const long long pp = p + static_cast<long long>(u) * k;
+      if (pp < p1) raw[u] = __ldg(xv + pp * vecs + v);
     }
-    yv[p * vecs + v] = bf16x8_pack(f);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const long long pp = p + static_cast<long long>(u) * k;
+      if (pp < p1) {
+        float f[8];
+        bf16x8_unpack(raw[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(f[j], sc[j], sf[j]);
+          if (SILU) t = __fdividef(t, 1.f + __expf(-t));
+          f[j] = t;
+        }
+        yv[pp * vecs + v] = bf16x8_pack(f);
+      }
+    }
   }
 }
 
@@ -189,8 +220,8 @@ long long group_norm_nhwc_ws_bytes(long long B, long long HW, int C, int G) {
   return B * chunks * G * 2ll * static_cast<long long>(sizeof(float));
 }
 
-int group_norm_nhwc(const void* x, const float* add_bc, const float* gamma, const float* beta, void* y, void* ws, long long B,
-                    long long HW, int C, int G, float eps, bool silu, cudaStream_t stream) {
+int group_norm_nhwc(const void* x, const float* add_bc, const float* gamma, const float* beta, void* y, float* save_stats,
+                    void* ws, long long B, long long HW, int C, int G, float eps, bool silu, cudaStream_t stream) {
   PV_REQUIRE(group_norm_nhwc_ws_bytes(B, HW, C, G) >= 0,
              "need C %% 8 == 0, C %% G == 0, G <= %d, C <= %d (B=%lld HW=%lld C=%d G=%d)", GN_MAX_G, 8 * GN_THREADS_MAX, B, HW, C, G);
   PV_REQUIRE(B <= 65535, "batch too large for one launch (B=%lld)", B);
@@ -207,11 +238,215 @@ int group_norm_nhwc(const void* x, const float* add_bc, const float* gamma, cons
   if (silu)
     gn_apply_nhwc_kernel<true><<<dim3(chunks, static_cast<unsigned>(B)), threads, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x), add_bc, static_cast<const float*>(ws), gamma, beta, static_cast<__nv_bfloat16*>(y),
-        HW, C, G, chunks, rows, k, eps);
+        save_stats, HW, C, G, chunks, rows, k, eps);
   else
     gn_apply_nhwc_kernel<false><<<dim3(chunks, static_cast<unsigned>(B)), threads, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x), add_bc, static_cast<const float*>(ws), gamma, beta, static_cast<__nv_bfloat16*>(y),
-        HW, C, G, chunks, rows, k, eps);
+        save_stats, HW, C, G, chunks, rows, k, eps);
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
+// ---- backward of y = [SiLU](GroupNorm(x + add) * gamma + beta) with respect to x (training step: the backbone is frozen,
+// train.py:348-370, so only the input gradient is needed).  With xh = (x + add - mean) * rstd, z = xh * gamma + beta,
+// dz = dy * silu'(z):   dx = rstd * (dz * gamma - mean_g(dz * gamma) - xh * mean_g(dz * gamma * xh)).
+// Same two-pass shape as the forward: per-(sample, pixel chunk, group) partial sums, then the element pass.
+struct GnBwdChan {
+  float g[8], bt[8], xs[8], xo[8];       // gamma, beta, rstd_g, (add_c - mean_g) * rstd_g
+};
+__device__ __forceinline__ void gn_bwd_chan(GnBwdChan& ch, const float* __restrict__ stats, const float* __restrict__ addv,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta, int b, int v,
+                                            int C, int G, int cpg) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = v * 8 + j;
+    const int g = c / cpg;
+    const float mean = stats[(static_cast<size_t>(b) * G + g) * 2], rstd = stats[(static_cast<size_t>(b) * G + g) * 2 + 1];
+    const float a = addv != nullptr ? addv[static_cast<size_t>(b) * C + c] : 0.f;
+    ch.g[j] = __ldg(gamma + c);
+    ch.bt[j] = __ldg(beta + c);
+    ch.xs[j] = rstd;
+    ch.xo[j] = (a - mean) * rstd;
+  }
+}
+template <bool SILU>
+__device__ __forceinline__ float gn_dz(float dy, float z) {
+  if (!SILU) return dy;
+  const float sg = __fdividef(1.f, 1.f + __expf(-z));
+  return dy * sg * fmaf(z, 1.f - sg, 1.f);
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS_MAX)
+gn_bwd_stats_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ addv, const __nv_bfloat16* __restrict__ dy,
+                         const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* __restrict__ part, long long HW, int C, int G, int rows_per_cta, int k) {
+  extern __shared__ float gn_smem[];               // [2][k][C]
+  const int vecs = C >> 3;
+  const int v = threadIdx.x % vecs;
+  const int pl = threadIdx.x / vecs;
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  GnBwdChan ch;
+  gn_bwd_chan(ch, stats, addv, gamma, beta, b, v, C, G, cpg);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const long long p0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long p1 = p0 + rows_per_cta < HW ? p0 + rows_per_cta : HW;
+  const uint4* xv = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * HW * C);
+  const uint4* dv = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(b) * HW * C);
+  for (long long p = p0 + pl; p < p1; p += 2ll * k) {
+    uint4 rx[2], rd[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long pp = p + static_cast<long long>(u) * k;
+      if (pp < p1) {
+        rx[u] = __ldg(xv + pp * vecs + v);
+        rd[u] = __ldg(dv + pp * vecs + v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + static_cast<long long>(u) * k < p1) {
+        float f[8], d[8];
+        bf16x8_unpack(rx[u], f);
+        bf16x8_unpack(rd[u], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(f[j], ch.xs[j], ch.xo[j]);
+          const float t = gn_dz<SILU>(d[j], fmaf(xh, ch.g[j], ch.bt[j])) * ch.g[j];
+          s[j] += t;
+          q[j] = fmaf(t, xh, q[j]);
+        }
+      }
+    }
+  }
+  float* ss = gn_smem;
+  float* sq = gn_smem + k * C;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ss[pl * C + v * 8 + j] = s[j];
+    sq[pl * C + v * 8 + j] = q[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, d = 0.f;
+    for (int l = 0; l < k; ++l) {
+      a += ss[l * C + c];
+      d += sq[l * C + c];
+    }
+    ss[c] = a;
+    sq[c] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float a = 0.f, d = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += ss[c];
+      d += sq[c];
+    }
+    float* o = part + ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * G + g) * 2;
+    o[0] = a;
+    o[1] = d;
+  }
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS_MAX)
+gn_bwd_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ addv, const __nv_bfloat16* __restrict__ dy,
+                         const float* __restrict__ stats, const float* __restrict__ part, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ dx, long long HW, int C, int G,
+                         int stat_chunks, int rows_per_cta, int k) {
+  __shared__ float s_m1[GN_MAX_G], s_m2[GN_MAX_G];
+  const int vecs = C >> 3;
+  const int v = threadIdx.x % vecs;
+  const int pl = threadIdx.x / vecs;
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float a = 0.f, d = 0.f;
+    const float* pp = part + (static_cast<size_t>(b) * stat_chunks * G + g) * 2;
+    for (int c = 0; c < stat_chunks; ++c) {
+      a += pp[static_cast<size_t>(c) * G * 2];
+      d += pp[static_cast<size_t>(c) * G * 2 + 1];
+    }
+    const float n = static_cast<float>(HW) * static_cast<float>(cpg);
+    s_m1[g] = a / n;
+    s_m2[g] = d / n;
+  }
+  GnBwdChan ch;
+  gn_bwd_chan(ch, stats, addv, gamma, beta, b, v, C, G, cpg);
+  __syncthreads();
+  float m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (v * 8 + j) / cpg;
+    m1[j] = s_m1[g];
+    m2[j] = s_m2[g];
+  }
+  const long long p0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long p1 = p0 + rows_per_cta < HW ? p0 + rows_per_cta : HW;
+  const uint4* xv = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * HW * C);
+  const uint4* dv = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(b) * HW * C);
+  uint4* ov = reinterpret_cast<uint4*>(dx + static_cast<size_t>(b) * HW * C);
+  for (long long p = p0 + pl; p < p1; p += 2ll * k) {
+    uint4 rx[2], rd[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long pp = p + static_cast<long long>(u) * k;
+      if (pp < p1) {
+        rx[u] = __ldg(xv + pp * vecs + v);
+        rd[u] = __ldg(dv + pp * vecs + v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long pp = p + static_cast<long long>(u) * k;
+      if (pp < p1) {
+        float f[8], d[8];
+        bf16x8_unpack(rx[u], f);
+        bf16x8_unpack(rd[u], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(f[j], ch.xs[j], ch.xo[j]);
+          const float t = gn_dz<SILU>(d[j], fmaf(xh, ch.g[j], ch.bt[j])) * ch.g[j];
+          f[j] = ch.xs[j] * (t - m1[j] - xh * m2[j]);
+        }
+        ov[pp * vecs + v] = bf16x8_pack(f);
+      }
+    }
+  }
+}
+
+int group_norm_nhwc_bwd(const void* x, const float* add_bc, const void* dy, const float* stats, const float* gamma,
+                        const float* beta, void* dx, void* ws, long long B, long long HW, int C, int G, bool silu,
+                        cudaStream_t stream) {
+  PV_REQUIRE(group_norm_nhwc_ws_bytes(B, HW, C, G) >= 0,
+             "need C %% 8 == 0, C %% G == 0, G <= %d, C <= %d (B=%lld HW=%lld C=%d G=%d)", GN_MAX_G, 8 * GN_THREADS_MAX, B, HW, C, G);
+  PV_REQUIRE(B <= 65535, "batch too large for one launch (B=%lld)", B);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) % 16 == 0,
+             "x / dy / dx must be 16-byte aligned");
+  int k, chunks, rows;
+  gn_geometry(B, HW, C, &k, &chunks, &rows);
+  const int threads = (C / 8) * k;
+  const size_t smem = 2ull * k * C * sizeof(float);
+  const dim3 grid(chunks, static_cast<unsigned>(B));
+  const __nv_bfloat16* xx = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* dd = static_cast<const __nv_bfloat16*>(dy);
+  if (silu) {
+    gn_bwd_stats_nhwc_kernel<true><<<grid, threads, smem, stream>>>(xx, add_bc, dd, stats, gamma, beta, static_cast<float*>(ws), HW, C, G, rows, k);
+    PV_LAUNCHED();
+    gn_bwd_apply_nhwc_kernel<true><<<grid, threads, 0, stream>>>(xx, add_bc, dd, stats, static_cast<const float*>(ws), gamma, beta,
+                                                                 static_cast<__nv_bfloat16*>(dx), HW, C, G, chunks, rows, k);
+  } else {
+    gn_bwd_stats_nhwc_kernel<false><<<grid, threads, smem, stream>>>(xx, add_bc, dd, stats, gamma, beta, static_cast<float*>(ws), HW, C, G, rows, k);
+    PV_LAUNCHED();
+    gn_bwd_apply_nhwc_kernel<false><<<grid, threads, 0, stream>>>(xx, add_bc, dd, stats, static_cast<const float*>(ws), gamma, beta,
+                                                                  static_cast<__nv_bfloat16*>(dx), HW, C, G, chunks, rows, k);
+  }
   PV_LAUNCHED();
   return PV_OK;
 }

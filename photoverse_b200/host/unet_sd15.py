@@ -48,6 +48,28 @@ def _nhwc(x: torch.Tensor) -> bool:
             and not x.is_contiguous())
 
 
+class _GroupNormActFn(torch.autograd.Function):
+    """Training-time ``[silu](norm(x))`` on a channels-last activation with a FROZEN affine (the PhotoVerse training set is
+    adapters + to_k_ip / to_v_ip + LoRA factors, train.py:348-370): forward and input gradient are two launches each
+    (csrc/pv_backbone.cu) instead of the stock copy / moments / normalise / SiLU / copy chain and its backward; only x and
+    the per-(sample, group) statistics are kept."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, silu):
+        from .. import ops
+        y, stats = ops.group_norm_nhwc(x, gamma, beta, groups, eps, silu, None, save_stats=True)
+        ctx.save_for_backward(x, stats, gamma, beta)
+        ctx.cfg = (groups, silu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .. import ops
+        x, stats, gamma, beta = ctx.saved_tensors
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        return ops.group_norm_nhwc_bwd(x, dy, stats, gamma, beta, *ctx.cfg), None, None, None, None, None
+
+
 def group_norm_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool, add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``silu(norm(x + add[:, :, None, None]))`` / ``norm(...)`` -- one fused pass over a channels-last activation when the
     kernel applies (``add``: fp32 ``[B, C]``)."""
@@ -55,6 +77,10 @@ def group_norm_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool, add: Optiona
         from .. import ops
         gamma, beta = _f32_params(norm, "weight", "bias")
         return ops.group_norm_nhwc(x, gamma, beta, norm.num_groups, norm.eps, silu, add)
+    if (add is None and torch.is_grad_enabled() and FUSED_EPILOGUES and getattr(norm, "_pv_fused", True) and x.is_cuda
+            and x.dtype == torch.bfloat16 and _nhwc(x) and not (norm.weight.requires_grad or norm.bias.requires_grad)):
+        gamma, beta = _f32_params(norm, "weight", "bias")
+        return _GroupNormActFn.apply(x, gamma, beta, norm.num_groups, norm.eps, silu)
     if add is not None:
         x = x + add.to(x.dtype)[:, :, None, None]
     y = norm(x)

@@ -371,22 +371,26 @@ def self_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> 
 # ------------------------------------------------------------------------------------------------------------
 # epilogues of the UNet evaluation around the path (SURVEY 8 row f1; inference only)
 # ------------------------------------------------------------------------------------------------------------
-def group_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
-                    add: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[SiLU](GroupNorm(x + add) * gamma + beta) of a ``torch.channels_last`` bf16 activation ``[B, C, H, W]`` (also accepts
-    the equivalent dense ``[B, HW, C]``); gamma / beta fp32 ``[C]``; ``add``: optional fp32 ``[B, C]`` broadcast over the
-    pixels.  The result has the layout of ``x``."""
+def _gn_geometry(x: torch.Tensor, what: str):
     if not (x.is_cuda and x.dtype == torch.bfloat16):
-        raise _lib.PhotoverseB200Error("group_norm_nhwc: CUDA bfloat16 activations required (there is no CPU path)")
+        raise _lib.PhotoverseB200Error(f"{what}: CUDA bfloat16 activations required (there is no CPU path)")
     if x.dim() == 4:
         B, C, H, W = x.shape
-        HW = H * W
         if not x.is_contiguous(memory_format=torch.channels_last):
-            raise _lib.PhotoverseB200Error("group_norm_nhwc: the activation must be channels_last-contiguous")
-    else:
-        B, HW, C = x.shape
-        if not x.is_contiguous():
-            raise _lib.PhotoverseB200Error("group_norm_nhwc: [B, HW, C] input must be contiguous")
+            raise _lib.PhotoverseB200Error(f"{what}: the activation must be channels_last-contiguous")
+        return B, H * W, C
+    B, HW, C = x.shape
+    if not x.is_contiguous():
+        raise _lib.PhotoverseB200Error(f"{what}: [B, HW, C] input must be contiguous")
+    return B, HW, C
+
+
+def group_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+                    add: Optional[torch.Tensor] = None, save_stats: bool = False):
+    """[SiLU](GroupNorm(x + add) * gamma + beta) of a ``torch.channels_last`` bf16 activation ``[B, C, H, W]`` (also accepts
+    the equivalent dense ``[B, HW, C]``); gamma / beta fp32 ``[C]``; ``add``: optional fp32 ``[B, C]`` broadcast over the
+    pixels.  The result has the layout of ``x``.  ``save_stats``: also return the fp32 ``[B, groups, 2]`` (mean, rstd)."""
+    B, HW, C = _gn_geometry(x, "group_norm_nhwc")
     assert gamma.dtype == beta.dtype == torch.float32 and gamma.is_contiguous() and beta.is_contiguous() and gamma.numel() == C
     if add is not None:
         assert add.dtype == torch.float32 and add.is_contiguous() and add.shape == (B, C) and add.is_cuda
@@ -396,9 +400,25 @@ def group_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gr
         raise _lib.PhotoverseB200Error(f"group_norm_nhwc: unsupported shape B={B} HW={HW} C={C} groups={groups}")
     ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
     y = torch.empty_like(x)                     # preserve_format: channels_last stays channels_last
-    check(lib.pv_group_norm_nhwc_fwd(PV_BF16, _ptr(x), _ptr(add), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(ws), B, HW, C, groups,
-                                     float(eps), 1 if silu else 0, _stream()), "pv_group_norm_nhwc_fwd")
-    return y
+    stats = torch.empty(B, groups, 2, device=x.device, dtype=torch.float32) if save_stats else None
+    check(lib.pv_group_norm_nhwc_fwd(PV_BF16, _ptr(x), _ptr(add), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), _ptr(ws), B, HW, C,
+                                     groups, float(eps), 1 if silu else 0, _stream()), "pv_group_norm_nhwc_fwd")
+    return (y, stats) if save_stats else y
+
+
+def group_norm_nhwc_bwd(x: torch.Tensor, dy: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                        groups: int, silu: bool, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Input gradient of :func:`group_norm_nhwc` (frozen affine): ``dy`` in the layout of ``x``."""
+    B, HW, C = _gn_geometry(x, "group_norm_nhwc_bwd")
+    if dy.shape != x.shape or dy.dtype != x.dtype or dy.stride() != x.stride():
+        raise _lib.PhotoverseB200Error("group_norm_nhwc_bwd: dy must have the shape, dtype and memory layout of x")
+    assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.shape == (B, groups, 2)
+    lib = _lib.lib()
+    ws = torch.empty(int(lib.pv_group_norm_nhwc_ws_bytes(B, HW, C, groups)), device=x.device, dtype=torch.uint8)
+    dx = torch.empty_like(x)
+    check(lib.pv_group_norm_nhwc_bwd(PV_BF16, _ptr(x), _ptr(add), _ptr(dy), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(dx), _ptr(ws),
+                                     B, HW, C, groups, 1 if silu else 0, _stream()), "pv_group_norm_nhwc_bwd")
+    return dx
 
 
 def add_bias_nhwc(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:

@@ -39,6 +39,80 @@ def test_group_norm_nhwc_matches_torch(cuda_device, shape, silu, with_add):
     assert torch.equal(y, ops.group_norm_nhwc(x, gamma, beta, 32, eps, silu, add))
 
 
+BWD_SHAPES = [(2, 320, 64, 64), (2, 640, 32, 32), (1, 1920, 16, 16), (2, 2560, 8, 8), (3, 1280, 5, 7), (16, 320, 64, 64)]
+
+
+@pytest.mark.parametrize("shape", BWD_SHAPES, ids=[f"B{b}_C{c}_{h}x{w}" for b, c, h, w in BWD_SHAPES])
+@pytest.mark.parametrize("silu", [True, False], ids=["silu", "plain"])
+def test_group_norm_nhwc_backward_matches_autograd(cuda_device, shape, silu):
+    """Input gradient of the training-time GroupNorm (+ SiLU) against torch.autograd through the fp32 torch ops on the same
+    bf16 input and upstream gradient (the affine is frozen on the PhotoVerse path: no gamma / beta gradients)."""
+    from photoverse_b200 import ops
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(C + H + B)
+    x = (torch.randn(B, C, H, W, generator=g) * 0.8 + torch.randn(1, C, 1, 1, generator=g) * 2.0 + 1.0)
+    x = x.to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(B, C, H, W, generator=g).to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gamma = (1.0 + 0.3 * torch.randn(C, generator=g)).to(cuda_device)
+    beta = (0.2 * torch.randn(C, generator=g)).to(cuda_device)
+    y, stats = ops.group_norm_nhwc(x, gamma, beta, 32, 1e-5, silu, None, save_stats=True)
+    assert torch.equal(y, ops.group_norm_nhwc(x, gamma, beta, 32, 1e-5, silu))          # saving statistics changes nothing
+    dx = ops.group_norm_nhwc_bwd(x, dy, stats, gamma, beta, 32, silu)
+    assert dx.dtype == torch.bfloat16 and dx.is_contiguous(memory_format=torch.channels_last)
+    xr = x.float().requires_grad_(True)
+    ref = F.group_norm(xr, 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref.backward(dy.float())
+    err = (dx.float() - xr.grad).abs()
+    scale = xr.grad.abs().max().item()
+    assert err.max().item() <= 1e-2 * scale + 1e-2 * 0, f"max err {err.max().item():.3e} vs gradient scale {scale:.3e}"
+    rel = ((dx.float() - xr.grad).norm() / xr.grad.norm()).item()
+    assert rel <= 6e-3, rel
+    assert torch.equal(dx, ops.group_norm_nhwc_bwd(x, dy, stats, gamma, beta, 32, silu))      # fixed summation order
+    m = x.float().view(B, 32, C // 32, H * W).mean(dim=(2, 3))
+    assert torch.allclose(stats[..., 0], m, atol=2e-3, rtol=1e-3)
+
+
+def test_training_group_norm_function_in_the_unet(cuda_device):
+    """Grad mode, channels-last bf16 UNet: the GroupNorms run the fused forward / backward pair (launch count) and the
+    gradients that reach the trainable set agree with the stock ops."""
+    import photoverse_b200 as pv
+    from photoverse_b200 import _lib
+    from photoverse_b200.host.unet_sd15 import UNetSD15
+    torch.manual_seed(4)
+    unet = UNetSD15()
+    pv.set_visual_cross_attention_adapter(unet, num_tokens=(5,))
+    unet.requires_grad_(False).eval().to(device=cuda_device, dtype=torch.bfloat16).to(memory_format=torch.channels_last)
+    trainable = [p for n, p in unet.named_parameters() if "to_k_ip" in n or "to_v_ip" in n]
+    for p in trainable:
+        p.requires_grad_(True)
+    x = torch.randn(2, 4, 32, 32, device=cuda_device, dtype=torch.bfloat16)
+    text = torch.randn(2, 77, 768, device=cuda_device, dtype=torch.bfloat16)
+    img = torch.randn(2, 5, 768, device=cuda_device, dtype=torch.bfloat16)
+    t = torch.tensor([500], device=cuda_device)
+    target = torch.randn(2, 4, 32, 32, device=cuda_device, dtype=torch.bfloat16)
+
+    def grads(fused):
+        unet.set_fused_epilogues(fused)
+        for p in trainable:
+            p.grad = None
+        torch.manual_seed(11)                       # the fusion rule draws one random number per layer in grad mode
+        n0 = _lib.launch_count()
+        out = unet(x, t, (text, img)).sample
+        F.mse_loss(out.float(), target.float()).backward()
+        return torch.cat([p.grad.float().flatten() for p in trainable]), _lib.launch_count() - n0, out.detach()
+
+    g_stock, n_stock, o_stock = grads(False)
+    g_fused, n_fused, o_fused = grads(True)
+    # every GroupNorm downstream of the first trainable layer runs 2 + 2 launches, the ones upstream 2 (no backward)
+    assert n_fused > n_stock + 2 * 61 + 2 * 40, (n_stock, n_fused)
+    cos = F.cosine_similarity(g_stock.double(), g_fused.double(), dim=0).item()
+    print(f"training UNet, fused vs stock GroupNorm: gradient cosine {cos:.5f}, output cosine "
+          f"{F.cosine_similarity(o_stock.double().flatten(), o_fused.double().flatten(), dim=0).item():.6f}; native launches {n_stock} -> {n_fused}")
+    assert cos >= 0.99
+
+
 def test_group_norm_nhwc_rejects_what_it_cannot_do(cuda_device):
     from photoverse_b200 import _lib, ops
     x = torch.randn(2, 320, 8, 8, device=cuda_device, dtype=torch.bfloat16)

@@ -67,7 +67,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "launch__occupancy_limit_shared_mem",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active"]
-for what in ("attn", "gemm", "adapter", "bwd", "sattn"):
+for what in ("attn", "gemm", "adapter", "bwd", "sattn", "backbone"):
     rep = os.path.join(G, f"prof_{what}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue

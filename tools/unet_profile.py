@@ -1,6 +1,7 @@
 """Top GPU kernels of ONE UNet evaluation of the benchmarked configuration (batch 16 rows = uncond + cond of batch 8,
 latent 64, bf16, channels-last, fused epilogues on unless --stock-epilogues), by torch.profiler CUDA time.
-Usage: python tools/unet_profile.py [--stock-epilogues] [--top N]"""
+Usage: python tools/unet_profile.py [--stock-epilogues] [--top N] [--once]      (--once: two evaluations, no profiler: the
+target of an `ncu -k regex:...` capture)"""
 import os
 import sys
 
@@ -21,6 +22,12 @@ x = torch.randn(rows, 4, 64, 64, device=dev, dtype=dt)
 text = torch.randn(rows, 77, 768, device=dev, dtype=dt)
 img = torch.randn(rows, 1, 768, device=dev, dtype=dt)
 t = torch.tensor([500], device=dev)
+if "--once" in sys.argv:
+    with torch.no_grad():
+        unet(x, t, (text, img))
+        unet(x, t, (text, img))
+    torch.cuda.synchronize()
+    sys.exit(0)
 with torch.no_grad():
     for _ in range(3):
         unet(x, t, (text, img))
