@@ -409,6 +409,8 @@ def train_leg(args, rank, world, device, lora_rank, steps, warmup, lora_dropout=
             p.data = p.data.float()                       # fp32 masters for the trainable set
             p.requires_grad_(True)
     unet.eval()
+    if args.stock_epilogues:
+        unet.set_fused_epilogues(False)                       # A/B: stock GroupNorm / SiLU in the frozen backbone
     if lora_dropout > 0:
         pv.unet.set_cross_attention_layers_to_train(unet)     # train.py:462 (activates the LoRA dropout)
     tr = Trainer(unet, ia, ta, text_encoder=te)

@@ -27,9 +27,17 @@ from torch import nn
 FUSED_EPILOGUES = True
 
 
+def _enabled(mod: nn.Module, x: torch.Tensor) -> bool:
+    return FUSED_EPILOGUES and getattr(mod, "_pv_fused", True) and x.is_cuda and x.dtype == torch.bfloat16
+
+
 def _fused(mod: nn.Module, x: torch.Tensor) -> bool:
-    return (FUSED_EPILOGUES and getattr(mod, "_pv_fused", True) and x.is_cuda and x.dtype == torch.bfloat16
-            and not torch.is_grad_enabled())
+    """The inference-only kernels (LayerNorm, GEGLU) apply."""
+    return _enabled(mod, x) and not torch.is_grad_enabled()
+
+
+def _frozen(*tensors) -> bool:
+    return not any(t is not None and t.requires_grad for t in tensors)
 
 
 def _f32_params(mod: nn.Module, *names):
@@ -55,32 +63,45 @@ class _GroupNormActFn(torch.autograd.Function):
     the per-(sample, group) statistics are kept."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups, eps, silu):
+    def forward(ctx, x, add, gamma, beta, groups, eps, silu):
         from .. import ops
-        y, stats = ops.group_norm_nhwc(x, gamma, beta, groups, eps, silu, None, save_stats=True)
-        ctx.save_for_backward(x, stats, gamma, beta)
+        y, stats = ops.group_norm_nhwc(x, gamma, beta, groups, eps, silu, add, save_stats=True)
+        ctx.save_for_backward(x, stats, gamma, beta, *([] if add is None else [add]))
         ctx.cfg = (groups, silu)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         from .. import ops
-        x, stats, gamma, beta = ctx.saved_tensors
+        x, stats, gamma, beta, *rest = ctx.saved_tensors
         dy = dy.contiguous(memory_format=torch.channels_last)
-        return ops.group_norm_nhwc_bwd(x, dy, stats, gamma, beta, *ctx.cfg), None, None, None, None, None
+        dx = ops.group_norm_nhwc_bwd(x, dy, stats, gamma, beta, *ctx.cfg, add=rest[0] if rest else None)
+        return dx, None, None, None, None, None, None        # the addend (conv bias + temb of a frozen backbone) has no gradient
+
+
+class _AddBiasFn(torch.autograd.Function):
+    """``a + b + bias[c]`` (frozen bias) in one pass; the gradient of both operands is the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, a, b, bias):
+        from .. import ops
+        return ops.add_bias_nhwc(a, b, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy, None
 
 
 def group_norm_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool, add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``silu(norm(x + add[:, :, None, None]))`` / ``norm(...)`` -- one fused pass over a channels-last activation when the
     kernel applies (``add``: fp32 ``[B, C]``)."""
-    if _fused(norm, x) and _nhwc(x):
-        from .. import ops
+    if _enabled(norm, x) and _nhwc(x):
         gamma, beta = _f32_params(norm, "weight", "bias")
-        return ops.group_norm_nhwc(x, gamma, beta, norm.num_groups, norm.eps, silu, add)
-    if (add is None and torch.is_grad_enabled() and FUSED_EPILOGUES and getattr(norm, "_pv_fused", True) and x.is_cuda
-            and x.dtype == torch.bfloat16 and _nhwc(x) and not (norm.weight.requires_grad or norm.bias.requires_grad)):
-        gamma, beta = _f32_params(norm, "weight", "bias")
-        return _GroupNormActFn.apply(x, gamma, beta, norm.num_groups, norm.eps, silu)
+        if not torch.is_grad_enabled():
+            from .. import ops
+            return ops.group_norm_nhwc(x, gamma, beta, norm.num_groups, norm.eps, silu, add)
+        if _frozen(norm.weight, norm.bias, add):
+            return _GroupNormActFn.apply(x, add, gamma, beta, norm.num_groups, norm.eps, silu)
     if add is not None:
         x = x + add.to(x.dtype)[:, :, None, None]
     y = norm(x)
@@ -200,7 +221,7 @@ class Transformer2DModel(nn.Module):
     def forward(self, x, encoder_hidden_states):
         B, C, H, W = x.shape
         res = x
-        if _fused(self.norm, x) and _nhwc(x):
+        if _enabled(self.norm, x) and _nhwc(x):
             # channels-last: the 1x1 convolutions are Linears on the [B, HW, C] view (bias in the GEMM epilogue instead of a
             # broadcast-add launch), the residual sum runs on the same view
             h = group_norm_act(self.norm, x, False).permute(0, 2, 3, 1).reshape(B, H * W, C)
@@ -230,7 +251,10 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
-        if _fused(self.norm1, x) and _nhwc(x) and self.conv1.out_channels % 8 == 0:
+        if (_enabled(self.norm1, x) and _nhwc(x) and self.conv1.out_channels % 8 == 0
+                and (not torch.is_grad_enabled()
+                     or _frozen(temb, self.conv1.bias, self.conv2.bias, self.time_emb_proj.weight, self.time_emb_proj.bias,
+                                None if self.conv_shortcut is None else self.conv_shortcut.bias))):
             # the convolutions run bias-free; conv1's bias and the time-embedding projection enter norm2's two passes as a
             # per-(sample, channel) addend, conv2's (and the shortcut's) bias enters the residual sum: 2 launches instead
             # of 4 broadcast adds that each re-read and re-write the activation
@@ -242,6 +266,8 @@ class ResnetBlock2D(nn.Module):
             if cs is not None:
                 x = F.conv2d(x, cs.weight, None, cs.stride, cs.padding)
                 bias = self._shortcut_bias()
+            if torch.is_grad_enabled() and (x.requires_grad or h.requires_grad):
+                return _AddBiasFn.apply(x, h, bias)
             from .. import ops
             return ops.add_bias_nhwc(x, h, bias)
         h = self.conv1(group_norm_act(self.norm1, x, True))

@@ -101,12 +101,15 @@ def test_training_group_norm_function_in_the_unet(cuda_device):
         n0 = _lib.launch_count()
         out = unet(x, t, (text, img)).sample
         F.mse_loss(out.float(), target.float()).backward()
-        return torch.cat([p.grad.float().flatten() for p in trainable]), _lib.launch_count() - n0, out.detach()
+        # a branch the fusion rule dropped leaves its parameters without a gradient (same draw on both arms: same seed)
+        flat = [(p.grad if p.grad is not None else torch.zeros_like(p)).float().flatten() for p in trainable]
+        return torch.cat(flat), _lib.launch_count() - n0, out.detach()
 
+    grads(False)                                    # first call packs the processors' weights: keep it out of the counts
     g_stock, n_stock, o_stock = grads(False)
     g_fused, n_fused, o_fused = grads(True)
-    # every GroupNorm downstream of the first trainable layer runs 2 + 2 launches, the ones upstream 2 (no backward)
-    assert n_fused > n_stock + 2 * 61 + 2 * 40, (n_stock, n_fused)
+    # 61 GroupNorms x 2 launches forward, 2 more backward for those downstream of the first trainable layer, 22 residual sums
+    assert n_fused >= n_stock + 2 * 61 + 2 * 40 + 22, (n_stock, n_fused)
     cos = F.cosine_similarity(g_stock.double(), g_fused.double(), dim=0).item()
     print(f"training UNet, fused vs stock GroupNorm: gradient cosine {cos:.5f}, output cosine "
           f"{F.cosine_similarity(o_stock.double().flatten(), o_fused.double().flatten(), dim=0).item():.6f}; native launches {n_stock} -> {n_fused}")
