@@ -87,6 +87,8 @@ int group_norm_nhwc_bwd(const void* x, const float* add_bc, const void* dy, cons
 int add_bias_nhwc(const void* a, const void* b, const float* bias, void* out, long long rows, int C, cudaStream_t stream);
 int layer_norm_bf16(const void* x, const float* gamma, const float* beta, void* y, long long rows, int C, float eps,
                     cudaStream_t stream);
+int layer_norm_bwd_bf16(const void* x, const void* dy, const float* gamma, void* dx, long long rows, int C, float eps,
+                        cudaStream_t stream);
 int geglu(const void* h, void* y, long long M, int N, long long ldh, cudaStream_t stream);
 int dropout_bwd_acc(bool bf16, void* dst, const void* src, const uint8_t* mask, float alpha, long long n,
                     cudaStream_t stream);
@@ -540,6 +542,13 @@ int pv_layer_norm_fwd(pv_dtype dt, const void* x, const float* gamma, const floa
   PV_REQUIRE(x && gamma && beta && y, "null pointer");
   PV_REQUIRE(dt == PV_BF16, "bf16 activations only");
   return layer_norm_bf16(x, gamma, beta, y, rows, C, eps, as_stream(stream));
+}
+
+int pv_layer_norm_bwd(pv_dtype dt, const void* x, const void* dy, const float* gamma, void* dx, int64_t rows, int C, float eps,
+                      void* stream) {
+  PV_REQUIRE(x && dy && gamma && dx, "null pointer");
+  PV_REQUIRE(dt == PV_BF16, "bf16 activations only");
+  return layer_norm_bwd_bf16(x, dy, gamma, dx, rows, C, eps, as_stream(stream));
 }
 
 int pv_geglu_fwd(pv_dtype dt, const void* h, void* y, int64_t M, int N, int64_t ldh, void* stream) {

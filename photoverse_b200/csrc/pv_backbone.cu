@@ -561,6 +561,104 @@ int layer_norm_bf16(const void* x, const float* gamma, const float* beta, void* 
   return PV_OK;
 }
 
+// Input gradient of the LayerNorm above (frozen affine): dx = rstd * (dy * gamma - mean(dy * gamma) - xh * mean(dy * gamma * xh)).
+// One warp per row with x and dy in registers; mean / rstd are recomputed from the row (nothing but x is kept by the
+// forward pass).
+template <int NV>
+__global__ void __launch_bounds__(256)
+layer_norm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ gamma,
+                           __nv_bfloat16* __restrict__ dx, long long rows, int C, float eps) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int vecs = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  const uint4* dr = reinterpret_cast<const uint4*>(dy + row * C);
+  float f[NV][8], t[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = i * 32 + lane;
+    if (idx < vecs) {
+      bf16x8_unpack(__ldg(xr + idx), f[i]);
+      bf16x8_unpack(__ldg(dr + idx), t[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i * 32 + lane < vecs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        ss = fmaf(d, d, ss);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / static_cast<float>(C) + eps);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = i * 32 + lane;
+    if (idx < vecs) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[i][j] = (f[i][j] - mean) * rstd;          // xh
+        t[i][j] *= gg[j];                           // dy * gamma
+        s1 += t[i][j];
+        s2 = fmaf(t[i][j], f[i][j], s2);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float m1 = s1 / static_cast<float>(C), m2 = s2 / static_cast<float>(C);
+  uint4* outr = reinterpret_cast<uint4*>(dx + row * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = i * 32 + lane;
+    if (idx < vecs) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (t[i][j] - m1 - f[i][j] * m2);
+      outr[idx] = bf16x8_pack(o);
+    }
+  }
+}
+
+int layer_norm_bwd_bf16(const void* x, const void* dy, const float* gamma, void* dx, long long rows, int C, float eps,
+                        cudaStream_t stream) {
+  PV_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 8 * 32 * 5, "need C %% 8 == 0 and C <= 1280 (rows=%lld C=%d)", rows, C);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+              reinterpret_cast<uintptr_t>(gamma)) % 16 == 0, "pointers must be 16-byte aligned");
+  const int nv = (C / 8 + 31) / 32;
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  const __nv_bfloat16* xx = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* dd = static_cast<const __nv_bfloat16*>(dy);
+  __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(dx);
+  switch (nv) {
+    case 1: layer_norm_bwd_bf16_kernel<1><<<blocks, 256, 0, stream>>>(xx, dd, gamma, oo, rows, C, eps); break;
+    case 2: layer_norm_bwd_bf16_kernel<2><<<blocks, 256, 0, stream>>>(xx, dd, gamma, oo, rows, C, eps); break;
+    case 3: layer_norm_bwd_bf16_kernel<3><<<blocks, 256, 0, stream>>>(xx, dd, gamma, oo, rows, C, eps); break;
+    case 4: layer_norm_bwd_bf16_kernel<4><<<blocks, 256, 0, stream>>>(xx, dd, gamma, oo, rows, C, eps); break;
+    default: layer_norm_bwd_bf16_kernel<5><<<blocks, 256, 0, stream>>>(xx, dd, gamma, oo, rows, C, eps); break;
+  }
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
 // y[m, n] = h[m, n] * gelu(h[m, N + n]);  h: [M, 2N] (row stride ldh), y: [M, N] dense; N % 8 == 0.
 __global__ void __launch_bounds__(256)
 geglu_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ y, long long M, int N, long long ldh) {

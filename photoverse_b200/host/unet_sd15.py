@@ -108,11 +108,31 @@ def group_norm_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool, add: Optiona
     return F.silu(y) if silu else y
 
 
-def layer_norm(norm: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
-    if _fused(norm, x) and x.is_contiguous() and x.shape[-1] % 8 == 0 and x.shape[-1] <= 1280:
+class _LayerNormFn(torch.autograd.Function):
+    """Training-time LayerNorm with a frozen affine: one launch forward, one for the input gradient; only x is kept."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
         from .. import ops
+        ctx.save_for_backward(x, gamma)
+        ctx.eps = eps
+        return ops.layer_norm(x, gamma, beta, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .. import ops
+        x, gamma = ctx.saved_tensors
+        return ops.layer_norm_bwd(x, dy.contiguous(), gamma, ctx.eps), None, None, None
+
+
+def layer_norm(norm: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    if _enabled(norm, x) and x.is_contiguous() and x.shape[-1] % 8 == 0 and x.shape[-1] <= 1280:
         gamma, beta = _f32_params(norm, "weight", "bias")
-        return ops.layer_norm(x, gamma, beta, norm.eps)
+        if not torch.is_grad_enabled():
+            from .. import ops
+            return ops.layer_norm(x, gamma, beta, norm.eps)
+        if _frozen(norm.weight, norm.bias):
+            return _LayerNormFn.apply(x, gamma, beta, norm.eps)
     return norm(x)
 
 

@@ -453,6 +453,19 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     return y
 
 
+def layer_norm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:
+    """Input gradient of :func:`layer_norm` (frozen affine) from the contiguous bf16 ``x`` and ``dy``."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and dy.dtype == x.dtype and dy.is_contiguous()
+            and dy.shape == x.shape):
+        raise _lib.PhotoverseB200Error("layer_norm_bwd: contiguous CUDA bfloat16 x and dy of one shape required")
+    C = x.shape[-1]
+    assert gamma.dtype == torch.float32 and gamma.is_contiguous() and gamma.numel() == C
+    dx = torch.empty_like(x)
+    check(_lib.lib().pv_layer_norm_bwd(PV_BF16, _ptr(x), _ptr(dy), _ptr(gamma), _ptr(dx), x.numel() // C, C, float(eps), _stream()),
+          "pv_layer_norm_bwd")
+    return dx
+
+
 def geglu(h: torch.Tensor) -> torch.Tensor:
     """``h[..., :N] * gelu(h[..., N:])`` (exact GELU) of a bf16 projection ``[..., 2N]`` with contiguous rows."""
     if not (h.is_cuda and h.dtype == torch.bfloat16 and h.is_contiguous()):

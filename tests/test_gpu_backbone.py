@@ -108,8 +108,9 @@ def test_training_group_norm_function_in_the_unet(cuda_device):
     grads(False)                                    # first call packs the processors' weights: keep it out of the counts
     g_stock, n_stock, o_stock = grads(False)
     g_fused, n_fused, o_fused = grads(True)
-    # 61 GroupNorms x 2 launches forward, 2 more backward for those downstream of the first trainable layer, 22 residual sums
-    assert n_fused >= n_stock + 2 * 61 + 2 * 40 + 22, (n_stock, n_fused)
+    # 61 GroupNorms x 2 launches forward, 2 more backward for those downstream of the first trainable layer, 22 residual
+    # sums, 48 LayerNorms forward + backward
+    assert n_fused >= n_stock + 2 * 61 + 2 * 40 + 22 + 48 + 40, (n_stock, n_fused)
     cos = F.cosine_similarity(g_stock.double(), g_fused.double(), dim=0).item()
     print(f"training UNet, fused vs stock GroupNorm: gradient cosine {cos:.5f}, output cosine "
           f"{F.cosine_similarity(o_stock.double().flatten(), o_fused.double().flatten(), dim=0).item():.6f}; native launches {n_stock} -> {n_fused}")
@@ -158,6 +159,22 @@ def test_layer_norm_matches_torch(cuda_device, rows, C):
     assert (y.float() - ref).abs().max() <= (stock.float() - ref).abs().max() + 1e-2     # no worse than the op it replaces
 
 
+@pytest.mark.parametrize("rows,C", [(16 * 4096, 320), (16 * 1024, 640), (4096, 1280), (5, 328), (3, 8)])
+def test_layer_norm_backward_matches_autograd(cuda_device, rows, C):
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(rows * 3 + C)
+    x = (torch.randn(rows, C, generator=g) * 2.0 + torch.randn(rows, 1, generator=g) * 3.0).to(cuda_device, torch.bfloat16)
+    dy = torch.randn(rows, C, generator=g).to(cuda_device, torch.bfloat16)
+    gamma = (1.0 + 0.3 * torch.randn(C, generator=g)).to(cuda_device)
+    beta = (0.2 * torch.randn(C, generator=g)).to(cuda_device)
+    dx = ops.layer_norm_bwd(x, dy, gamma, 1e-5)
+    xr = x.float().requires_grad_(True)
+    F.layer_norm(xr, (C,), gamma, beta, 1e-5).backward(dy.float())
+    rel = ((dx.float() - xr.grad).norm() / xr.grad.norm()).item()
+    assert dx.dtype == torch.bfloat16 and rel <= 5e-3, rel
+    assert (dx.float() - xr.grad).abs().max().item() <= 1e-2 * xr.grad.abs().max().item() + 1e-3
+
+
 @pytest.mark.parametrize("shape", [(16, 320, 64, 64), (2, 1280, 8, 8), (3, 640, 5, 7)])
 def test_add_bias_nhwc_matches_torch(cuda_device, shape):
     from photoverse_b200 import ops
@@ -204,13 +221,17 @@ def test_unet_with_fused_epilogues_matches_stock(cuda_device):
     rel = ((stock.float() - fused.float()).norm() / stock.float().norm()).item()
     print(f"UNet eval, fused vs stock epilogues: cosine {cos:.6f} relative L2 {rel:.4e}; native launches {n_stock} -> {n_fused}")
     assert cos >= 0.9995 and rel <= 3e-2
-    # with autograd on (training) the stock ops run: the kernels are inference-only
+    # autograd on: a frozen norm runs the training pair (forward keeps the statistics), a trainable one the stock op
     from photoverse_b200.host.unet_sd15 import group_norm_act
     norm = unet.conv_norm_out
     h = torch.randn(2, 320, 8, 8, device=cuda_device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     n0 = _lib.launch_count()
-    group_norm_act(norm, h, True)
-    assert _lib.launch_count() == n0
-    with torch.no_grad():
-        group_norm_act(norm, h, True)
+    y_train = group_norm_act(norm, h, True)
     assert _lib.launch_count() == n0 + 2
+    with torch.no_grad():
+        y_inf = group_norm_act(norm, h, True)
+    assert _lib.launch_count() == n0 + 4 and torch.equal(y_train, y_inf)
+    norm.weight.requires_grad_(True)
+    group_norm_act(norm, h, True)
+    assert _lib.launch_count() == n0 + 4
+    norm.weight.requires_grad_(False)
