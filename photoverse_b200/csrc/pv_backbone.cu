@@ -196,18 +196,19 @@ gn_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
   }
 }
 
+// Launch geometry from (HW, C) alone -- not from the batch or the device -- so that a sample's statistics are summed in the
+// same order whatever batch it is generated in (generation shards by sample across GPUs and must not depend on the
+// shard size): one CTA per ~32 KB of a sample's activation.
 static void gn_geometry(long long B, long long HW, int C, int* k, int* chunks, int* rows_per_cta) {
+  (void)B;
   const int vecs = C / 8;
   int kk = GN_THREADS_MAX / vecs;
   if (kk < 1) kk = 1;
   if (kk > 16) kk = 16;
   if (kk > HW) kk = static_cast<int>(HW);
-  long long want = (4ll * sm_count() + B - 1) / B;             // ~4 CTAs per SM over the whole launch
-  long long maxc = (HW + kk - 1) / kk;
-  if (want > maxc) want = maxc;
-  if (want < 1) want = 1;
-  long long rows = (HW + want - 1) / want;
+  long long rows = (32768 + 2ll * C - 1) / (2ll * C);
   rows = (rows + kk - 1) / kk * kk;
+  if (rows > HW) rows = (HW + kk - 1) / kk * kk;
   *k = kk;
   *rows_per_cta = static_cast<int>(rows);
   *chunks = static_cast<int>((HW + rows - 1) / rows);

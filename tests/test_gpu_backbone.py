@@ -35,8 +35,13 @@ def test_group_norm_nhwc_matches_torch(cuda_device, shape, silu, with_add):
     err = (y.float() - ref).abs()
     tol = 1e-2 + 1e-2 * ref.abs()                              # bf16 output: 2^-8 relative + the affine cancellation
     assert bool((err <= tol).all()), f"max err {err.max().item():.4e} at |ref| {ref.abs().flatten()[err.argmax()].item():.3f}"
-    # bit-reproducible (fixed summation order)
+    # bit-reproducible (fixed summation order) ...
     assert torch.equal(y, ops.group_norm_nhwc(x, gamma, beta, 32, eps, silu, add))
+    # ... and a sample's result does not depend on the batch it is normalised in (generation shards by sample)
+    if B > 1:
+        y1 = ops.group_norm_nhwc(x[1:2].contiguous(memory_format=torch.channels_last), gamma, beta, 32, eps, silu,
+                                 None if add is None else add[1:2].contiguous())
+        assert torch.equal(y1[0], y[1])
 
 
 BWD_SHAPES = [(2, 320, 64, 64), (2, 640, 32, 32), (1, 1920, 16, 16), (2, 2560, 8, 8), (3, 1280, 5, 7), (16, 320, 64, 64)]
