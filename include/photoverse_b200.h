@@ -249,8 +249,10 @@ int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* k
  * only), so no affine gradients are produced.  Same workspace size, two launches.
  * pv_add_bias_nhwc_fwd: out[r, c] = a[r, c] + b[r, c] + bias[c] (rows x C dense, bias fp32, C % 8 == 0; out may alias a
  * or b) -- a block's residual sum together with the bias of its last convolution.
- * pv_layer_norm_fwd: y = LayerNorm(x) * gamma + beta over the last dimension of x [rows, C] dense, C % 8 == 0, C <= 1280,
- * gamma / beta fp32 (BasicTransformerBlock norm1 / norm2 / norm3).  pv_layer_norm_bwd: its input gradient from dy and x
+ * pv_layer_norm_fwd: y = LayerNorm(s) * gamma + beta over the last dimension, s = x [rows, C] dense, C % 8 == 0, C <= 1280,
+ * gamma / beta fp32 (BasicTransformerBlock norm1 / norm2 / norm3).  With `residual` (and `sum_out`, both or neither):
+ * s = x + residual, rounded to bf16 and written to sum_out -- the block's `x = attn(...) + x` in the pass of the norm
+ * that follows it.  pv_layer_norm_bwd: its input gradient from dy and x
  * (frozen affine; mean / rstd are recomputed from the row).
  * pv_geglu_fwd: y[m, n] = h[m, n] * gelu(h[m, N + n]) with the exact (erf) GELU, gelu(.) rounded to bf16 before the
  * product like the two-kernel torch sequence; h: [M, 2N] with row stride ldh (elements), y: [M, N] dense; N % 8 == 0. */
@@ -263,8 +265,8 @@ int pv_group_norm_nhwc_bwd(pv_dtype dt, const void* x, const float* add_bc, cons
                            int silu, void* stream);
 int pv_add_bias_nhwc_fwd(pv_dtype dt, const void* a, const void* b, const float* bias, void* out, int64_t rows, int C,
                          void* stream);
-int pv_layer_norm_fwd(pv_dtype dt, const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C,
-                      float eps, void* stream);
+int pv_layer_norm_fwd(pv_dtype dt, const void* x, const void* residual, void* sum_out, const float* gamma, const float* beta,
+                      void* y, int64_t rows, int C, float eps, void* stream);
 int pv_layer_norm_bwd(pv_dtype dt, const void* x, const void* dy, const float* gamma, void* dx, int64_t rows, int C, float eps,
                       void* stream);
 int pv_geglu_fwd(pv_dtype dt, const void* h, void* y, int64_t M, int N, int64_t ldh, void* stream);

@@ -64,7 +64,7 @@ _SIGNATURES = {
     "pv_group_norm_nhwc_fwd": (c_int, [c_int] + [c_void_p] * 7 + [c_int64, c_int64, c_int, c_int, c_float, c_int, c_void_p]),
     "pv_group_norm_nhwc_bwd": (c_int, [c_int] + [c_void_p] * 8 + [c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "pv_add_bias_nhwc_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
-    "pv_layer_norm_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "pv_layer_norm_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "pv_layer_norm_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "pv_geglu_fwd": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p]),
 }

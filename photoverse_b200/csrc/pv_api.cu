@@ -85,8 +85,8 @@ int group_norm_nhwc_bwd(const void* x, const float* add_bc, const void* dy, cons
                         const float* beta, void* dx, void* ws, long long B, long long HW, int C, int G, bool silu,
                         cudaStream_t stream);
 int add_bias_nhwc(const void* a, const void* b, const float* bias, void* out, long long rows, int C, cudaStream_t stream);
-int layer_norm_bf16(const void* x, const float* gamma, const float* beta, void* y, long long rows, int C, float eps,
-                    cudaStream_t stream);
+int layer_norm_bf16(const void* x, const void* res, void* sum_out, const float* gamma, const float* beta, void* y, long long rows,
+                    int C, float eps, cudaStream_t stream);
 int layer_norm_bwd_bf16(const void* x, const void* dy, const float* gamma, void* dx, long long rows, int C, float eps,
                         cudaStream_t stream);
 int geglu(const void* h, void* y, long long M, int N, long long ldh, cudaStream_t stream);
@@ -537,11 +537,11 @@ int pv_add_bias_nhwc_fwd(pv_dtype dt, const void* a, const void* b, const float*
   return add_bias_nhwc(a, b, bias, out, rows, C, as_stream(stream));
 }
 
-int pv_layer_norm_fwd(pv_dtype dt, const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C,
-                      float eps, void* stream) {
+int pv_layer_norm_fwd(pv_dtype dt, const void* x, const void* residual, void* sum_out, const float* gamma, const float* beta,
+                      void* y, int64_t rows, int C, float eps, void* stream) {
   PV_REQUIRE(x && gamma && beta && y, "null pointer");
   PV_REQUIRE(dt == PV_BF16, "bf16 activations only");
-  return layer_norm_bf16(x, gamma, beta, y, rows, C, eps, as_stream(stream));
+  return layer_norm_bf16(x, residual, sum_out, gamma, beta, y, rows, C, eps, as_stream(stream));
 }
 
 int pv_layer_norm_bwd(pv_dtype dt, const void* x, const void* dy, const float* gamma, void* dx, int64_t rows, int C, float eps,

@@ -198,7 +198,7 @@ gn_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
 
 // Launch geometry from (HW, C) alone -- not from the batch or the device -- so that a sample's statistics are summed in the
 // same order whatever batch it is generated in (generation shards by sample across GPUs and must not depend on the
-// shard size): one CTA per ~32 KB of a sample's activation.
+// shard size): one CTA per ~64 KB of a sample's activation (32 KB: 35 % slower at the 64 x 64 maps).
 static void gn_geometry(long long B, long long HW, int C, int* k, int* chunks, int* rows_per_cta) {
   (void)B;
   const int vecs = C / 8;
@@ -206,7 +206,7 @@ static void gn_geometry(long long B, long long HW, int C, int* k, int* chunks, i
   if (kk < 1) kk = 1;
   if (kk > 16) kk = 16;
   if (kk > HW) kk = static_cast<int>(HW);
-  long long rows = (32768 + 2ll * C - 1) / (2ll * C);
+  long long rows = (65536 + 2ll * C - 1) / (2ll * C);
   rows = (rows + kk - 1) / kk * kk;
   if (rows > HW) rows = (HW + kk - 1) / kk * kk;
   *k = kk;
@@ -488,9 +488,12 @@ int add_bias_nhwc(const void* a, const void* b, const float* bias, void* out, lo
 
 // LayerNorm over the last dimension, bf16 in / out, fp32 affine: one warp per row, the row held in registers (NV 16-byte
 // vectors per lane), mean and variance as two passes over the registers.
+// res != nullptr: the residual sum that precedes the norm rides along -- s = x + res is written to `sum_out` (rounded to
+// bf16 like the stand-alone add) and the norm is taken of the rounded sum (BasicTransformerBlock: x = attn(..) + x; norm(x)).
 template <int NV>
 __global__ void __launch_bounds__(256)
-layer_norm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+layer_norm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                       __nv_bfloat16* __restrict__ sum_out, const float* __restrict__ gamma, const float* __restrict__ beta,
                        __nv_bfloat16* __restrict__ y, long long rows, int C, float eps) {
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -504,6 +507,15 @@ layer_norm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
     const int idx = i * 32 + lane;
     if (idx < vecs) {
       bf16x8_unpack(__ldg(xr + idx), f[i]);
+      if (res != nullptr) {
+        float r[8];
+        bf16x8_unpack(__ldg(reinterpret_cast<const uint4*>(res + row * C) + idx), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[i][j] += r[j];
+        const uint4 packed = bf16x8_pack(f[i]);
+        reinterpret_cast<uint4*>(sum_out + row * C)[idx] = packed;
+        bf16x8_unpack(packed, f[i]);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += f[i][j];
     }
@@ -542,21 +554,25 @@ layer_norm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
   }
 }
 
-int layer_norm_bf16(const void* x, const float* gamma, const float* beta, void* y, long long rows, int C, float eps,
-                    cudaStream_t stream) {
+int layer_norm_bf16(const void* x, const void* res, void* sum_out, const float* gamma, const float* beta, void* y, long long rows,
+                    int C, float eps, cudaStream_t stream) {
   PV_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 8 * 32 * 5, "need C %% 8 == 0 and C <= 1280 (rows=%lld C=%d)", rows, C);
+  PV_REQUIRE((res == nullptr) == (sum_out == nullptr), "res and sum_out go together");
   PV_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
-              reinterpret_cast<uintptr_t>(beta)) % 16 == 0, "pointers must be 16-byte aligned");
+              reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(sum_out)) % 16 == 0,
+             "pointers must be 16-byte aligned");
   const int nv = (C / 8 + 31) / 32;
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
   const __nv_bfloat16* xx = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* rr = static_cast<const __nv_bfloat16*>(res);
+  __nv_bfloat16* so = static_cast<__nv_bfloat16*>(sum_out);
   __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
   switch (nv) {
-    case 1: layer_norm_bf16_kernel<1><<<blocks, 256, 0, stream>>>(xx, gamma, beta, yy, rows, C, eps); break;
-    case 2: layer_norm_bf16_kernel<2><<<blocks, 256, 0, stream>>>(xx, gamma, beta, yy, rows, C, eps); break;
-    case 3: layer_norm_bf16_kernel<3><<<blocks, 256, 0, stream>>>(xx, gamma, beta, yy, rows, C, eps); break;
-    case 4: layer_norm_bf16_kernel<4><<<blocks, 256, 0, stream>>>(xx, gamma, beta, yy, rows, C, eps); break;
-    default: layer_norm_bf16_kernel<5><<<blocks, 256, 0, stream>>>(xx, gamma, beta, yy, rows, C, eps); break;
+    case 1: layer_norm_bf16_kernel<1><<<blocks, 256, 0, stream>>>(xx, rr, so, gamma, beta, yy, rows, C, eps); break;
+    case 2: layer_norm_bf16_kernel<2><<<blocks, 256, 0, stream>>>(xx, rr, so, gamma, beta, yy, rows, C, eps); break;
+    case 3: layer_norm_bf16_kernel<3><<<blocks, 256, 0, stream>>>(xx, rr, so, gamma, beta, yy, rows, C, eps); break;
+    case 4: layer_norm_bf16_kernel<4><<<blocks, 256, 0, stream>>>(xx, rr, so, gamma, beta, yy, rows, C, eps); break;
+    default: layer_norm_bf16_kernel<5><<<blocks, 256, 0, stream>>>(xx, rr, so, gamma, beta, yy, rows, C, eps); break;
   }
   PV_LAUNCHED();
   return PV_OK;

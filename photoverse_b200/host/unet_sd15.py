@@ -225,6 +225,15 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x, encoder_hidden_states):
+        if (_fused(self.norm2, x) and _fused(self.norm3, x) and x.is_contiguous() and x.shape[-1] % 8 == 0
+                and x.shape[-1] <= 1280):
+            # inference: each residual sum rides in the pass of the LayerNorm that follows it
+            from .. import ops
+            h = self.attn1(layer_norm(self.norm1, x))
+            x, n = ops.add_layer_norm(h.contiguous(), x, *_f32_params(self.norm2, "weight", "bias"), self.norm2.eps)
+            h = self.attn2(n, encoder_hidden_states=encoder_hidden_states)
+            x, n = ops.add_layer_norm(h.contiguous(), x, *_f32_params(self.norm3, "weight", "bias"), self.norm3.eps)
+            return self.ff(n) + x
         x = self.attn1(layer_norm(self.norm1, x)) + x
         x = self.attn2(layer_norm(self.norm2, x), encoder_hidden_states=encoder_hidden_states) + x
         return self.ff(layer_norm(self.norm3, x)) + x

@@ -448,9 +448,22 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     C = x.shape[-1]
     assert gamma.dtype == beta.dtype == torch.float32 and gamma.is_contiguous() and beta.is_contiguous() and gamma.numel() == C
     y = torch.empty_like(x)
-    check(_lib.lib().pv_layer_norm_fwd(PV_BF16, _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // C, C, float(eps), _stream()),
-          "pv_layer_norm_fwd")
+    check(_lib.lib().pv_layer_norm_fwd(PV_BF16, _ptr(x), None, None, _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // C, C, float(eps),
+                                       _stream()), "pv_layer_norm_fwd")
     return y
+
+
+def add_layer_norm(x: torch.Tensor, residual: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
+    """``s = x + residual`` (bf16) and ``LayerNorm(s)`` in one pass; returns ``(s, y)``."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and residual.dtype == x.dtype
+            and residual.is_contiguous() and residual.shape == x.shape):
+        raise _lib.PhotoverseB200Error("add_layer_norm: two contiguous CUDA bfloat16 tensors of one shape required")
+    C = x.shape[-1]
+    assert gamma.dtype == beta.dtype == torch.float32 and gamma.is_contiguous() and beta.is_contiguous() and gamma.numel() == C
+    s, y = torch.empty_like(x), torch.empty_like(x)
+    check(_lib.lib().pv_layer_norm_fwd(PV_BF16, _ptr(x), _ptr(residual), _ptr(s), _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // C, C,
+                                       float(eps), _stream()), "pv_layer_norm_fwd")
+    return s, y
 
 
 def layer_norm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:

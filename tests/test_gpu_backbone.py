@@ -162,6 +162,10 @@ def test_layer_norm_matches_torch(cuda_device, rows, C):
     assert y.dtype == torch.bfloat16 and bool((err <= 1e-2 + 1e-2 * ref.abs()).all()), err.max().item()
     stock = F.layer_norm(x, (C,), gamma.to(torch.bfloat16), beta.to(torch.bfloat16), 1e-5)
     assert (y.float() - ref).abs().max() <= (stock.float() - ref).abs().max() + 1e-2     # no worse than the op it replaces
+    # residual sum in the same pass: the sum is the bf16 sum, the norm is the norm of that sum (bit for bit)
+    r = torch.randn(rows, C, generator=g).to(cuda_device, torch.bfloat16)
+    s2, y2 = ops.add_layer_norm(x, r, gamma, beta, 1e-5)
+    assert torch.equal(s2, x + r) and torch.equal(y2, ops.layer_norm(x + r, gamma, beta, 1e-5))
 
 
 @pytest.mark.parametrize("rows,C", [(16 * 4096, 320), (16 * 1024, 640), (4096, 1280), (5, 328), (3, 8)])
@@ -220,7 +224,7 @@ def test_unet_with_fused_epilogues_matches_stock(cuda_device):
         n0 = _lib.launch_count()
         fused = unet(x, t, (text, img)).sample
         n_fused = _lib.launch_count() - n0
-    # 61 GroupNorms x 2 launches + 16 GEGLUs + 48 LayerNorms + 22 residual sums
+    # 61 GroupNorms x 2 launches + 16 GEGLUs + 48 LayerNorms (32 of them with the residual sum) + 22 resnet residual sums
     assert n_fused == n_stock + 2 * 61 + 16 + 48 + 22, (n_stock, n_fused)
     cos = F.cosine_similarity(stock.double().flatten(1), fused.double().flatten(1), dim=1).min().item()
     rel = ((stock.float() - fused.float()).norm() / stock.float().norm()).item()
