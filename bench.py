@@ -220,13 +220,16 @@ def _graph_time_us(fn, nbuf, reps=20):
         for i in range(reps):
             fn(i % nbuf)
     gr.replay()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    gr.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / reps
+    times = []
+    for _ in range(3):                     # median of three replays: one replay is ~0.5 ms, short against a power-cap dip
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e3 / reps)
+    return sorted(times)[1]
 
 
 def roofline_leg(device, rows_b, Li, scale):
@@ -311,7 +314,7 @@ def roofline_leg(device, rows_b, Li, scale):
             "achieved": round(ach, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": round(ach / peaks["bf16_tflops"], 4), "peak_source": peaks["source"] + " cuBLAS bf16 burst",
             "traffic": traffic, "traffic_unit": "bytes per launch, S4096_C320 layer", "traffic_source": traffic_src,
-            "how": f"CUDA events around a CUDA graph of 20 launches per attn2 layer shape at {rows_b} rows (uncond+cond), "
+            "how": f"CUDA events around a CUDA graph of 20 launches per attn2 layer shape at {rows_b} rows (uncond+cond), median of 3 replays, "
                    f"inputs rotated through > L2 of buffers; aggregated over the 16 layers of one UNet evaluation; "
                    f"algorithmic FLOPs = 2 rows C^2 + 4 rows C (77 + Li) per launch (processor: 4 rows C^2 + ...); "
                    f"proc_us = whole processor call with the library's default launch policy (one launch for C <= 320, "
