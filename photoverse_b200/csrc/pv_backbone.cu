@@ -113,8 +113,7 @@ gn_stats_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     sq[c] = d;                                     // reads column c of every lane and writes column c of lane 0
   }
   __syncthreads();
-  if (threadIdx.x < G) {
-    const int g = threadIdx.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {       // (blocks of a tiny activation can be narrower than G)
     float a = 0.f, d = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
       a += ss[c];
@@ -139,8 +138,7 @@ gn_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
   const int b = blockIdx.y;
   const int cpg = C / G;
   const __nv_bfloat16* xb = x + static_cast<size_t>(b) * HW * C;
-  if (threadIdx.x < G) {
-    const int g = threadIdx.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {       // (blocks of a tiny activation can be narrower than G)
     float a = 0.f, d = 0.f;
     const float* pp = part + (static_cast<size_t>(b) * stat_chunks * G + g) * 2;
     for (int c = 0; c < stat_chunks; ++c) {
@@ -341,8 +339,7 @@ gn_bwd_stats_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
     sq[c] = d;
   }
   __syncthreads();
-  if (threadIdx.x < G) {
-    const int g = threadIdx.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {       // (blocks of a tiny activation can be narrower than G)
     float a = 0.f, d = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
       a += ss[c];
@@ -366,8 +363,7 @@ gn_bwd_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
   const int pl = threadIdx.x / vecs;
   const int b = blockIdx.y;
   const int cpg = C / G;
-  if (threadIdx.x < G) {
-    const int g = threadIdx.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {       // (blocks of a tiny activation can be narrower than G)
     float a = 0.f, d = 0.f;
     const float* pp = part + (static_cast<size_t>(b) * stat_chunks * G + g) * 2;
     for (int c = 0; c < stat_chunks; ++c) {

@@ -122,6 +122,25 @@ def test_training_group_norm_function_in_the_unet(cuda_device):
     assert cos >= 0.99
 
 
+@pytest.mark.parametrize("B,HW,C", [(2, 1, 64), (3, 2, 256), (1, 5, 32)])
+def test_group_norm_nhwc_blocks_narrower_than_the_group_count(cuda_device, B, HW, C):
+    """Tiny activations ([B, HW, C] form): the block has C / 8 x min(HW, 16) threads, fewer than the 32 groups."""
+    from photoverse_b200 import ops
+    g = torch.Generator().manual_seed(C + HW)
+    x = (torch.randn(B, HW, C, generator=g) + 2.0).to(cuda_device, torch.bfloat16)
+    dy = torch.randn(B, HW, C, generator=g).to(cuda_device, torch.bfloat16)
+    gamma = (1.0 + 0.3 * torch.randn(C, generator=g)).to(cuda_device)
+    beta = (0.2 * torch.randn(C, generator=g)).to(cuda_device)
+    y, stats = ops.group_norm_nhwc(x, gamma, beta, 32, 1e-5, True, None, save_stats=True)
+    dx = ops.group_norm_nhwc_bwd(x, dy, stats, gamma, beta, 32, True)
+    xr = x.float().permute(0, 2, 1).contiguous().requires_grad_(True)          # [B, C, HW] for F.group_norm
+    ref = F.silu(F.group_norm(xr, 32, gamma, beta, 1e-5))
+    ref.backward(dy.float().permute(0, 2, 1))
+    assert bool(((y.float() - ref.detach().permute(0, 2, 1)).abs() <= 1e-2 + 1e-2 * ref.detach().permute(0, 2, 1).abs()).all())
+    gref = xr.grad.permute(0, 2, 1)
+    assert ((dx.float() - gref).norm() / gref.norm().clamp_min(1e-6)).item() <= 1e-2
+
+
 def test_group_norm_nhwc_rejects_what_it_cannot_do(cuda_device):
     from photoverse_b200 import _lib, ops
     x = torch.randn(2, 320, 8, 8, device=cuda_device, dtype=torch.bfloat16)
