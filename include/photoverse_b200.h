@@ -255,7 +255,8 @@ int pv_dropout_bwd_acc(pv_dtype dt, void* dst, const void* src, const uint8_t* k
  * that follows it.  pv_layer_norm_bwd: its input gradient from dy and x
  * (frozen affine; mean / rstd are recomputed from the row).
  * pv_geglu_fwd: y[m, n] = h[m, n] * gelu(h[m, N + n]) with the exact (erf) GELU, gelu(.) rounded to bf16 before the
- * product like the two-kernel torch sequence; h: [M, 2N] with row stride ldh (elements), y: [M, N] dense; N % 8 == 0. */
+ * product like the two-kernel torch sequence; h: [M, 2N] with row stride ldh (elements), y: [M, N] dense; N % 8 == 0.
+ * pv_geglu_bwd: dh [M, 2N] dense = [dy * gelu(gate) | dy * hidden * gelu'(gate)] from h and dy [M, N] dense. */
 int64_t pv_group_norm_nhwc_ws_bytes(int64_t B, int64_t HW, int C, int groups);
 int pv_group_norm_nhwc_fwd(pv_dtype dt, const void* x, const float* add_bc, const float* gamma, const float* beta, void* y,
                            float* save_stats, void* ws, int64_t B, int64_t HW, int C, int groups, float eps, int silu,
@@ -270,6 +271,7 @@ int pv_layer_norm_fwd(pv_dtype dt, const void* x, const void* residual, void* su
 int pv_layer_norm_bwd(pv_dtype dt, const void* x, const void* dy, const float* gamma, void* dx, int64_t rows, int C, float eps,
                       void* stream);
 int pv_geglu_fwd(pv_dtype dt, const void* h, void* y, int64_t M, int N, int64_t ldh, void* stream);
+int pv_geglu_bwd(pv_dtype dt, const void* h, const void* dy, void* dh, int64_t M, int N, int64_t ldh, void* stream);
 
 #ifdef __cplusplus
 }

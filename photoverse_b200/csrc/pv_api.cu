@@ -90,6 +90,7 @@ int layer_norm_bf16(const void* x, const void* res, void* sum_out, const float* 
 int layer_norm_bwd_bf16(const void* x, const void* dy, const float* gamma, void* dx, long long rows, int C, float eps,
                         cudaStream_t stream);
 int geglu(const void* h, void* y, long long M, int N, long long ldh, cudaStream_t stream);
+int geglu_bwd(const void* h, const void* dy, void* dh, long long M, int N, long long ldh, cudaStream_t stream);
 int dropout_bwd_acc(bool bf16, void* dst, const void* src, const uint8_t* mask, float alpha, long long n,
                     cudaStream_t stream);
 
@@ -555,6 +556,12 @@ int pv_geglu_fwd(pv_dtype dt, const void* h, void* y, int64_t M, int N, int64_t 
   PV_REQUIRE(h && y, "null pointer");
   PV_REQUIRE(dt == PV_BF16, "bf16 activations only");
   return geglu(h, y, M, N, ldh, as_stream(stream));
+}
+
+int pv_geglu_bwd(pv_dtype dt, const void* h, const void* dy, void* dh, int64_t M, int N, int64_t ldh, void* stream) {
+  PV_REQUIRE(h && dy && dh, "null pointer");
+  PV_REQUIRE(dt == PV_BF16, "bf16 activations only");
+  return geglu_bwd(h, dy, dh, M, N, ldh, as_stream(stream));
 }
 
 }  // extern "C"

@@ -707,4 +707,48 @@ int geglu(const void* h, void* y, long long M, int N, long long ldh, cudaStream_
   return PV_OK;
 }
 
+// dh = [dy * gelu(g) | dy * a * gelu'(g)] for h = [a | g]:  gelu'(g) = Phi(g) + g * phi(g).
+__global__ void __launch_bounds__(256)
+geglu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dh,
+                 long long M, int N, long long ldh) {
+  const int vecs = N >> 3;
+  const long long total = M * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / vecs;
+    const int v = static_cast<int>(i - m * vecs);
+    const uint4* row = reinterpret_cast<const uint4*>(h + m * ldh);
+    float a[8], g[8], d[8];
+    bf16x8_unpack(__ldg(row + v), a);
+    bf16x8_unpack(__ldg(row + vecs + v), g);
+    bf16x8_unpack(__ldg(reinterpret_cast<const uint4*>(dy + m * N) + v), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float cdf = 0.5f * (1.f + erff(g[j] * 0.70710678118654752f));
+      const float pdf = 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
+      const float da = d[j] * (g[j] * cdf);
+      const float dg = d[j] * a[j] * fmaf(g[j], pdf, cdf);
+      a[j] = da;
+      g[j] = dg;
+    }
+    uint4* orow = reinterpret_cast<uint4*>(dh + m * 2 * N);
+    orow[v] = bf16x8_pack(a);
+    orow[vecs + v] = bf16x8_pack(g);
+  }
+}
+
+int geglu_bwd(const void* h, const void* dy, void* dh, long long M, int N, long long ldh, cudaStream_t stream) {
+  PV_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && ldh >= 2ll * N && ldh % 8 == 0, "need N %% 8 == 0 and ldh >= 2N, ldh %% 8 == 0 (M=%lld N=%d ldh=%lld)", M, N, ldh);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dh)) % 16 == 0,
+             "h / dy / dh must be 16-byte aligned");
+  const long long total = M * (N / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = 8ll * sm_count();
+  if (blocks > cap) blocks = cap;
+  geglu_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(dy),
+                                                                     static_cast<__nv_bfloat16*>(dh), M, N, ldh);
+  PV_LAUNCHED();
+  return PV_OK;
+}
+
 }  // namespace pv

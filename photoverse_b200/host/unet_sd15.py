@@ -189,6 +189,22 @@ class Attention(nn.Module):
                               attention_mask=attention_mask, **kw)
 
 
+class _GegluFn(torch.autograd.Function):
+    """Training-time GEGLU product: one launch forward, one backward; only the projection is kept."""
+
+    @staticmethod
+    def forward(ctx, h):
+        from .. import ops
+        ctx.save_for_backward(h)
+        return ops.geglu(h)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .. import ops
+        (h,) = ctx.saved_tensors
+        return ops.geglu_bwd(h, dy.contiguous())
+
+
 class GEGLU(nn.Module):
     def __init__(self, dim_in, dim_out):
         super().__init__()
@@ -196,7 +212,9 @@ class GEGLU(nn.Module):
 
     def forward(self, x):
         h = self.proj(x)
-        if _fused(self, h) and h.is_contiguous() and h.shape[-1] % 16 == 0:
+        if _enabled(self, h) and h.is_contiguous() and h.shape[-1] % 16 == 0:
+            if torch.is_grad_enabled() and h.requires_grad:
+                return _GegluFn.apply(h)
             from .. import ops
             return ops.geglu(h)
         x, gate = h.chunk(2, dim=-1)

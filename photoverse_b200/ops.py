@@ -488,3 +488,15 @@ def geglu(h: torch.Tensor) -> torch.Tensor:
     y = torch.empty(*h.shape[:-1], N, device=h.device, dtype=h.dtype)
     check(_lib.lib().pv_geglu_fwd(PV_BF16, _ptr(h), _ptr(y), M, N, 2 * N, _stream()), "pv_geglu_fwd")
     return y
+
+
+def geglu_bwd(h: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """Gradient of :func:`geglu` with respect to the ``[..., 2N]`` projection ``h`` from ``dy`` ``[..., N]`` (both contiguous bf16)."""
+    if not (h.is_cuda and h.dtype == torch.bfloat16 and h.is_contiguous() and dy.dtype == h.dtype and dy.is_contiguous()):
+        raise _lib.PhotoverseB200Error("geglu_bwd: contiguous CUDA bfloat16 h and dy required (there is no CPU path)")
+    N = h.shape[-1] // 2
+    M = h.numel() // (2 * N)
+    assert dy.shape == (*h.shape[:-1], N)
+    dh = torch.empty_like(h)
+    check(_lib.lib().pv_geglu_bwd(PV_BF16, _ptr(h), _ptr(dy), _ptr(dh), M, N, 2 * N, _stream()), "pv_geglu_bwd")
+    return dh
