@@ -18,12 +18,14 @@ import torch.nn.functional as F
 from torch import nn
 
 
-# Inference-time epilogues of the backbone as photoverse_b200 kernels (csrc/pv_backbone.cu): GroupNorm (+ SiLU) directly on
-# the channels-last activation (the stock sequence is NHWC -> NCHW copy, moments, normalise, SiLU, NCHW -> NHWC copy: 16 %
-# of a generation step's GPU time) and the GEGLU product.  Used for CUDA bf16 channels-last activations with autograd
-# off; training, fp32 parity runs and NCHW models keep the stock PyTorch ops.  ``FUSED_EPILOGUES = False`` restores the
-# stock sequence everywhere; ``UNetSD15.set_fused_epilogues(False)`` does so for one model (bench.py --stock-epilogues;
-# the oracle arm of the parity tests; tests compare the two).
+# Epilogues of the backbone as photoverse_b200 kernels (csrc/pv_backbone.cu): GroupNorm (+ SiLU) directly on the
+# channels-last activation (the stock sequence is NHWC -> NCHW copy, moments, normalise, SiLU, NCHW -> NHWC copy), LayerNorm,
+# the GEGLU product, bias / residual sums -- the glue that was half of a generation step's GPU time.  Used for CUDA bf16
+# channels-last activations: plain calls with autograd off, torch.autograd.Functions with an input-gradient kernel with
+# autograd on when the module's affine is frozen (the PhotoVerse training set never includes the backbone); fp32 parity
+# runs, NCHW models and trainable norms keep the stock PyTorch ops.  ``FUSED_EPILOGUES = False`` restores the stock
+# sequence everywhere; ``UNetSD15.set_fused_epilogues(False)`` does so for one model (bench.py --stock-epilogues; the
+# oracle arm of the parity tests; tests compare the two).
 FUSED_EPILOGUES = True
 
 
