@@ -298,3 +298,34 @@ def test_dpmpp_2m_schedule_is_exact_for_a_perfect_denoiser():
     # first-order update of diffusers at the terminal node: x_t = (sigma_t / sigma_s) x - alpha_t (exp(-h) - 1) x0 with
     # sigma_t = 0, alpha_t = 1, h = lambda_t - lambda_s = +inf  ->  0 * x + 1 * x0
     assert (0.0 / (1 - ac[20]) ** 0.5, -1.0 * (np.exp(-np.inf) - 1.0)) == (0.0, 1.0)
+
+
+def test_backbone_epilogue_helpers_keep_the_stock_ops_off_the_gpu_path():
+    """`group_norm_act` / `layer_norm` / GEGLU of the host UNet (photoverse_b200/host/unet_sd15.py) are the stock PyTorch ops
+    whenever the pv_backbone.cu kernels do not apply (CPU tensors here); the per-model switch marks exactly the norm / GEGLU
+    modules."""
+    import torch.nn.functional as F
+    from photoverse_b200.host import unet_sd15 as U
+    torch.manual_seed(0)
+    norm = torch.nn.GroupNorm(4, 16)
+    x = torch.randn(2, 16, 5, 3)
+    add = torch.randn(2, 16)
+    assert torch.equal(U.group_norm_act(norm, x, True), F.silu(norm(x)))
+    assert torch.equal(U.group_norm_act(norm, x, False), norm(x))
+    assert torch.allclose(U.group_norm_act(norm, x, True, add), F.silu(norm(x + add[:, :, None, None])))
+    ln = torch.nn.LayerNorm(16)
+    t = torch.randn(2, 7, 16)
+    assert torch.equal(U.layer_norm(ln, t), ln(t))
+    ge = U.GEGLU(16, 32)
+    h = ge.proj(t)
+    assert torch.equal(ge(t), h[..., :32] * F.gelu(h[..., 32:]))
+    unet = UNetSD15(block_out_channels=(32, 64), layers_per_block=1, heads=2, cross_attention_dim=16, sample_size=8)
+    marked = [m for m in unet.set_fused_epilogues(False).modules() if getattr(m, "_pv_fused", None) is False]
+    expect = [m for m in unet.modules() if isinstance(m, (torch.nn.GroupNorm, torch.nn.LayerNorm, U.GEGLU))]
+    assert marked and len(marked) == len(expect)
+    # a resnet block on the stock path: conv bias and the time-embedding term are added before norm2, as in diffusers
+    blk = U.ResnetBlock2D(16, 32, 8, groups=4)
+    xin, temb = torch.randn(2, 16, 4, 4), torch.randn(2, 8)
+    hh = blk.conv1(F.silu(blk.norm1(xin))) + blk.time_emb_proj(F.silu(temb))[:, :, None, None]
+    ref = blk.conv_shortcut(xin) + blk.conv2(F.silu(blk.norm2(hh)))
+    assert torch.allclose(blk(xin, temb), ref, atol=1e-6)
