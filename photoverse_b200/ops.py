@@ -410,7 +410,8 @@ def group_norm_nhwc_bwd(x: torch.Tensor, dy: torch.Tensor, stats: torch.Tensor, 
                         groups: int, silu: bool, add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Input gradient of :func:`group_norm_nhwc` (frozen affine): ``dy`` in the layout of ``x``."""
     B, HW, C = _gn_geometry(x, "group_norm_nhwc_bwd")
-    if dy.shape != x.shape or dy.dtype != x.dtype or dy.stride() != x.stride():
+    # same shape and the same (channels-last / dense) layout; strides of size-1 dimensions are free to differ
+    if dy.shape != x.shape or _gn_geometry(dy, "group_norm_nhwc_bwd") != (B, HW, C):
         raise _lib.PhotoverseB200Error("group_norm_nhwc_bwd: dy must have the shape, dtype and memory layout of x")
     assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.shape == (B, groups, 2)
     lib = _lib.lib()
